@@ -1,0 +1,179 @@
+/*
+ * b200_attn.h -- C ABI of the B200-native paged attention kernels.
+ *
+ * This is the drop-in boundary for eth-easl/Scratchpad's attention hot path:
+ * the entry points below are what a new `cuda_b200` AttentionBackend
+ * (scratchpad/nn/attention/backend.py:11-105) binds through ctypes.  Plain
+ * pointers, sizes and a raw cudaStream_t only; no torch types.  Every call
+ *   - returns 0 on success, a B200_ERR_* code or 1000+cudaError_t otherwise,
+ *   - never throws, never synchronises the host, never allocates device memory,
+ *   - launches on the stream it is given with grids that do not depend on
+ *     device-side values (capture-safe for CUDA graphs,
+ *     scratchpad/model_executor/cuda_graph_runner.py:394-423,483-510).
+ *
+ * Data layout contract (all paths relative to /root/reference):
+ *   req_to_token  int32 [rows, cols] row-major, row stride given in elements
+ *                 (scratchpad/memory/pool.py:16-22)
+ *   k_buf/v_buf   [P+1, Hkv, D] contiguous in the last two dims, token stride
+ *                 given in elements; bf16, or fp8-e4m3 stored as bytes
+ *                 (pool.py:298-317,373-390); slot 0 is the padding slot
+ *   q / o         bf16 [T, Hq, D] with last dim contiguous, token and head
+ *                 strides in elements (q may be a column slice of the fused
+ *                 qkv GEMM output, scratchpad/nn/models/llama/llama.py:149-152)
+ *   req_pool_indices, seq_lens  int32 or int64 (eager batches are int64,
+ *                 schedule_batch.py:916-924; graph buffers int32,
+ *                 cuda_graph_runner.py:194-197) -- see idx_dtype fields
+ *   page size is 1 (model_runner.py:431-432): the gather unit is one token row.
+ */
+#ifndef B200_ATTN_H_
+#define B200_ATTN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ATTN_ABI_VERSION 3
+
+/* kv_dtype */
+#define B200_KV_BF16 0
+#define B200_KV_FP8_E4M3 1
+/* idx_dtype */
+#define B200_IDX_I32 0
+#define B200_IDX_I64 1
+/* compute path (b200_attn_config.path) */
+#define B200_PATH_MMA 0  /* GQA-packed tensor-core path (mma.sync m16n8k16) */
+#define B200_PATH_SIMT 1 /* CUDA-core path for small group sizes */
+
+/* error codes (cuda errors are reported as 1000 + cudaError_t) */
+#define B200_OK 0
+#define B200_ERR_INVALID 1     /* null pointer, bad size, misaligned stride */
+#define B200_ERR_UNSUPPORTED 2 /* head_dim / group size / dtype not built */
+#define B200_ERR_WORKSPACE 3   /* workspace smaller than b200_attn_get_config says */
+#define B200_ERR_NOT_PLANNED 4 /* decode called before b200_attn_plan on this workspace */
+
+typedef void* b200_stream_t; /* cudaStream_t */
+
+/* Static launch configuration of the decode path for one model shape.
+ * Replaces TritonAttnBackend.__init__'s num_kv_splits / attn_logits sizing
+ * (scratchpad/nn/attention/triton_backend.py:32-61). */
+typedef struct b200_attn_config {
+  int32_t path;            /* B200_PATH_* */
+  int32_t tile_tokens;     /* KV tokens per pipeline stage of one CTA */
+  int32_t grid_ctas;       /* persistent grid size (x); y = hkv / heads_per_cta */
+  int32_t heads_per_cta;   /* kv heads processed by one CTA */
+  int32_t sub_splits;      /* token sub-slices per tile that keep separate softmax state */
+  int32_t stages;          /* cp.async pipeline depth */
+  int32_t smem_bytes;      /* dynamic shared memory per CTA */
+  int32_t num_sms;
+  uint64_t workspace_bytes; /* for the max_bs passed to b200_attn_get_config */
+} b200_attn_config;
+
+/* One layer's batched decode attention (replaces decode_attention_fwd as called
+ * from triton_backend.py:183-195 and the FlashInfer decode wrapper call,
+ * flashinfer_backend.py:475-482). */
+typedef struct b200_decode_params {
+  const void* q;            /* bf16 [bs, hq, d] */
+  int64_t q_stride_t, q_stride_h;
+  const void* k_buf;        /* [P+1, hkv, d]  bf16 or fp8 bytes */
+  const void* v_buf;        /* [P+1, hkv, dv] */
+  int64_t k_stride_t, v_stride_t; /* token stride in elements */
+  void* o;                  /* bf16 [bs, hq, dv] */
+  int64_t o_stride_t, o_stride_h;
+  const int32_t* req_to_token;
+  int64_t req_to_token_stride;
+  int32_t bs, hq, hkv, d, dv;
+  int32_t kv_dtype;
+  float sm_scale;
+  float logit_cap;          /* <= 0: off (radix_attention.py:18; gemma3 passes None) */
+  const float* k_scale;     /* device fp32 [hkv] or NULL (=1.0): dequant x_hat * scale */
+  const float* v_scale;
+  void* workspace;          /* planned by b200_attn_plan for this batch */
+  uint64_t workspace_bytes;
+  int32_t max_bs;           /* the max_bs the workspace was sized for */
+  int32_t force_path;       /* -1 auto, else B200_PATH_* (tests) */
+} b200_decode_params;
+
+/* One layer's extend / chunked-prefill attention over prefix-cached chunks
+ * (replaces extend_attention_fwd as called from triton_backend.py:139-154):
+ * query row t of request i attends to the pool slots req_to_token[r, :pre_i]
+ * (non-causal) and to k_new/v_new[start_i : start_i + t + 1] (causal). */
+typedef struct b200_extend_params {
+  const void* q;            /* bf16 [T, hq, d] */
+  int64_t q_stride_t, q_stride_h;
+  const void* k_new;        /* bf16 [T, hkv, d]  (model dtype, unquantised) */
+  const void* v_new;        /* bf16 [T, hkv, dv] */
+  int64_t kn_stride_t, kn_stride_h, vn_stride_t, vn_stride_h;
+  const void* k_buf;
+  const void* v_buf;
+  int64_t k_stride_t, v_stride_t;
+  void* o;                  /* bf16 [T, hq, dv] */
+  int64_t o_stride_t, o_stride_h;
+  const int32_t* req_to_token;
+  int64_t req_to_token_stride;
+  const void* req_pool_indices; /* [bs] */
+  const void* seq_lens;         /* [bs] prefix + extend */
+  int32_t idx_dtype;            /* dtype of the two above */
+  const int32_t* extend_seq_lens;  /* int32 [bs] (forward_info.py:258-263) */
+  const int32_t* extend_start_loc; /* int32 [bs] */
+  int32_t bs, hq, hkv, d, dv;
+  int32_t total_tokens;         /* T */
+  int32_t max_extend_len;       /* upper bound of extend_seq_lens (host value) */
+  int32_t kv_dtype;
+  float sm_scale;
+  float logit_cap;
+  const float* k_scale;
+  const float* v_scale;
+} b200_extend_params;
+
+int b200_attn_abi_version(void);
+/* sizeof() of the structs above as compiled (which: 0 config, 1 decode, 2 extend),
+ * so a binding can verify its own layout before the first call. */
+uint64_t b200_attn_struct_size(int which);
+const char* b200_attn_error_string(int code);
+
+/* Launch configuration + workspace size for (max_bs, shape) on the current device. */
+int b200_attn_get_config(int32_t max_bs, int32_t hq, int32_t hkv, int32_t d, int32_t dv,
+                         int32_t kv_dtype, int32_t force_path, b200_attn_config* out);
+
+/* Per-step metadata, once per forward batch (replaces init_forward_metadata's
+ * attn_logits allocation, triton_backend.py:48-68, and FlashInfer's kv_indices
+ * flatten + host-side plan, flashinfer_backend.py:623-670): normalises the index
+ * dtypes and balances KV tiles over the persistent grid, entirely on device. */
+int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs,
+                   const void* req_pool_indices, const void* seq_lens, int32_t idx_dtype,
+                   int32_t bs, int32_t hq, int32_t hkv, int32_t d, int32_t dv, int32_t kv_dtype,
+                   int32_t force_path, b200_stream_t stream);
+
+int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream);
+int b200_attn_extend(const b200_extend_params* p, b200_stream_t stream);
+
+/* KV write: k_buf[loc[t]] = quant(k[t]) (replaces MHATokenToKVPool.set_kv_buffer's
+ * two index_put_ launches + div_/cast, pool.py:392-424).  k/v are bf16
+ * [T, hkv, d] with strides in elements; loc int32/int64 [T]; for fp8 the value
+ * stored is e4m3(bf16(x / scale[h])) and k/v are NOT modified in place. */
+int b200_kv_store(void* k_buf, void* v_buf, int64_t k_stride_t, int64_t v_stride_t,
+                  const void* loc, int32_t loc_dtype, const void* k, const void* v,
+                  int64_t k_src_stride_t, int64_t k_src_stride_h, int64_t v_src_stride_t,
+                  int64_t v_src_stride_h, int32_t num_tokens, int32_t hkv, int32_t d, int32_t dv,
+                  int32_t kv_dtype, const float* k_scale, const float* v_scale, b200_stream_t stream);
+
+/* Test hook for the bit-exact gather contract: copies, with the kernels' own
+ * slot -> row address arithmetic, rows buf[req_to_token[req_pool_indices[i], t]]
+ * for t < seq_lens[i] to out + out_offsets[i] * row_bytes (rows packed). */
+int b200_debug_gather(const void* buf, int64_t stride_t_bytes, int32_t row_bytes,
+                      const int32_t* req_to_token, int64_t req_to_token_stride,
+                      const void* req_pool_indices, const void* seq_lens, int32_t idx_dtype,
+                      const int64_t* out_offsets, int32_t bs, void* out, b200_stream_t stream);
+
+/* Test hook: straightforward one-warp-per-(request, q head) fp32 decode used to
+ * cross-check the tiled kernels at sizes the CPU oracle cannot reach. */
+int b200_debug_decode_naive(const b200_decode_params* p, const void* req_pool_indices,
+                            const void* seq_lens, int32_t idx_dtype, b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_ATTN_H_ */

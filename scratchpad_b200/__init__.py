@@ -1,0 +1,22 @@
+"""scratchpad_b200 -- B200-native paged decode/extend attention for eth-easl/Scratchpad.
+
+One hot path only: the `cuda_b200` AttentionBackend and the C-ABI kernel
+library behind it.  See DESIGN.md / INTEGRATION.md.
+"""
+
+from .backend import AttentionBackend, CudaB200AttnBackend
+from .forward_info import ForwardBatch, ForwardMode, compute_extend_start_loc
+from .pool import MHATokenToKVPool, ReqToTokenPool, TokenToKVPoolAllocator
+from .radix_attention import RadixAttention
+
+__all__ = [
+    "AttentionBackend",
+    "CudaB200AttnBackend",
+    "ForwardBatch",
+    "ForwardMode",
+    "compute_extend_start_loc",
+    "MHATokenToKVPool",
+    "ReqToTokenPool",
+    "TokenToKVPoolAllocator",
+    "RadixAttention",
+]

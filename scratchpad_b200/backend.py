@@ -1,0 +1,249 @@
+"""`cuda_b200` attention backend: the drop-in for the engine's AttentionBackend.
+
+``AttentionBackend`` restates the reference ABC
+(``scratchpad/nn/attention/backend.py:11-105``: same method names, argument
+order and dispatch rule).  ``CudaB200AttnBackend`` implements it the way
+``TritonAttnBackend`` does (``scratchpad/nn/attention/triton_backend.py:17-196``:
+KV write first, then attend; output ``[T, Hq*Dv]`` in q's dtype) but over the
+hand-written sm_100a kernels behind the C ABI in ``include/b200_attn.h``.
+
+Selection site in the engine (one ``elif`` in
+``scratchpad/model_executor/model_runner.py:453-470``)::
+
+    elif self.server_args.attention_backend == "cuda_b200":
+        from scratchpad_b200 import CudaB200AttnBackend
+        self.attn_backend = CudaB200AttnBackend(self)
+
+No Triton, no dispatch to another backend, no CPU fallback: every forward call
+goes through ``libb200attn.so`` and raises if it is missing.
+"""
+
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+class AttentionBackend(ABC):
+    """The base class of attention backends (reference backend.py:11-105)."""
+
+    @abstractmethod
+    def init_forward_metadata(self, forward_batch):
+        raise NotImplementedError()
+
+    def init_cuda_graph_state(self, max_bs: int):
+        raise NotImplementedError()
+
+    def init_forward_metadata_capture_cuda_graph(self, bs, num_tokens, req_pool_indices, seq_lens,
+                                                 encoder_lens, forward_mode, spec_info):
+        raise NotImplementedError()
+
+    def init_forward_metadata_replay_cuda_graph(self, bs, req_pool_indices, seq_lens, seq_lens_sum,
+                                                encoder_lens, forward_mode, spec_info, seq_lens_cpu=None):
+        raise NotImplementedError()
+
+    def get_cuda_graph_seq_len_fill_value(self):
+        raise NotImplementedError()
+
+    def forward(self, q, k, v, layer, forward_batch, save_kv_cache: bool = True):
+        if forward_batch.forward_mode.is_decode():
+            return self.forward_decode(q, k, v, layer, forward_batch, save_kv_cache=save_kv_cache)
+        else:
+            return self.forward_extend(q, k, v, layer, forward_batch, save_kv_cache=save_kv_cache)
+
+    def forward_decode(self, q, k, v, layer, forward_batch, save_kv_cache: bool = True):
+        raise NotImplementedError()
+
+    def forward_extend(self, q, k, v, layer, forward_batch, save_kv_cache: bool = True):
+        raise NotImplementedError()
+
+
+def _idx_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.int64:
+        return _lib.IDX_I64
+    if t.dtype == torch.int32:
+        return _lib.IDX_I32
+    raise TypeError(f"index tensors must be int32 or int64, got {t.dtype}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class CudaB200AttnBackend(AttentionBackend):
+    def __init__(self, model_runner, force_path: int = _lib.PATH_AUTO):
+        super().__init__()
+        self.lib = _lib.load()  # raises when the extension is not built
+        cfg = model_runner.model_config
+        tp = model_runner.tp_size
+        if getattr(model_runner.server_args, "enable_dp_attention", False):
+            self.num_head = cfg.num_attention_heads
+        else:
+            self.num_head = cfg.num_attention_heads // tp
+        self.num_kv_head = cfg.get_num_kv_heads(tp)
+        self.head_dim = cfg.head_dim
+        self.device = model_runner.device
+        self.req_to_token_pool = model_runner.req_to_token_pool
+        self.token_to_kv_pool = model_runner.token_to_kv_pool
+        self.v_head_dim = self.token_to_kv_pool.get_value_buffer(0).shape[-1]
+        self.kv_dtype = self.token_to_kv_pool.kv_dtype_code()
+        self.force_path = force_path
+        if getattr(model_runner, "sliding_window_size", None) not in (None, -1):
+            raise NotImplementedError("cuda_b200 backend: sliding-window attention is not supported")
+        if model_runner.dtype != torch.bfloat16:
+            raise NotImplementedError("cuda_b200 backend: model dtype must be bfloat16")
+        self.cuda_graph_max_seq_len = cfg.context_len
+        self.max_bs = 0
+        self.workspace = None
+        self.config = None
+        self.forward_metadata = None
+        self._planned_for = None
+        self._ensure_workspace(int(getattr(self.req_to_token_pool, "size", 256)))
+
+    # ---- workspace / launch configuration ---------------------------------
+    def _ensure_workspace(self, max_bs: int) -> None:
+        if self.workspace is not None and max_bs <= self.max_bs:
+            return
+        cfg = _lib.AttnConfig()
+        rc = self.lib.b200_attn_get_config(max_bs, self.num_head, self.num_kv_head, self.head_dim,
+                                           self.v_head_dim, self.kv_dtype, self.force_path, cfg)
+        _lib.check(rc, "b200_attn_get_config")
+        self.config = cfg
+        self.max_bs = max_bs
+        self.workspace = torch.empty(int(cfg.workspace_bytes), dtype=torch.uint8, device=self.device)
+
+    def _plan(self, bs: int, req_pool_indices: torch.Tensor, seq_lens: torch.Tensor) -> None:
+        if req_pool_indices.dtype != seq_lens.dtype:
+            seq_lens = seq_lens.to(req_pool_indices.dtype)
+        rc = self.lib.b200_attn_plan(
+            self.workspace.data_ptr(), self.workspace.numel(), self.max_bs,
+            req_pool_indices.data_ptr(), seq_lens.data_ptr(), _idx_code(req_pool_indices), bs,
+            self.num_head, self.num_kv_head, self.head_dim, self.v_head_dim, self.kv_dtype,
+            self.force_path, torch.cuda.current_stream().cuda_stream,
+        )
+        _lib.check(rc, "b200_attn_plan")
+        self._planned_for = bs
+
+    # ---- AttentionBackend surface -------------------------------------------
+    def init_forward_metadata(self, forward_batch):
+        """Once per forward batch: balance the batch's KV tiles over the persistent
+        grid on device.  No kv_indices flatten, no host sync (cf.
+        triton_backend.py:48-68, flashinfer_backend.py:623-670)."""
+        if forward_batch.forward_mode.is_decode():
+            bs = forward_batch.batch_size
+            self._ensure_workspace(bs)
+            self._plan(bs, forward_batch.req_pool_indices, forward_batch.seq_lens)
+            self.forward_metadata = ("decode", bs)
+        else:
+            lens = forward_batch.extend_seq_lens_cpu
+            if lens is None:  # the reference's Triton backend syncs here too (triton_backend.py:66)
+                lens = forward_batch.extend_seq_lens.tolist()
+            self.forward_metadata = ("extend", max(lens) if len(lens) else 0)
+
+    def init_cuda_graph_state(self, max_bs: int):
+        self._ensure_workspace(max_bs)
+
+    def init_forward_metadata_capture_cuda_graph(self, bs, num_tokens, req_pool_indices, seq_lens,
+                                                 encoder_lens, forward_mode, spec_info):
+        assert encoder_lens is None, "Not supported"
+        assert forward_mode.is_decode(), "Not supported"
+        assert spec_info is None, "Not supported"
+        assert bs <= self.max_bs, "init_cuda_graph_state(max_bs) must cover every captured batch size"
+        self._plan(bs, req_pool_indices[:bs], seq_lens[:bs])
+        self.forward_metadata = ("decode", bs)
+
+    def init_forward_metadata_replay_cuda_graph(self, bs, req_pool_indices, seq_lens, seq_lens_sum,
+                                                encoder_lens, forward_mode, spec_info, seq_lens_cpu=None):
+        # same static workspace the captured kernels read; refreshed in place, no sync
+        self._plan(bs, req_pool_indices[:bs], seq_lens[:bs])
+        self.forward_metadata = ("decode", bs)
+
+    def get_cuda_graph_seq_len_fill_value(self):
+        return 1
+
+    def _scales(self, layer):
+        return self.token_to_kv_pool.get_kv_scales(layer.layer_id)
+
+    def _logit_cap(self, layer) -> float:
+        cap = getattr(layer, "logit_cap", 0.0)
+        return float(cap) if cap else 0.0
+
+    def _check_layer(self, layer) -> None:
+        if getattr(layer, "is_cross_attention", False):
+            raise NotImplementedError("cuda_b200 backend: cross attention is not supported")
+        if getattr(layer, "sliding_window_size", -1) not in (None, -1):
+            raise NotImplementedError("cuda_b200 backend: sliding-window attention is not supported")
+
+    def forward_decode(self, q, k, v, layer, forward_batch, save_kv_cache: bool = True):
+        self._check_layer(layer)
+        hq, d, dv = layer.tp_q_head_num, layer.qk_head_dim, layer.v_head_dim
+        q = q.reshape(-1, hq * d)
+        if q.stride(1) != 1:
+            q = q.contiguous()
+        o = q.new_empty((q.shape[0], hq * dv))
+        pool = forward_batch.token_to_kv_pool
+        if save_kv_cache:
+            pool.set_kv_buffer(layer, forward_batch.out_cache_loc, k, v)
+        kind, bs = self.forward_metadata
+        assert kind == "decode" and bs == q.shape[0], "init_forward_metadata was not called for this batch"
+        kb, vb = pool.k_buffer[layer.layer_id], pool.v_buffer[layer.layer_id]
+        r2t = forward_batch.req_to_token_pool.req_to_token
+        ks, vs = self._scales(layer)
+        p = _lib.DecodeParams(
+            q=q.data_ptr(), q_stride_t=q.stride(0), q_stride_h=d,
+            k_buf=kb.data_ptr(), v_buf=vb.data_ptr(), k_stride_t=kb.stride(0), v_stride_t=vb.stride(0),
+            o=o.data_ptr(), o_stride_t=o.stride(0), o_stride_h=dv,
+            req_to_token=r2t.data_ptr(), req_to_token_stride=r2t.stride(0),
+            bs=bs, hq=hq, hkv=layer.tp_k_head_num, d=d, dv=dv, kv_dtype=self.kv_dtype,
+            sm_scale=float(layer.scaling), logit_cap=self._logit_cap(layer),
+            k_scale=_ptr(ks), v_scale=_ptr(vs),
+            workspace=self.workspace.data_ptr(), workspace_bytes=self.workspace.numel(),
+            max_bs=self.max_bs, force_path=self.force_path,
+        )
+        rc = self.lib.b200_attn_decode(p, torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "b200_attn_decode")
+        return o
+
+    def forward_extend(self, q, k, v, layer, forward_batch, save_kv_cache: bool = True):
+        self._check_layer(layer)
+        hq, hkv, d, dv = layer.tp_q_head_num, layer.tp_k_head_num, layer.qk_head_dim, layer.v_head_dim
+        q3 = q.view(-1, hq, d) if q.dim() == 2 else q
+        if q3.stride(2) != 1:
+            q3 = q3.contiguous()
+        o = q.new_empty((q3.shape[0], hq * dv))
+        pool = forward_batch.token_to_kv_pool
+        if save_kv_cache:
+            pool.set_kv_buffer(layer, forward_batch.out_cache_loc, k, v)
+        kind, max_extend_len = self.forward_metadata
+        assert kind == "extend", "init_forward_metadata was not called for this batch"
+        k3, v3 = k.view(-1, hkv, d), v.view(-1, hkv, dv)
+        if k3.stride(2) != 1 or v3.stride(2) != 1:
+            k3, v3 = k3.contiguous(), v3.contiguous()
+        kb, vb = pool.k_buffer[layer.layer_id], pool.v_buffer[layer.layer_id]
+        r2t = forward_batch.req_to_token_pool.req_to_token
+        ks, vs = self._scales(layer)
+        rpi, sl = forward_batch.req_pool_indices, forward_batch.seq_lens
+        if rpi.dtype != sl.dtype:
+            sl = sl.to(rpi.dtype)
+        p = _lib.ExtendParams(
+            q=q3.data_ptr(), q_stride_t=q3.stride(0), q_stride_h=q3.stride(1),
+            k_new=k3.data_ptr(), v_new=v3.data_ptr(),
+            kn_stride_t=k3.stride(0), kn_stride_h=k3.stride(1), vn_stride_t=v3.stride(0), vn_stride_h=v3.stride(1),
+            k_buf=kb.data_ptr(), v_buf=vb.data_ptr(), k_stride_t=kb.stride(0), v_stride_t=vb.stride(0),
+            o=o.data_ptr(), o_stride_t=o.stride(0), o_stride_h=dv,
+            req_to_token=r2t.data_ptr(), req_to_token_stride=r2t.stride(0),
+            req_pool_indices=rpi.data_ptr(), seq_lens=sl.data_ptr(), idx_dtype=_idx_code(rpi),
+            extend_seq_lens=forward_batch.extend_seq_lens.data_ptr(),
+            extend_start_loc=forward_batch.extend_start_loc.data_ptr(),
+            bs=forward_batch.batch_size, hq=hq, hkv=hkv, d=d, dv=dv,
+            total_tokens=q3.shape[0], max_extend_len=int(max_extend_len), kv_dtype=self.kv_dtype,
+            sm_scale=float(layer.scaling), logit_cap=self._logit_cap(layer),
+            k_scale=_ptr(ks), v_scale=_ptr(vs),
+        )
+        rc = self.lib.b200_attn_extend(p, torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "b200_attn_extend")
+        return o

@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# Builds libb200attn.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
+set -euo pipefail
+here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+root="$(cd "$here/../.." && pwd)"
+out="$here/libb200attn.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a
+       -Xcompiler -fPIC --expt-relaxed-constexpr
+       -I"$root/include" -I"$here" ${B200_PTXAS_V:+-Xptxas -v})
+objs=()
+pids=()
+for f in decode store extend; do
+  "$NVCC" "${FLAGS[@]}" -c "$here/$f.cu" -o "$here/$f.o" &
+  pids+=($!)
+  objs+=("$here/$f.o")
+done
+for p in "${pids[@]}"; do wait "$p"; done
+"$NVCC" -shared -o "$out" "${objs[@]}" -gencode arch=compute_100a,code=sm_100a
+echo "built $out"

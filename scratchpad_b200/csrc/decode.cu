@@ -1,0 +1,815 @@
+// Paged decode attention for B200 (sm_100a): plan -> persistent split-KV
+// flash-decoding kernel -> log-sum-exp merge.
+//
+// Replaces, behind the same AttentionBackend surface, what the reference does
+// with triteia/Triton `decode_attention_fwd` (scratchpad/nn/attention/
+// triton_backend.py:183-195; math as in triton_attn/decode_attention.py:251-434)
+// and FlashInfer's BatchDecodeWithPagedKVCacheWrapper
+// (flashinfer_backend.py:475-482, 623-670).  Not a port of either: see DESIGN.md.
+//
+// Work decomposition
+//   * A KV "tile" is TN consecutive token positions of one request, all
+//     HPC kv heads of the CTA's head group: for every token one contiguous
+//     HPC*D*elt-byte span of the pool row (page size is 1, so a token row is
+//     the gather unit; keeping all local heads of a row in one CTA makes the
+//     DRAM access 512 B - 1 KiB contiguous instead of 128 B).
+//   * plan_kernel numbers all tiles of the batch 0..T-1 (prefix sum of
+//     ceil(seq_len/TN)); CTA c of the persistent grid owns the contiguous tile
+//     range [c*tpc, (c+1)*tpc).  Work is balanced to one tile regardless of
+//     how sequence lengths are distributed, with no host sync and a grid that
+//     does not depend on device data (CUDA-graph safe).
+//   * A CTA streams its tiles through a 3-stage cp.async (LDGSTS, 16 B per
+//     thread, XOR-swizzled) pipeline that keeps running across request
+//     boundaries; softmax state is flushed as one partial (O/l, lse) per
+//     (CTA, request, token sub-slice) into slot (c + b) of the workspace.
+//   * merge_kernel combines the <= few partials of each (request, q head).
+//
+// Tensor-core mapping (GQA query-group packing, "swapped" orientation):
+//   S^T[16 tokens x 8 q-heads] = K[16 x D] . Q^T[D x 8]      (A = K via ldmatrix)
+//   O^T[D x 8 q-heads]        += V^T[D x 16] . P^T[16 x 8]    (A = V via ldmatrix.trans)
+// so the g q-heads that share a kv head fill the N=8 side of m16n8k16 (g=8:
+// dense, g=4: half) and the softmax reductions run over tokens with warp
+// shuffles.  P^T moves from accumulator to B-operand layout with movmatrix.
+// fp8-e4m3 KV is dequantised in registers (cvt.rn.f16x2.e4m3x2) and multiplied
+// in f16; per-head scales are folded into the softmax scale (K) and the
+// epilogue (V).
+
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kStages = 3;
+constexpr int kPlanMagic = 0x62323030;  // "b200"
+constexpr int kHdrInts = 16;
+
+struct WsLayout {
+  size_t tile_off, seq_len, req_idx, part_lse, part_o, total;
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static WsLayout ws_layout(int max_bs, int grid, int nsub, int hq, int dv) {
+  WsLayout L;
+  size_t off = kHdrInts * sizeof(int);
+  L.tile_off = off;
+  off = align_up(off + (size_t)(max_bs + 1) * sizeof(int), 16);
+  L.seq_len = off;
+  off = align_up(off + (size_t)max_bs * sizeof(int), 16);
+  L.req_idx = off;
+  off = align_up(off + (size_t)max_bs * sizeof(int), 256);
+  size_t nparts = (size_t)(grid + max_bs) * nsub * hq;
+  L.part_lse = off;
+  off = align_up(off + nparts * sizeof(float), 256);
+  L.part_o = off;
+  off = align_up(off + nparts * dv * sizeof(float), 256);
+  L.total = off;
+  return L;
+}
+
+// ---------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* __restrict__ tile_off,
+                                                    int* __restrict__ seq32, int* __restrict__ req32,
+                                                    const void* __restrict__ req, const void* __restrict__ seq,
+                                                    int idx64, int bs, int tile_tokens, int grid) {
+  __shared__ int warp_sums[32];
+  __shared__ int s_running;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_running = 0;
+  __syncthreads();
+  for (int base = 0; base < bs; base += 1024) {
+    const int i = base + tid;
+    int n = 0;
+    if (i < bs) {
+      int64_t s = load_idx(seq, idx64, i);
+      if (s < 0) s = 0;
+      seq32[i] = static_cast<int>(s);
+      req32[i] = static_cast<int>(load_idx(req, idx64, i));
+      n = static_cast<int>((s + tile_tokens - 1) / tile_tokens);
+    }
+    int x = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_sums[lane] = w;  // inclusive
+    }
+    __syncthreads();
+    const int running = s_running;
+    const int incl = running + x + (warp > 0 ? warp_sums[warp - 1] : 0);
+    if (i < bs) tile_off[i] = incl - n;
+    __syncthreads();
+    if (tid == 1023) s_running = incl;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int total = s_running;
+    tile_off[bs] = total;
+    int tpc = (total + grid - 1) / grid;
+    if (tpc < 1) tpc = 1;
+    hdr[0] = total;
+    hdr[1] = tpc;
+    hdr[2] = (total + tpc - 1) / tpc;
+    hdr[3] = bs;
+    hdr[4] = tile_tokens;
+    hdr[5] = grid;
+    hdr[6] = kPlanMagic;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// decode kernel
+// ---------------------------------------------------------------------------
+struct DecodeArgs {
+  const __nv_bfloat16* q;
+  int64_t q_st, q_sh;
+  const uint8_t* kbuf;
+  const uint8_t* vbuf;
+  int64_t k_st_bytes, v_st_bytes;
+  const int32_t* r2t;
+  int64_t r2t_stride;
+  const int* hdr;
+  const int* tile_off;
+  const int* seq_len;
+  const int* req_idx;
+  float* part_o;
+  float* part_lse;
+  int hq, hkv, g;
+  float sm_scale, logit_cap;
+  const float* k_scale;
+  const float* v_scale;
+};
+
+struct Cursor {
+  int gt, gt_end;  // global tile index / end of this CTA's range
+  int b;           // request (batch row) the tile belongs to
+  int b_begin, b_end;  // tile range of request b
+  int seq_len;
+  const int32_t* row;  // req_to_token row of request b
+};
+
+__device__ __forceinline__ void cursor_load_req(Cursor& c, const DecodeArgs& a) {
+  c.b_begin = __ldg(a.tile_off + c.b);
+  c.b_end = __ldg(a.tile_off + c.b + 1);
+  c.seq_len = __ldg(a.seq_len + c.b);
+  c.row = a.r2t + static_cast<int64_t>(__ldg(a.req_idx + c.b)) * a.r2t_stride;
+}
+__device__ __forceinline__ bool cursor_valid(const Cursor& c) { return c.gt < c.gt_end; }
+__device__ __forceinline__ void cursor_advance(Cursor& c, const DecodeArgs& a) {
+  c.gt++;
+  if (c.gt < c.gt_end && c.gt >= c.b_end) {
+    do {
+      c.b++;
+    } while (c.gt >= __ldg(a.tile_off + c.b + 1));
+    cursor_load_req(c, a);
+  }
+}
+
+template <int D_, bool FP8_, int HPC_, int NW_>
+struct DecodeCfg {
+  static constexpr int D = D_;
+  static constexpr bool FP8 = FP8_;
+  static constexpr int HPC = HPC_;     // kv heads per CTA
+  static constexpr int NW = NW_;       // warps per CTA
+  static constexpr int NT = NW * 32;
+  static constexpr int ELT = FP8 ? 1 : 2;
+  static constexpr int SEG = D * ELT;  // bytes of one (token, head) K or V row
+  static constexpr int CPS = SEG / 16; // 16-byte chunks per segment
+  static constexpr int NSUB = NW / HPC;  // token sub-slices (one warp each per head)
+  static constexpr int TN = 16 * NSUB;   // tokens per tile
+  static constexpr int CPT = HPC * CPS;  // chunks per token (contiguous in the pool row)
+  static constexpr int PASSES = TN * CPT / NT;
+  static constexpr int TOK_PER_PASS = NT / CPT;
+  static constexpr int TILE_BYTES = HPC * TN * SEG;  // K (or V) bytes per stage
+  static constexpr int STAGE_BYTES = 2 * TILE_BYTES;
+  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES;
+  static constexpr int NSLOT = (TN + 31) / 32;  // slot-id registers per lane
+  static constexpr int KC = D / 16;             // MMA k-chunks (bf16) == 16-elt chunks (fp8)
+  static constexpr int MT = D / 16;             // PV m-tiles
+  static_assert(NW % HPC == 0, "warps must tile the heads");
+  static_assert(NT % CPT == 0 && PASSES >= 1, "copy mapping");
+  static_assert(CPS == 4 || CPS == 8 || CPS == 16, "segment size");
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int D = C::D, HPC = C::HPC, TN = C::TN, SEG = C::SEG, CPS = C::CPS, CPT = C::CPT;
+  constexpr bool FP8 = C::FP8;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cta = blockIdx.x;
+  const int h0 = blockIdx.y * HPC;  // first kv head of this CTA
+
+  const int total = __ldg(a.hdr + 0), tpc = __ldg(a.hdr + 1), bs = __ldg(a.hdr + 3);
+  const int gt_begin = cta * tpc;
+  const int gt_end = min(gt_begin + tpc, total);
+  if (gt_begin >= gt_end) return;
+
+  // request containing the first tile: last b with tile_off[b] <= gt_begin
+  int lo = 0, hi = bs;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(a.tile_off + mid) <= gt_begin) lo = mid;
+    else hi = mid;
+  }
+  Cursor pc;  // producer cursor
+  pc.gt = gt_begin;
+  pc.gt_end = gt_end;
+  pc.b = lo;
+  cursor_load_req(pc, a);
+  Cursor cc = pc;  // consumer cursor
+
+  // ---- producer: per-thread constants of the copy mapping -------------------
+  const int p_tok = tid / CPT;  // token of pass 0; pass i adds i * TOK_PER_PASS
+  const int p_wc = tid % CPT;   // 16-byte chunk inside the token's HPC*SEG span
+  const int p_head = p_wc / CPS, p_col = p_wc % CPS;
+  const uint32_t smem_base = smem_u32(smem);
+  const int64_t k_head_off = static_cast<int64_t>(h0) * SEG + p_wc * 16;  // byte offset inside a pool row
+
+  int slot_reg[C::NSLOT];
+  auto prefetch_slots = [&](const Cursor& c) {
+    const int tok0 = (c.gt - c.b_begin) * TN;
+#pragma unroll
+    for (int j = 0; j < C::NSLOT; ++j) {
+      const int t = tok0 + j * 32 + lane;
+      slot_reg[j] = (j * 32 + lane < TN && t < c.seq_len) ? __ldg(c.row + t) : 0;
+    }
+  };
+  auto issue_tile = [&](const Cursor& c, int stage) {
+    const int tok0 = (c.gt - c.b_begin) * TN;
+    const uint32_t sk = smem_base + stage * C::STAGE_BYTES;
+    const uint32_t sv = sk + C::TILE_BYTES;
+#pragma unroll
+    for (int i = 0; i < C::PASSES; ++i) {
+      const int tok = p_tok + i * C::TOK_PER_PASS;
+      int sreg = slot_reg[0];
+#pragma unroll
+      for (int j = 1; j < C::NSLOT; ++j)
+        if ((tok >> 5) == j) sreg = slot_reg[j];  // predicated select keeps slot_reg in registers
+      const int slot = __shfl_sync(0xffffffffu, sreg, tok & 31);
+      const int nbytes = (tok0 + tok < c.seq_len) ? 16 : 0;
+      const uint32_t doff = ((p_head * TN + tok) * CPS + swz_chunk<CPS>(p_col, tok)) * 16;
+      cp_async16(sk + doff, kv_row_ptr(a.kbuf, slot, a.k_st_bytes) + k_head_off, nbytes);
+      cp_async16(sv + doff, kv_row_ptr(a.vbuf, slot, a.v_st_bytes) + k_head_off, nbytes);
+    }
+  };
+
+  // ---- consumer: warp -> (kv head, token sub-slice) ---------------------------
+  const int w_head = warp % HPC;
+  const int w_sub = warp / HPC;
+  const int kvh = h0 + w_head;
+  const int gid = lane >> 2, cid = lane & 3;  // mma "groupID" / "threadID_in_group"
+  const int G = a.g;
+  const float ks = a.k_scale ? __ldg(a.k_scale + kvh) : 1.0f;
+  const float vs = a.v_scale ? __ldg(a.v_scale + kvh) : 1.0f;
+  const float cap = a.logit_cap;
+  const float sc_raw = a.sm_scale * ks;           // logits = s * sc_raw
+  const float sc_log2 = sc_raw * kLog2e;          // exp2 domain
+
+  uint32_t qf[C::KC][2];
+  float m[2], l[2];
+  float o[C::MT][4];
+  auto reset_state = [&]() {
+    m[0] = m[1] = -INFINITY;
+    l[0] = l[1] = 0.f;
+#pragma unroll
+    for (int i = 0; i < C::MT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  };
+  // B fragments of Q^T: lane holds q-head n = gid (of this kv head's group)
+  auto load_q = [&](int b) {
+    const bool live = gid < G;
+    const __nv_bfloat16* qp = a.q + static_cast<int64_t>(b) * a.q_st + static_cast<int64_t>(kvh * G + (live ? gid : 0)) * a.q_sh;
+#pragma unroll
+    for (int kc = 0; kc < C::KC; ++kc) {
+      if constexpr (!FP8) {
+        // slots (2c,2c+1) <-> d = 16kc+2c+{0,1};  (2c+8,2c+9) <-> d+8
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(qp + kc * 16 + cid * 2);
+        qf[kc][0] = live ? __ldg(p) : 0u;
+        qf[kc][1] = live ? __ldg(p + 4) : 0u;
+      } else {
+        // 16-element chunk kc: slots (2c,2c+1) <-> d = 16kc+4c+{0,1}; (2c+8,2c+9) <-> d = 16kc+4c+{2,3}
+        const uint2 raw = live ? __ldg(reinterpret_cast<const uint2*>(qp + kc * 16 + cid * 4)) : make_uint2(0u, 0u);
+        const __nv_bfloat162 x01 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+        const __nv_bfloat162 x23 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+        qf[kc][0] = pack_f16x2(__low2float(x01), __high2float(x01));
+        qf[kc][1] = pack_f16x2(__low2float(x23), __high2float(x23));
+      }
+    }
+  };
+
+  auto compute_tile = [&](int stage, int nvalid) {
+    // nvalid: valid tokens in this warp's 16-token slice (>= 1)
+    const uint32_t sk = smem_base + stage * C::STAGE_BYTES + (w_head * TN + w_sub * 16) * SEG;
+    const uint32_t sv = sk + C::TILE_BYTES;
+    const int lrow = lane & 15;  // ldmatrix row (token) this lane addresses
+    const int lhi = lane >> 4;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (!FP8) {
+#pragma unroll
+      for (int kc = 0; kc < C::KC; ++kc) {
+        uint32_t af[4];
+        ldmatrix_x4(af, sk + lrow * SEG + swz_chunk<CPS>(2 * kc + lhi, lrow) * 16);
+        mma_16816<false>(s, af, qf[kc][0], qf[kc][1]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < C::KC / 2; ++j) {
+        uint32_t r[4];  // r0:(tok 0-7, chunk 2j) r1:(tok 8-15, 2j) r2:(tok 0-7, 2j+1) r3:(tok 8-15, 2j+1)
+        ldmatrix_x4(r, sk + lrow * SEG + swz_chunk<CPS>(2 * j + lhi, lrow) * 16);
+        uint32_t af[4];
+        af[0] = e4m3x2_to_f16x2(static_cast<uint16_t>(r[0] & 0xffffu));
+        af[1] = e4m3x2_to_f16x2(static_cast<uint16_t>(r[1] & 0xffffu));
+        af[2] = e4m3x2_to_f16x2(static_cast<uint16_t>(r[0] >> 16));
+        af[3] = e4m3x2_to_f16x2(static_cast<uint16_t>(r[1] >> 16));
+        mma_16816<true>(s, af, qf[2 * j][0], qf[2 * j][1]);
+        af[0] = e4m3x2_to_f16x2(static_cast<uint16_t>(r[2] & 0xffffu));
+        af[1] = e4m3x2_to_f16x2(static_cast<uint16_t>(r[3] & 0xffffu));
+        af[2] = e4m3x2_to_f16x2(static_cast<uint16_t>(r[2] >> 16));
+        af[3] = e4m3x2_to_f16x2(static_cast<uint16_t>(r[3] >> 16));
+        mma_16816<true>(s, af, qf[2 * j + 1][0], qf[2 * j + 1][1]);
+      }
+    }
+    // s[0],s[1]: token gid, heads 2cid,2cid+1; s[2],s[3]: token gid+8
+    if (cap > 0.f) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[i] = softcap(s[i] * sc_raw, cap) * kLog2e;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[i] *= sc_log2;
+    }
+    if (gid >= nvalid) s[0] = s[1] = -INFINITY;
+    if (gid + 8 >= nvalid) s[2] = s[3] = -INFINITY;
+    float mx0 = fmaxf(s[0], s[2]), mx1 = fmaxf(s[1], s[3]);
+#pragma unroll
+    for (int x = 4; x < 32; x <<= 1) {
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, x));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, x));
+    }
+    const float mn0 = fmaxf(m[0], mx0), mn1 = fmaxf(m[1], mx1);  // finite: nvalid >= 1
+    const float al0 = ex2(m[0] - mn0), al1 = ex2(m[1] - mn1);
+    m[0] = mn0;
+    m[1] = mn1;
+    const float p0 = ex2(s[0] - mn0), p1 = ex2(s[1] - mn1), p2 = ex2(s[2] - mn0), p3 = ex2(s[3] - mn1);
+    l[0] = l[0] * al0 + p0 + p2;  // per-lane partial sums, reduced over lanes at flush
+    l[1] = l[1] * al1 + p1 + p3;
+#pragma unroll
+    for (int i = 0; i < C::MT; ++i) {
+      o[i][0] *= al0;
+      o[i][1] *= al1;
+      o[i][2] *= al0;
+      o[i][3] *= al1;
+    }
+    // P^T (tokens x heads, accumulator layout) -> B fragment (k = tokens, n = heads)
+    const uint32_t pb0 = movmatrix_trans(pack2<FP8>(p0, p1));
+    const uint32_t pb1 = movmatrix_trans(pack2<FP8>(p2, p3));
+    const int vtok = (lane & 7) + ((lane >> 4) << 3);  // ldmatrix.trans row (token)
+    const int vhalf = (lane >> 3) & 1;
+    if constexpr (!FP8) {
+#pragma unroll
+      for (int mt = 0; mt < C::MT; ++mt) {
+        uint32_t af[4];  // V^T tile: rows d = 16mt + {gid, gid+8}, cols tokens
+        ldmatrix_x4_trans(af, sv + vtok * SEG + swz_chunk<CPS>(2 * mt + vhalf, vtok) * 16);
+        mma_16816<false>(o[mt], af, pb0, pb1);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < C::MT / 2; ++j) {
+        uint32_t r[4];  // transposed: lane holds bytes {V[2c][d0],V[2c][d0+1],V[2c+1][d0],V[2c+1][d0+1]}, d0 = 16ch+2gid
+        ldmatrix_x4_trans(r, sv + lrow * SEG + swz_chunk<CPS>(2 * j + lhi, lrow) * 16);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t t0 = prmt(r[2 * h], 0u, 0x3120u);      // tokens 0-7 : {d0:(2c,2c+1) | d0+1:(2c,2c+1)}
+          const uint32_t t1 = prmt(r[2 * h + 1], 0u, 0x3120u);  // tokens 8-15
+          uint32_t af[4];
+          af[0] = e4m3x2_to_f16x2(static_cast<uint16_t>(t0 & 0xffffu));  // row gid   <-> d0,   k 2c..
+          af[1] = e4m3x2_to_f16x2(static_cast<uint16_t>(t0 >> 16));      // row gid+8 <-> d0+1
+          af[2] = e4m3x2_to_f16x2(static_cast<uint16_t>(t1 & 0xffffu));  // k 2c+8..
+          af[3] = e4m3x2_to_f16x2(static_cast<uint16_t>(t1 >> 16));
+          mma_16816<true>(o[2 * j + h], af, pb0, pb1);
+        }
+      }
+    }
+  };
+
+  // one partial per (cta, request, sub-slice): slot = cta + b is unique along the
+  // monotone staircase of (cta, request) pairs
+  auto flush = [&](int b) {
+    float l0 = l[0], l1 = l[1];
+#pragma unroll
+    for (int x = 4; x < 32; x <<= 1) {
+      l0 += __shfl_xor_sync(0xffffffffu, l0, x);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, x);
+    }
+    const float inv0 = l0 > 0.f ? vs / l0 : 0.f, inv1 = l1 > 0.f ? vs / l1 : 0.f;
+    const int64_t slot = static_cast<int64_t>(cta + b) * C::NSUB + w_sub;
+    const int n0 = 2 * cid, n1 = 2 * cid + 1;  // q-head index inside the group
+    const int64_t pi0 = slot * a.hq + kvh * G + n0;
+    const int64_t pi1 = pi0 + 1;
+    if (gid == 0) {
+      if (n0 < G) a.part_lse[pi0] = l0 > 0.f ? m[0] + lg2(l0) : -INFINITY;
+      if (n1 < G) a.part_lse[pi1] = l1 > 0.f ? m[1] + lg2(l1) : -INFINITY;
+    }
+#pragma unroll
+    for (int mt = 0; mt < C::MT; ++mt) {
+      const int da = FP8 ? 16 * mt + 2 * gid : 16 * mt + gid;
+      const int db = FP8 ? da + 1 : da + 8;
+      if (n0 < G) {
+        a.part_o[pi0 * D + da] = o[mt][0] * inv0;
+        a.part_o[pi0 * D + db] = o[mt][2] * inv0;
+      }
+      if (n1 < G) {
+        a.part_o[pi1 * D + da] = o[mt][1] * inv1;
+        a.part_o[pi1 * D + db] = o[mt][3] * inv1;
+      }
+    }
+  };
+
+  // ---- pipeline ---------------------------------------------------------------
+  prefetch_slots(pc);
+#pragma unroll
+  for (int s = 0; s < kStages - 1; ++s) {
+    if (cursor_valid(pc)) {
+      issue_tile(pc, s);
+      cursor_advance(pc, a);
+      if (cursor_valid(pc)) prefetch_slots(pc);
+    }
+    cp_async_commit();
+  }
+  reset_state();
+  load_q(cc.b);
+
+  int stage = 0;
+  while (cursor_valid(cc)) {
+    cp_async_wait<kStages - 2>();
+    __syncthreads();
+    {
+      int pstage = stage + kStages - 1;
+      if (pstage >= kStages) pstage -= kStages;
+      if (cursor_valid(pc)) {
+        issue_tile(pc, pstage);
+        cursor_advance(pc, a);
+        if (cursor_valid(pc)) prefetch_slots(pc);
+      }
+      cp_async_commit();
+    }
+    const int tok0 = (cc.gt - cc.b_begin) * TN + w_sub * 16;
+    const int nvalid = min(16, cc.seq_len - tok0);
+    if (nvalid > 0) compute_tile(stage, nvalid);
+
+    const int b_cur = cc.b;
+    const bool req_done = (cc.gt + 1 >= cc.gt_end) || (cc.gt + 1 >= cc.b_end);
+    cursor_advance(cc, a);
+    if (req_done) {
+      flush(b_cur);
+      if (cursor_valid(cc)) {
+        reset_state();
+        load_q(cc.b);
+      }
+    }
+    stage = stage + 1 == kStages ? 0 : stage + 1;
+  }
+  cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------
+// merge: o[b, h, :] = sum_i w_i * O_i,  w_i = 2^(lse_i - max) / sum_j 2^(lse_j - max)
+// ---------------------------------------------------------------------------
+template <int DV>
+__global__ void __launch_bounds__(DV) merge_kernel(const int* __restrict__ hdr, const int* __restrict__ tile_off,
+                                                   const float* __restrict__ part_o,
+                                                   const float* __restrict__ part_lse, __nv_bfloat16* __restrict__ o,
+                                                   int64_t o_st, int64_t o_sh, int hq, int nsub) {
+  const int b = blockIdx.x, h = blockIdx.y, d = threadIdx.x;
+  const int tpc = __ldg(hdr + 1);
+  const int t0 = __ldg(tile_off + b), t1 = __ldg(tile_off + b + 1);
+  __nv_bfloat16* op = o + static_cast<int64_t>(b) * o_st + static_cast<int64_t>(h) * o_sh + d;
+  if (t1 <= t0) {  // seq_len == 0
+    *op = __float2bfloat16(0.f);
+    return;
+  }
+  const int c0 = t0 / tpc, c1 = (t1 - 1) / tpc;
+  const int64_t first = static_cast<int64_t>(c0 + b) * nsub;
+  const int n = (c1 - c0 + 1) * nsub;  // consecutive slots (c + b) * nsub + sub
+  float mx = -INFINITY;
+  for (int i = 0; i < n; ++i) mx = fmaxf(mx, __ldg(part_lse + (first + i) * hq + h));
+  float acc = 0.f, den = 0.f;
+  if (mx > -INFINITY) {
+    for (int i = 0; i < n; ++i) {
+      const int64_t pi = (first + i) * hq + h;
+      const float w = ex2(__ldg(part_lse + pi) - mx);
+      den += w;
+      acc += w * __ldg(part_o + pi * DV + d);
+    }
+  }
+  *op = __float2bfloat16(den > 0.f ? acc / den : 0.f);
+}
+
+// ---------------------------------------------------------------------------
+// debug / test hooks
+// ---------------------------------------------------------------------------
+__global__ void gather_kernel(const uint8_t* __restrict__ buf, int64_t stride_t_bytes, int row_bytes,
+                              const int32_t* __restrict__ r2t, int64_t r2t_stride, const void* __restrict__ req,
+                              const void* __restrict__ seq, int idx64, const int64_t* __restrict__ out_off,
+                              uint8_t* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int64_t n = load_idx(seq, idx64, b);
+  const int32_t* row = r2t + load_idx(req, idx64, b) * r2t_stride;
+  for (int64_t t = blockIdx.x; t < n; t += gridDim.x) {
+    const uint8_t* src = kv_row_ptr(buf, __ldg(row + t), stride_t_bytes);
+    uint8_t* dst = out + (out_off[b] + t) * row_bytes;
+    for (int i = threadIdx.x * 16; i < row_bytes; i += blockDim.x * 16)
+      *reinterpret_cast<uint4*>(dst + i) = __ldg(reinterpret_cast<const uint4*>(src + i));
+  }
+}
+
+// one warp per (request, q head); fp32 everywhere; the obviously-correct twin
+__global__ void __launch_bounds__(32) naive_decode_kernel(const b200_decode_params p, const void* __restrict__ req,
+                                                          const void* __restrict__ seq, int idx64) {
+  const int b = blockIdx.x, h = blockIdx.y, lane = threadIdx.x;
+  const int g = p.hq / p.hkv, kvh = h / g;
+  const int64_t n = load_idx(seq, idx64, b);
+  const int32_t* row = p.req_to_token + load_idx(req, idx64, b) * p.req_to_token_stride;
+  const bool fp8 = p.kv_dtype == B200_KV_FP8_E4M3;
+  const int elt = fp8 ? 1 : 2;
+  const float ks = p.k_scale ? p.k_scale[kvh] : 1.f, vs = p.v_scale ? p.v_scale[kvh] : 1.f;
+  const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(p.q) + b * p.q_stride_t + h * p.q_stride_h;
+  float acc[8];  // dv <= 256
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  for (int64_t t = 0; t < n; ++t) {
+    const int32_t slot = row[t];
+    const uint8_t* kr = kv_row_ptr(static_cast<const uint8_t*>(p.k_buf), slot, p.k_stride_t * elt) + kvh * p.d * elt;
+    const uint8_t* vr = kv_row_ptr(static_cast<const uint8_t*>(p.v_buf), slot, p.v_stride_t * elt) + kvh * p.dv * elt;
+    float s = 0.f;
+    for (int i = lane; i < p.d; i += 32) {
+      const float kx = fp8 ? e4m3_to_float(kr[i]) * ks : bf16_bits_to_float(reinterpret_cast<const uint16_t*>(kr)[i]);
+      s += __bfloat162float(q[i]) * kx;
+    }
+#pragma unroll
+    for (int x = 16; x > 0; x >>= 1) s += __shfl_xor_sync(0xffffffffu, s, x);
+    s *= p.sm_scale;
+    if (p.logit_cap > 0.f) s = p.logit_cap * tanhf(s / p.logit_cap);
+    const float mn = fmaxf(m, s);
+    const float al = expf(m - mn), pr = expf(s - mn);
+    l = l * al + pr;
+    for (int i = lane, j = 0; i < p.dv; i += 32, ++j) {
+      const float vx = fp8 ? e4m3_to_float(vr[i]) * vs : bf16_bits_to_float(reinterpret_cast<const uint16_t*>(vr)[i]);
+      acc[j] = acc[j] * al + pr * vx;
+    }
+    m = mn;
+  }
+  __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.o) + b * p.o_stride_t + h * p.o_stride_h;
+  for (int i = lane, j = 0; i < p.dv; i += 32, ++j) op[i] = __float2bfloat16(l > 0.f ? acc[j] / l : 0.f);
+}
+
+// ---------------------------------------------------------------------------
+// host side: config selection + launchers
+// ---------------------------------------------------------------------------
+struct KernelChoice {
+  int d, fp8, hpc, nw;
+};
+
+static int pick_hpc(int hkv, int nw) {
+  int hpc = 1;
+  while (hpc * 2 <= nw && hkv % (hpc * 2) == 0) hpc *= 2;
+  return hpc;
+}
+
+static int choose(int hq, int hkv, int d, int dv, int kv_dtype, KernelChoice* kc) {
+  if (hq <= 0 || hkv <= 0 || hq % hkv != 0) return B200_ERR_INVALID;
+  if (d != dv) return B200_ERR_UNSUPPORTED;            // MLA-style split dims: out of scope
+  if (d != 64 && d != 128) return B200_ERR_UNSUPPORTED;
+  if (kv_dtype != B200_KV_BF16 && kv_dtype != B200_KV_FP8_E4M3) return B200_ERR_UNSUPPORTED;
+  if (hq / hkv > 8) return B200_ERR_UNSUPPORTED;       // one N=8 mma tile of q heads per kv head
+  kc->d = d;
+  kc->fp8 = kv_dtype == B200_KV_FP8_E4M3;
+  kc->nw = (d == 128 && !kc->fp8) ? 4 : 8;  // keep a stage at 32 KiB
+  kc->hpc = pick_hpc(hkv, kc->nw);
+  return B200_OK;
+}
+
+struct DeviceInfo {
+  int num_sms = 0;
+};
+static int device_info(DeviceInfo* di) {
+  static int cached_dev = -1;
+  static DeviceInfo cached;
+  int dev = 0;
+  B200_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != cached_dev) {
+    B200_CUDA_TRY(cudaDeviceGetAttribute(&cached.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    cached_dev = dev;
+  }
+  *di = cached;
+  return B200_OK;
+}
+
+template <class C>
+static int launch_decode_t(const DecodeArgs& a, int grid_x, int grid_y, cudaStream_t st, bool query_only,
+                           int* occ_out) {
+  auto kern = decode_mma_kernel<C>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  if (query_only) {
+    B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, C::NT, C::SMEM_BYTES));
+    return B200_OK;
+  }
+  kern<<<dim3(grid_x, grid_y), C::NT, C::SMEM_BYTES, st>>>(a);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+template <int D, bool FP8>
+static int dispatch_hpc(const KernelChoice& kc, const DecodeArgs& a, int gx, int gy, cudaStream_t st, bool q, int* occ) {
+  constexpr int NW = (D == 128 && !FP8) ? 4 : 8;
+  switch (kc.hpc) {
+    case 1: return launch_decode_t<DecodeCfg<D, FP8, 1, NW>>(a, gx, gy, st, q, occ);
+    case 2: return launch_decode_t<DecodeCfg<D, FP8, 2, NW>>(a, gx, gy, st, q, occ);
+    case 4: return launch_decode_t<DecodeCfg<D, FP8, 4, NW>>(a, gx, gy, st, q, occ);
+    case 8:
+      if constexpr (NW >= 8) return launch_decode_t<DecodeCfg<D, FP8, 8, NW>>(a, gx, gy, st, q, occ);
+  }
+  return B200_ERR_UNSUPPORTED;
+}
+
+static int dispatch(const KernelChoice& kc, const DecodeArgs& a, int gx, int gy, cudaStream_t st, bool q, int* occ) {
+  if (kc.d == 64) return kc.fp8 ? dispatch_hpc<64, true>(kc, a, gx, gy, st, q, occ) : dispatch_hpc<64, false>(kc, a, gx, gy, st, q, occ);
+  return kc.fp8 ? dispatch_hpc<128, true>(kc, a, gx, gy, st, q, occ) : dispatch_hpc<128, false>(kc, a, gx, gy, st, q, occ);
+}
+
+static int get_config(int max_bs, int hq, int hkv, int d, int dv, int kv_dtype, int force_path, b200_attn_config* out) {
+  (void)force_path;
+  if (!out || max_bs <= 0) return B200_ERR_INVALID;
+  KernelChoice kc;
+  int rc = choose(hq, hkv, d, dv, kv_dtype, &kc);
+  if (rc) return rc;
+  DeviceInfo di;
+  rc = device_info(&di);
+  if (rc) return rc;
+  int occ = 0;
+  DecodeArgs dummy{};
+  rc = dispatch(kc, dummy, 0, 0, nullptr, true, &occ);
+  if (rc) return rc;
+  if (occ < 1) return B200_ERR_UNSUPPORTED;
+  if (occ > 2) occ = 2;
+  const int elt = kc.fp8 ? 1 : 2;
+  out->path = B200_PATH_MMA;
+  out->heads_per_cta = kc.hpc;
+  out->sub_splits = kc.nw / kc.hpc;
+  out->tile_tokens = 16 * out->sub_splits;
+  const int gy = hkv / kc.hpc;
+  // persistent grid: every resident CTA slot of the machine, shared by the head groups
+  int gx = di.num_sms * occ / gy;
+  if (gx < 1) gx = 1;
+  out->grid_ctas = gx;
+  out->stages = kStages;
+  out->smem_bytes = kStages * 2 * kc.hpc * out->tile_tokens * d * elt;
+  out->num_sms = di.num_sms;
+  out->workspace_bytes = ws_layout(max_bs, gx, out->sub_splits, hq, dv).total;
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_attn_abi_version(void) { return B200_ATTN_ABI_VERSION; }
+
+uint64_t b200_attn_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(b200_attn_config);
+    case 1: return sizeof(b200_decode_params);
+    case 2: return sizeof(b200_extend_params);
+    default: return 0;
+  }
+}
+
+const char* b200_attn_error_string(int code) {
+  switch (code) {
+    case B200_OK: return "ok";
+    case B200_ERR_INVALID: return "invalid argument (null pointer, bad size or misaligned stride)";
+    case B200_ERR_UNSUPPORTED: return "unsupported configuration (head_dim must be 64 or 128 with d == dv, group size <= 8, kv dtype bf16 or fp8-e4m3)";
+    case B200_ERR_WORKSPACE: return "workspace too small for this configuration";
+    case B200_ERR_NOT_PLANNED: return "workspace has not been planned (call b200_attn_plan first)";
+    default:
+      if (code >= 1000) return cudaGetErrorString(static_cast<cudaError_t>(code - 1000));
+      return "unknown error";
+  }
+}
+
+int b200_attn_get_config(int32_t max_bs, int32_t hq, int32_t hkv, int32_t d, int32_t dv, int32_t kv_dtype,
+                         int32_t force_path, b200_attn_config* out) {
+  return get_config(max_bs, hq, hkv, d, dv, kv_dtype, force_path, out);
+}
+
+int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs, const void* req_pool_indices,
+                   const void* seq_lens, int32_t idx_dtype, int32_t bs, int32_t hq, int32_t hkv, int32_t d, int32_t dv,
+                   int32_t kv_dtype, int32_t force_path, b200_stream_t stream) {
+  if (!workspace || !req_pool_indices || !seq_lens || bs <= 0 || bs > max_bs) return B200_ERR_INVALID;
+  b200_attn_config cfg;
+  int rc = get_config(max_bs, hq, hkv, d, dv, kv_dtype, force_path, &cfg);
+  if (rc) return rc;
+  if (workspace_bytes < cfg.workspace_bytes) return B200_ERR_WORKSPACE;
+  const WsLayout L = ws_layout(max_bs, cfg.grid_ctas, cfg.sub_splits, hq, dv);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  plan_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<int*>(ws), reinterpret_cast<int*>(ws + L.tile_off), reinterpret_cast<int*>(ws + L.seq_len),
+      reinterpret_cast<int*>(ws + L.req_idx), req_pool_indices, seq_lens, idx_dtype == B200_IDX_I64, bs,
+      cfg.tile_tokens, cfg.grid_ctas);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
+  if (!p || !p->q || !p->k_buf || !p->v_buf || !p->o || !p->req_to_token || !p->workspace) return B200_ERR_INVALID;
+  if (p->bs <= 0 || p->bs > p->max_bs) return B200_ERR_INVALID;
+  KernelChoice kc;
+  int rc = choose(p->hq, p->hkv, p->d, p->dv, p->kv_dtype, &kc);
+  if (rc) return rc;
+  const int elt = kc.fp8 ? 1 : 2;
+  // 16-byte vector access on pool rows, 8-byte on q
+  if ((p->k_stride_t * elt) % 16 || (p->v_stride_t * elt) % 16 || p->q_stride_t % 4 || p->q_stride_h % 4 ||
+      (reinterpret_cast<uintptr_t>(p->k_buf) & 15) || (reinterpret_cast<uintptr_t>(p->v_buf) & 15) ||
+      (reinterpret_cast<uintptr_t>(p->q) & 7))
+    return B200_ERR_INVALID;
+  b200_attn_config cfg;
+  rc = get_config(p->max_bs, p->hq, p->hkv, p->d, p->dv, p->kv_dtype, p->force_path, &cfg);
+  if (rc) return rc;
+  if (p->workspace_bytes < cfg.workspace_bytes) return B200_ERR_WORKSPACE;
+  const WsLayout L = ws_layout(p->max_bs, cfg.grid_ctas, cfg.sub_splits, p->hq, p->dv);
+  uint8_t* ws = static_cast<uint8_t*>(p->workspace);
+  DecodeArgs a;
+  a.q = static_cast<const __nv_bfloat16*>(p->q);
+  a.q_st = p->q_stride_t;
+  a.q_sh = p->q_stride_h;
+  a.kbuf = static_cast<const uint8_t*>(p->k_buf);
+  a.vbuf = static_cast<const uint8_t*>(p->v_buf);
+  a.k_st_bytes = p->k_stride_t * elt;
+  a.v_st_bytes = p->v_stride_t * elt;
+  a.r2t = p->req_to_token;
+  a.r2t_stride = p->req_to_token_stride;
+  a.hdr = reinterpret_cast<const int*>(ws);
+  a.tile_off = reinterpret_cast<const int*>(ws + L.tile_off);
+  a.seq_len = reinterpret_cast<const int*>(ws + L.seq_len);
+  a.req_idx = reinterpret_cast<const int*>(ws + L.req_idx);
+  a.part_lse = reinterpret_cast<float*>(ws + L.part_lse);
+  a.part_o = reinterpret_cast<float*>(ws + L.part_o);
+  a.hq = p->hq;
+  a.hkv = p->hkv;
+  a.g = p->hq / p->hkv;
+  a.sm_scale = p->sm_scale;
+  a.logit_cap = p->logit_cap;
+  a.k_scale = p->k_scale;
+  a.v_scale = p->v_scale;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = dispatch(kc, a, cfg.grid_ctas, p->hkv / kc.hpc, st, false, nullptr);
+  if (rc) return rc;
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p->o);
+  if (p->dv == 64)
+    merge_kernel<64><<<dim3(p->bs, p->hq), 64, 0, st>>>(a.hdr, a.tile_off, a.part_o, a.part_lse, o, p->o_stride_t, p->o_stride_h, p->hq, cfg.sub_splits);
+  else
+    merge_kernel<128><<<dim3(p->bs, p->hq), 128, 0, st>>>(a.hdr, a.tile_off, a.part_o, a.part_lse, o, p->o_stride_t, p->o_stride_h, p->hq, cfg.sub_splits);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_debug_gather(const void* buf, int64_t stride_t_bytes, int32_t row_bytes, const int32_t* req_to_token,
+                      int64_t req_to_token_stride, const void* req_pool_indices, const void* seq_lens,
+                      int32_t idx_dtype, const int64_t* out_offsets, int32_t bs, void* out, b200_stream_t stream) {
+  if (!buf || !req_to_token || !req_pool_indices || !seq_lens || !out_offsets || !out || bs <= 0) return B200_ERR_INVALID;
+  if (row_bytes % 16 || stride_t_bytes % 16) return B200_ERR_INVALID;
+  gather_kernel<<<dim3(64, bs), 64, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(buf), stride_t_bytes, row_bytes, req_to_token, req_to_token_stride, req_pool_indices,
+      seq_lens, idx_dtype == B200_IDX_I64, out_offsets, static_cast<uint8_t*>(out));
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_debug_decode_naive(const b200_decode_params* p, const void* req_pool_indices, const void* seq_lens,
+                            int32_t idx_dtype, b200_stream_t stream) {
+  if (!p || !req_pool_indices || !seq_lens || p->bs <= 0 || p->dv > 256) return B200_ERR_INVALID;
+  naive_decode_kernel<<<dim3(p->bs, p->hq), 32, 0, static_cast<cudaStream_t>(stream)>>>(*p, req_pool_indices, seq_lens,
+                                                                                        idx_dtype == B200_IDX_I64);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+"""Paged KV pool types with the layout the reference engine uses, plus the
+fp8-e4m3 scale metadata the new backend needs.
+
+Mirrors ``scratchpad/memory/pool.py`` (reference): ``ReqToTokenPool`` (:13-72),
+``TokenToKVPoolAllocator`` (:189-255, page size 1, slot 0 reserved for padded
+tokens) and ``MHATokenToKVPool`` (:258-424, per-layer ``[size+1, Hkv, D]``
+buffers, fp8 stored as uint8).  What changes for the cuda_b200 backend
+(BASELINE.json north_star, "KV pool layout/scale metadata"):
+
+* ``kv_cache_dtype`` may be ``torch.float8_e4m3fn``; the pool then carries
+  per-layer, per-kv-head fp32 dequantisation scales (``k_scale``/``v_scale``
+  ``[layer_num, Hkv]`` on the device, default 1.0) which the kernels read
+  directly -- per-tensor scaling is the special case of equal entries;
+* ``set_kv_buffer`` is one fused CUDA launch (``b200_kv_store``) instead of
+  two ``index_put_`` plus ``div_``/cast, and does not modify the caller's k/v.
+
+Only CUDA tensors are accepted by ``set_kv_buffer``: the product path has no
+CPU fallback.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Tuple, Union
+
+import torch
+
+from . import _lib
+
+FP8_DTYPES = (torch.float8_e4m3fn,)
+
+
+class ReqToTokenPool:
+    """Request row -> KV slot ids (``int32 [size, max_context_len]``)."""
+
+    def __init__(self, size: int, max_context_len: int, device: str, use_records: bool = False):
+        self.size = size
+        self.max_context_len = max_context_len
+        self.device = device
+        self.req_to_token = torch.zeros((size, max_context_len), dtype=torch.int32, device=device)
+        self.free_slots = list(range(size))
+        self.write_records = []
+        self.use_records = use_records
+
+    def write(self, indices, values):
+        self.req_to_token[indices] = values
+        if self.use_records:
+            self.write_records.append((indices, values))
+
+    def available_size(self):
+        return len(self.free_slots)
+
+    def alloc(self, need_size: int) -> Optional[List[int]]:
+        if need_size > len(self.free_slots):
+            return None
+        select_index = self.free_slots[:need_size]
+        self.free_slots = self.free_slots[need_size:]
+        return select_index
+
+    def free(self, free_index: Union[int, List[int]]):
+        if isinstance(free_index, int):
+            self.free_slots.append(free_index)
+        else:
+            self.free_slots.extend(free_index)
+
+    def clear(self):
+        self.free_slots = list(range(self.size))
+        self.write_records = []
+
+
+class TokenToKVPoolAllocator:
+    """Free list of int64 KV slot ids; slot 0 is the dummy slot for padded tokens."""
+
+    def __init__(self, size: int, dtype: torch.dtype, device: str, kvcache: "MHATokenToKVPool"):
+        self.size = size
+        self.dtype = dtype
+        self.device = device
+        self.page_size = 1
+        self._kvcache = kvcache
+        self.clear()
+
+    def available_size(self):
+        return len(self.free_slots)
+
+    def get_kvcache(self):
+        return self._kvcache
+
+    def alloc(self, need_size: int):
+        if need_size > len(self.free_slots):
+            return None
+        select_index = self.free_slots[:need_size]
+        self.free_slots = self.free_slots[need_size:]
+        return select_index
+
+    def free(self, free_index: torch.Tensor):
+        if free_index.numel() == 0:
+            return
+        self.free_slots = torch.cat((self.free_slots, free_index))
+
+    def clear(self):
+        self.free_slots = torch.arange(1, self.size + 1, dtype=torch.int64, device=self.device)
+
+
+class MHATokenToKVPool:
+    def __init__(
+        self,
+        size: int,
+        page_size: int,
+        dtype: torch.dtype,
+        head_num: int,
+        head_dim: int,
+        layer_num: int,
+        device: str,
+        enable_memory_saver: bool = False,
+        v_head_dim: Optional[int] = None,
+    ):
+        if page_size != 1:
+            raise NotImplementedError("page_size > 1 is not supported (model_runner.py:431-432)")
+        self.size = size
+        self.page_size = page_size
+        self.dtype = dtype
+        self.device = device
+        self.store_dtype = torch.uint8 if dtype in FP8_DTYPES + (torch.float8_e5m2,) else dtype
+        self.head_num = head_num
+        self.head_dim = head_dim
+        self.v_head_dim = v_head_dim or head_dim
+        self.layer_num = layer_num
+        # [size + page_size, head_num, head_dim] per layer; slot 0 = padded tokens
+        self.k_buffer = [
+            torch.zeros((size + page_size, head_num, head_dim), dtype=self.store_dtype, device=device)
+            for _ in range(layer_num)
+        ]
+        self.v_buffer = [
+            torch.zeros((size + page_size, head_num, self.v_head_dim), dtype=self.store_dtype, device=device)
+            for _ in range(layer_num)
+        ]
+        # fp8 metadata: x ~= x_hat * scale[layer, head]
+        self.k_scale = self.v_scale = None
+        if dtype in FP8_DTYPES:
+            self.k_scale = torch.ones((layer_num, head_num), dtype=torch.float32, device=device)
+            self.v_scale = torch.ones((layer_num, head_num), dtype=torch.float32, device=device)
+        self.capture_mode = False
+
+    # ---- scale metadata ---------------------------------------------------
+    def set_kv_scales(self, layer_id: int, k_scale, v_scale) -> None:
+        """``k_scale``/``v_scale``: python float (per-tensor) or ``[Hkv]`` tensor (per-head)."""
+        if self.k_scale is None:
+            raise ValueError("kv scales only exist for an fp8 pool")
+        for dst, s in ((self.k_scale, k_scale), (self.v_scale, v_scale)):
+            if isinstance(s, torch.Tensor):
+                dst[layer_id].copy_(s.to(torch.float32).reshape(-1).expand(self.head_num))
+            else:
+                dst[layer_id].fill_(float(s))
+
+    def get_kv_scales(self, layer_id: int) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        if self.k_scale is None:
+            return None, None
+        return self.k_scale[layer_id], self.v_scale[layer_id]
+
+    # ---- buffers ------------------------------------------------------------
+    def get_key_buffer(self, layer_id: int):
+        if self.store_dtype != self.dtype:
+            return self.k_buffer[layer_id].view(self.dtype)
+        return self.k_buffer[layer_id]
+
+    def get_value_buffer(self, layer_id: int):
+        if self.store_dtype != self.dtype:
+            return self.v_buffer[layer_id].view(self.dtype)
+        return self.v_buffer[layer_id]
+
+    def get_kv_buffer(self, layer_id: int):
+        return self.get_key_buffer(layer_id), self.get_value_buffer(layer_id)
+
+    def get_kv_size_bytes(self):
+        k = sum(b.numel() * b.element_size() for b in self.k_buffer)
+        v = sum(b.numel() * b.element_size() for b in self.v_buffer)
+        return k, v
+
+    def kv_dtype_code(self) -> int:
+        if self.dtype == torch.bfloat16:
+            return _lib.KV_BF16
+        if self.dtype == torch.float8_e4m3fn:
+            return _lib.KV_FP8_E4M3
+        raise NotImplementedError(f"kv cache dtype {self.dtype} is not supported by the cuda_b200 backend")
+
+    def set_kv_buffer(self, layer, loc: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor,
+                      k_scale=None, v_scale=None) -> None:
+        """``k_buffer[layer][loc] = quant(cache_k)`` (pool.py:392-424) as one CUDA launch.
+
+        ``k_scale``/``v_scale`` override the pool's stored scales when given
+        (floats, the reference's calling convention)."""
+        layer_id = layer.layer_id
+        if not cache_k.is_cuda:
+            raise RuntimeError("MHATokenToKVPool.set_kv_buffer needs CUDA tensors (no CPU fallback)")
+        if cache_k.dtype != torch.bfloat16:
+            raise NotImplementedError("the cuda_b200 backend stores from bf16 activations")
+        if k_scale is not None or v_scale is not None:
+            self.set_kv_scales(layer_id, 1.0 if k_scale is None else k_scale, 1.0 if v_scale is None else v_scale)
+        ks, vs = self.get_kv_scales(layer_id)
+        kb, vb = self.k_buffer[layer_id], self.v_buffer[layer_id]
+        cache_k = cache_k.view(-1, self.head_num, self.head_dim)
+        cache_v = cache_v.view(-1, self.head_num, self.v_head_dim)
+        if cache_k.stride(2) != 1 or cache_v.stride(2) != 1:
+            cache_k, cache_v = cache_k.contiguous(), cache_v.contiguous()
+        loc_code = {torch.int64: _lib.IDX_I64, torch.int32: _lib.IDX_I32}[loc.dtype]
+        lib = _lib.load()
+        rc = lib.b200_kv_store(
+            kb.data_ptr(), vb.data_ptr(), kb.stride(0), vb.stride(0),
+            loc.data_ptr(), loc_code, cache_k.data_ptr(), cache_v.data_ptr(),
+            cache_k.stride(0), cache_k.stride(1), cache_v.stride(0), cache_v.stride(1),
+            cache_k.shape[0], self.head_num, self.head_dim, self.v_head_dim, self.kv_dtype_code(),
+            ks.data_ptr() if ks is not None else None, vs.data_ptr() if vs is not None else None,
+            torch.cuda.current_stream().cuda_stream,
+        )
+        _lib.check(rc, "b200_kv_store")

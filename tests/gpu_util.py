@@ -1,0 +1,90 @@
+"""Helpers for the -m gpu parity tests: run a CPU-defined case through the
+cuda_b200 backend (Python surface -> ctypes -> C ABI -> sm_100a kernels)."""
+import torch
+
+from scratchpad_b200 import CudaB200AttnBackend, ForwardBatch, ForwardMode, compute_extend_start_loc
+from scratchpad_b200 import synth
+
+BF16_ABS, BF16_REL = 2e-2, 1e-2   # BASELINE.json north_star tolerance, bf16 KV
+FP8_ABS, FP8_REL = 5e-2, 5e-2     # fp8-e4m3 KV
+
+
+def rel_err(got, ref):
+    return ((got.float() - ref.float()).norm() / ref.float().norm().clamp_min(1e-12)).item()
+
+
+def assert_close(got, ref, abs_tol, rel_tol, what=""):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    mx = (got - ref).abs().max().item()
+    rl = rel_err(got, ref)
+    assert mx <= abs_tol and rl <= rel_tol, f"{what}: max-abs {mx:.4g} (tol {abs_tol}), rel {rl:.4g} (tol {rel_tol})"
+    return mx, rl
+
+
+def make_runner_from_case(k_buf, v_buf, r2t, kv_dtype, k_scale=None, v_scale=None, tp_hq=None):
+    """Pools on the GPU holding exactly the CPU case's bytes."""
+    p1, hkv, d = k_buf.shape
+    runner = synth.make_model_runner(tp_hq, hkv, d, tp_size=1, layer_num=1, pool_tokens=p1 - 1,
+                                     max_reqs=r2t.shape[0] - 1, context_len=r2t.shape[1] - 4, kv_dtype=kv_dtype)
+    pool = runner.token_to_kv_pool
+    pool.k_buffer[0].copy_(k_buf.view(pool.store_dtype))
+    pool.v_buffer[0].copy_(v_buf.view(pool.store_dtype))
+    runner.req_to_token_pool.req_to_token.copy_(r2t)
+    if k_scale is not None:
+        pool.set_kv_scales(0, k_scale, v_scale)
+    return runner
+
+
+def run_decode_case(q, k_buf, v_buf, r2t, rpi, sl, sm_scale, logit_cap=0.0, kv_dtype=torch.bfloat16,
+                    k_scale=None, v_scale=None, idx_dtype=torch.int64, q_slice_of_qkv=False, force_path=-1):
+    b, hq, d = q.shape
+    runner = make_runner_from_case(k_buf, v_buf, r2t, kv_dtype, k_scale, v_scale, tp_hq=hq)
+    backend = CudaB200AttnBackend(runner, force_path=force_path)
+    layer = synth.make_layer(runner, 0, logit_cap)
+    layer.scaling = sm_scale
+    fb = ForwardBatch(forward_mode=ForwardMode.DECODE, batch_size=b,
+                      req_pool_indices=rpi.to(idx_dtype).cuda(), seq_lens=sl.to(idx_dtype).cuda(),
+                      out_cache_loc=torch.zeros(b, dtype=torch.int64, device="cuda"), seq_lens_sum=int(sl.sum()),
+                      req_to_token_pool=runner.req_to_token_pool, token_to_kv_pool=runner.token_to_kv_pool,
+                      attn_backend=backend)
+    hkv = k_buf.shape[1]
+    if q_slice_of_qkv:  # q as a column slice of the fused qkv GEMM output (llama.py:149-152)
+        qkv = torch.zeros((b, (hq + 2 * hkv) * d), dtype=torch.bfloat16, device="cuda")
+        qkv[:, : hq * d] = q.reshape(b, hq * d).cuda()
+        qd = qkv[:, : hq * d]
+    else:
+        qd = q.reshape(b, hq * d).cuda()
+    backend.init_forward_metadata(fb)
+    o = layer(qd, None, None, fb, save_kv_cache=False)
+    torch.cuda.synchronize()
+    return o.view(b, hq, -1).cpu(), backend, runner, fb, layer
+
+
+def random_decode_case(hq, hkv, d, seq_lens, seed, kv_dtype=torch.bfloat16, shared_prefix=0, per_head=True,
+                       extra_rows=3, mode="random"):
+    """CPU tensors for one decode case (bf16-valued; fp8 pools quantised with amax/448 scales)."""
+    gen = torch.Generator().manual_seed(seed)
+    need = shared_prefix + sum(n - shared_prefix if shared_prefix and n >= shared_prefix else n for n in seq_lens)
+    pool = need + 17
+    b = len(seq_lens)
+    r2t = torch.zeros((b + extra_rows, max(max(seq_lens), 1) + 4), dtype=torch.int32)
+    rpi = synth.build_page_table(r2t, seq_lens, pool, gen, mode, shared_prefix)
+    kf = torch.randn((pool + 1, hkv, d), generator=gen).to(torch.bfloat16)
+    vf = torch.randn((pool + 1, hkv, d), generator=gen).to(torch.bfloat16)
+    q = torch.randn((b, hq, d), generator=gen).to(torch.bfloat16)
+    ks = vs = None
+    if kv_dtype != torch.bfloat16:
+        from oracle import attn_oracle as O
+        if per_head:
+            ks = kf.float().abs().amax(dim=(0, 2)) / 448.0
+            vs = vf.float().abs().amax(dim=(0, 2)) / 448.0
+        else:
+            ks = (kf.float().abs().amax() / 448.0).expand(hkv).clone()
+            vs = (vf.float().abs().amax() / 448.0).expand(hkv).clone()
+        kf = O.quantize_kv_ref(kf, kv_dtype, ks)
+        vf = O.quantize_kv_ref(vf, kv_dtype, vs)
+    sl = torch.tensor(seq_lens, dtype=torch.int64)
+    return dict(q=q, k_buf=kf, v_buf=vf, req_to_token=r2t, req_pool_indices=rpi, seq_lens=sl,
+                sm_scale=d ** -0.5, k_scale=ks, v_scale=vs, kv_dtype=kv_dtype)

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define B200_ATTN_ABI_VERSION 3
+#define B200_ATTN_ABI_VERSION 4
 
 /* kv_dtype */
 #define B200_KV_BF16 0
@@ -94,6 +94,8 @@ typedef struct b200_decode_params {
   uint64_t workspace_bytes;
   int32_t max_bs;           /* the max_bs the workspace was sized for */
   int32_t force_path;       /* -1 auto, else B200_PATH_* (tests) */
+  void* ev_kernel_begin;    /* optional cudaEvent_t pair recorded on `stream` around the */
+  void* ev_kernel_end;      /* split-KV kernel alone (bench.py roofline timing); NULL = off */
 } b200_decode_params;
 
 /* One layer's extend / chunked-prefill attention over prefix-cached chunks

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libb200attn.so")
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 KV_BF16, KV_FP8_E4M3 = 0, 1
 IDX_I32, IDX_I64 = 0, 1
@@ -64,6 +64,7 @@ class DecodeParams(C.Structure):
         ("k_scale", C.c_void_p), ("v_scale", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
         ("max_bs", C.c_int32), ("force_path", C.c_int32),
+        ("ev_kernel_begin", C.c_void_p), ("ev_kernel_end", C.c_void_p),
     ]
 
 

@@ -102,6 +102,8 @@ class CudaB200AttnBackend(AttentionBackend):
         self.config = None
         self.forward_metadata = None
         self._planned_for = None
+        # bench.py only: (begin, end) raw cudaEvent_t handles recorded around the split-KV kernel
+        self.profile_events = None
         self._ensure_workspace(int(getattr(self.req_to_token_pool, "size", 256)))
 
     # ---- workspace / launch configuration ---------------------------------
@@ -204,6 +206,8 @@ class CudaB200AttnBackend(AttentionBackend):
             workspace=self.workspace.data_ptr(), workspace_bytes=self.workspace.numel(),
             max_bs=self.max_bs, force_path=self.force_path,
         )
+        if self.profile_events is not None:
+            p.ev_kernel_begin, p.ev_kernel_end = self.profile_events
         rc = self.lib.b200_attn_decode(p, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "b200_attn_decode")
         return o

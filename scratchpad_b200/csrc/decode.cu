@@ -298,6 +298,11 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
         const uint32_t* p = reinterpret_cast<const uint32_t*>(qp + kc * 16 + cid * 2);
         qf[kc][0] = live ? __ldg(p) : 0u;
         qf[kc][1] = live ? __ldg(p + 4) : 0u;
+        // Pass the fragments through a shuffle so the loop's HMMAs read SHFL results, not LDG
+        // results: otherwise ptxas ties them to the scoreboard slot the per-tile slot-id LDG
+        // also uses and every tile's first HMMA waits a DRAM latency (ncu r1a: 22% long_scoreboard).
+        qf[kc][0] = __shfl_sync(0xffffffffu, qf[kc][0], lane);
+        qf[kc][1] = __shfl_sync(0xffffffffu, qf[kc][1], lane);
       } else {
         // 16-element chunk kc: slots (2c,2c+1) <-> d = 16kc+4c+{0,1}; (2c+8,2c+9) <-> d = 16kc+4c+{2,3}
         const uint2 raw = live ? __ldg(reinterpret_cast<const uint2*>(qp + kc * 16 + cid * 4)) : make_uint2(0u, 0u);
@@ -780,8 +785,10 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
   a.k_scale = p->k_scale;
   a.v_scale = p->v_scale;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->ev_kernel_begin) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(p->ev_kernel_begin), st));
   rc = dispatch(kc, a, cfg.grid_ctas, p->hkv / kc.hpc, st, false, nullptr);
   if (rc) return rc;
+  if (p->ev_kernel_end) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(p->ev_kernel_end), st));
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p->o);
   if (p->dv == 64)
     merge_kernel<64><<<dim3(p->bs, p->hq), 64, 0, st>>>(a.hdr, a.tile_off, a.part_o, a.part_lse, o, p->o_stride_t, p->o_stride_h, p->hq, cfg.sub_splits);

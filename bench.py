@@ -310,6 +310,123 @@ def workload_config(w, world, args, st):
     return cfg
 
 
+
+# ----------------------------------------------------------------------------
+# extend / chunked-prefill workloads (C4): tensor-bound, metric TFLOP/s
+# ----------------------------------------------------------------------------
+def run_extend_bench(args, rank, world, local_rank, dist):
+    from oracle import attn_oracle as O  # flop accounting only
+    from scratchpad_b200 import CudaB200AttnBackend, synth
+
+    w = synth.WORKLOADS[args.workload]
+    tp = world * args.shard
+    hq, hkv, d = w.hq_total // tp, w.hkv_total // tp, w.head_dim
+    dev = torch.device(f"cuda:{local_rank}")
+    pre, ext = [w.prefix_len] * w.batch, [w.extend_len] * w.batch
+    need = sum(p + e for p, e in zip(pre, ext))
+    L = args.layers or 2
+    runner = synth.make_model_runner(w.hq_total, w.hkv_total, d, tp_size=tp, layer_num=L, pool_tokens=need + 64,
+                                     max_reqs=w.batch, context_len=w.prefix_len + w.extend_len + 1,
+                                     kv_dtype=w.kv_dtype, device=str(dev))
+    fill_pool(runner.token_to_kv_pool, 1000 + rank % max(world, 1))
+    backend = CudaB200AttnBackend(runner)
+    gen = torch.Generator().manual_seed(args.seed)
+    fb = synth.make_extend_batch(runner, pre, ext, gen, mode=args.index_mode, backend=backend)
+    layers = [synth.make_layer(runner, i) for i in range(L)]
+    T = sum(ext)
+    gq = torch.Generator(device=dev).manual_seed(77 + rank)
+    qkv = torch.randn((T, (hq + 2 * hkv) * d), generator=gq, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    q, k, v = qkv[:, : hq * d], qkv[:, hq * d: (hq + hkv) * d], qkv[:, (hq + hkv) * d:]
+    flops = O.extend_algorithmic_flops(pre, ext, hq, d)
+    K, W = min(args.steps, 64), min(max(args.warmup, 3), 8)
+
+    def step(i):
+        if i % L == 0:
+            backend.init_forward_metadata(fb)
+        return layers[i % L](q, k, v, fb, save_kv_cache=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.sample()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(K):
+        step(i)
+    ev1.record()
+    torch.cuda.synchronize()
+    sampler.sample()
+    sampler.stop()
+    tt = torch.tensor([ev0.elapsed_time(ev1) * 1e-3], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_max = float(tt.item())
+    # e2e: host q/k/v + metadata in, o out, every step
+    h_qkv = qkv.cpu().pin_memory()
+    h_o = torch.empty((T, hq * d), dtype=torch.bfloat16).pin_memory()
+    d_qkv = torch.empty_like(qkv)
+    dq, dk, dv_ = d_qkv[:, : hq * d], d_qkv[:, hq * d: (hq + hkv) * d], d_qkv[:, (hq + hkv) * d:]
+    h_loc = fb.out_cache_loc.cpu().pin_memory()
+    ke = min(K, 16)
+
+    def e2e_step(i):
+        d_qkv.copy_(h_qkv, non_blocking=True)
+        fb.out_cache_loc.copy_(h_loc, non_blocking=True)
+        backend.init_forward_metadata(fb)
+        o = layers[i % L](dq, dk, dv_, fb, save_kv_cache=True)
+        h_o.copy_(o, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(ke):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops", 1590.0))
+        ach = flops / (t_max / K) / 1e12
+        line = {
+            "metric": "extend_attn_tflops", "value": ach * world, "unit": "TFLOP/s (algorithmic, causal half counted exactly)",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_max / K * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{w.name}: {w.description}", "batch": w.batch, "prefix_len": w.prefix_len,
+                       "extend_len": w.extend_len, "hq_per_gpu": hq, "hkv_per_gpu": hkv, "head_dim": d,
+                       "index": args.index_mode, "layers": L,
+                       "step": "one forward_extend layer-call: fused KV store + causal extend attention over the "
+                               "gathered prefix", "l2": "per-layer pools rotated; compute-bound"},
+            "tokens_per_s": T * K / t_max,
+            "roofline": {"bound": "tensor", "kernel": "extend_mma_kernel", "achieved": ach, "peak": peak,
+                         "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                         "algorithmic_flops_per_launch": flops,
+                         "peak_kind": "measured burst (MEASURED_PEAKS.json bf16_tflops)",
+                         "note": "step time used (KV store + extend kernel); the store is <1% of the step"},
+            "cpu_baseline": None,
+            "e2e": {"value": flops * ke / float(te.item()) / 1e12 * world, "unit": "TFLOP/s",
+                    "h2d_bytes_per_step": h_qkv.numel() * 2 + h_loc.numel() * 8, "d2h_bytes_per_step": h_o.numel() * 2,
+                    "steps": ke},
+            "gpu_launches": K * 2, "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
 # ----------------------------------------------------------------------------
 # b200 arm
 # ----------------------------------------------------------------------------
@@ -335,6 +452,10 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 
+    from scratchpad_b200 import synth as _synth
+    if _synth.WORKLOADS[args.workload].extend_len:
+        run_extend_bench(args, rank, world, local_rank, dist)
+        return
     st = build_state(args, rank, world * args.shard)
     w, backend, fb, layers, L = st["w"], st["backend"], st["fb"], st["layers"], st["L"]
     B, hq, hkv, d = w.batch, st["hq"], st["hkv"], st["d"]

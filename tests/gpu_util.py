@@ -88,3 +88,78 @@ def random_decode_case(hq, hkv, d, seq_lens, seed, kv_dtype=torch.bfloat16, shar
     sl = torch.tensor(seq_lens, dtype=torch.int64)
     return dict(q=q, k_buf=kf, v_buf=vf, req_to_token=r2t, req_pool_indices=rpi, seq_lens=sl,
                 sm_scale=d ** -0.5, k_scale=ks, v_scale=vs, kv_dtype=kv_dtype)
+
+
+def random_extend_case(hq, hkv, d, prefix_lens, extend_lens, seed, kv_dtype=torch.bfloat16, per_head=True,
+                       extra_rows=2, mode="random"):
+    """CPU tensors for one extend case: pool holding the prefixes (quantised for fp8), new q/k/v in bf16."""
+    gen = torch.Generator().manual_seed(seed)
+    seq_lens = [p + e for p, e in zip(prefix_lens, extend_lens)]
+    pool = sum(seq_lens) + 19
+    b = len(seq_lens)
+    r2t = torch.zeros((b + extra_rows, max(max(seq_lens), 1) + 4), dtype=torch.int32)
+    rpi = synth.build_page_table(r2t, seq_lens, pool, gen, mode)
+    kf = torch.randn((pool + 1, hkv, d), generator=gen).to(torch.bfloat16)
+    vf = torch.randn((pool + 1, hkv, d), generator=gen).to(torch.bfloat16)
+    t = sum(extend_lens)
+    q = torch.randn((t, hq, d), generator=gen).to(torch.bfloat16)
+    k_new = torch.randn((t, hkv, d), generator=gen).to(torch.bfloat16)
+    v_new = torch.randn((t, hkv, d), generator=gen).to(torch.bfloat16)
+    ks = vs = None
+    if kv_dtype != torch.bfloat16:
+        from oracle import attn_oracle as O
+        if per_head:
+            ks = kf.float().abs().amax(dim=(0, 2)) / 448.0
+            vs = vf.float().abs().amax(dim=(0, 2)) / 448.0
+        else:
+            ks = (kf.float().abs().amax() / 448.0).expand(hkv).clone()
+            vs = (vf.float().abs().amax() / 448.0).expand(hkv).clone()
+        kf = O.quantize_kv_ref(kf, kv_dtype, ks)
+        vf = O.quantize_kv_ref(vf, kv_dtype, vs)
+    el = torch.tensor(extend_lens, dtype=torch.int32)
+    out_loc = torch.cat([r2t[rpi[i], p:p + e] for i, (p, e) in enumerate(zip(prefix_lens, extend_lens))]).long()
+    return dict(q=q, k_new=k_new, v_new=v_new, k_buf=kf, v_buf=vf, req_to_token=r2t, req_pool_indices=rpi,
+                seq_lens=torch.tensor(seq_lens, dtype=torch.int64), extend_seq_lens=el,
+                extend_prefix_lens=torch.tensor(prefix_lens, dtype=torch.int32),
+                extend_start_loc=compute_extend_start_loc(el), out_cache_loc=out_loc, sm_scale=d ** -0.5,
+                k_scale=ks, v_scale=vs, kv_dtype=kv_dtype)
+
+
+def run_extend_case(c, logit_cap=0.0, idx_dtype=torch.int64, save_kv_cache=True, qkv_slices=True,
+                    forward_mode=ForwardMode.EXTEND):
+    """Runs one extend case through CudaB200AttnBackend.forward_extend.  Returns (o [T,Hq,Dv] cpu, runner)."""
+    t, hq, d = c["q"].shape
+    hkv = c["k_buf"].shape[1]
+    kv_dtype = c.get("kv_dtype", torch.bfloat16)
+    runner = make_runner_from_case(c["k_buf"], c["v_buf"], c["req_to_token"], kv_dtype, c.get("k_scale"),
+                                   c.get("v_scale"), tp_hq=hq)
+    backend = CudaB200AttnBackend(runner)
+    layer = synth.make_layer(runner, 0, logit_cap)
+    layer.scaling = c["sm_scale"]
+    el = c["extend_seq_lens"].to(torch.int32)
+    pre = (c["seq_lens"].to(torch.int64) - el.to(torch.int64)).to(torch.int32)
+    if "out_cache_loc" in c:
+        out_loc = c["out_cache_loc"]
+    else:
+        out_loc = torch.cat([c["req_to_token"][int(c["req_pool_indices"][i]), int(pre[i]):int(c["seq_lens"][i])]
+                             for i in range(len(el))]).long()
+    fb = ForwardBatch(forward_mode=forward_mode, batch_size=len(el),
+                      req_pool_indices=c["req_pool_indices"].to(idx_dtype).cuda(),
+                      seq_lens=c["seq_lens"].to(idx_dtype).cuda(), out_cache_loc=out_loc.cuda(),
+                      seq_lens_sum=int(c["seq_lens"].sum()), extend_num_tokens=t, extend_seq_lens=el.cuda(),
+                      extend_prefix_lens=pre.cuda(), extend_start_loc=c["extend_start_loc"].to(torch.int32).cuda(),
+                      extend_prefix_lens_cpu=pre.tolist(), extend_seq_lens_cpu=el.tolist(),
+                      req_to_token_pool=runner.req_to_token_pool, token_to_kv_pool=runner.token_to_kv_pool,
+                      attn_backend=backend)
+    if qkv_slices:  # q/k/v as column slices of the fused qkv GEMM output (llama.py:149-152)
+        qkv = torch.zeros((t, (hq + 2 * hkv) * d), dtype=torch.bfloat16, device="cuda")
+        qkv[:, : hq * d] = c["q"].reshape(t, -1).cuda()
+        qkv[:, hq * d: (hq + hkv) * d] = c["k_new"].reshape(t, -1).cuda()
+        qkv[:, (hq + hkv) * d:] = c["v_new"].reshape(t, -1).cuda()
+        qd, kd, vd = qkv[:, : hq * d], qkv[:, hq * d: (hq + hkv) * d], qkv[:, (hq + hkv) * d:]
+    else:
+        qd, kd, vd = c["q"].reshape(t, -1).cuda(), c["k_new"].reshape(t, -1).cuda(), c["v_new"].reshape(t, -1).cuda()
+    backend.init_forward_metadata(fb)
+    o = layer(qd, kd, vd, fb, save_kv_cache=save_kv_cache)
+    torch.cuda.synchronize()
+    return o.view(t, hq, -1).cpu(), runner

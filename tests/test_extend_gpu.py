@@ -1,0 +1,86 @@
+"""-m gpu parity tests of the extend / chunked-prefill path: CUDA kernel (through the Python
+backend surface and the C ABI) vs the fp32 oracle, the golden fixtures written from the
+reference's own kernel, and the reference's redundant_attention cross-check."""
+import pytest
+import torch
+
+from oracle import attn_oracle as O
+from golden_util import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import gpu_util as G
+    from scratchpad_b200 import ForwardMode
+
+
+def _oracle(c, logit_cap=0.0):
+    return O.extend_ref(c["q"], c["k_new"], c["v_new"], c["k_buf"], c["v_buf"], c["req_to_token"],
+                        c["req_pool_indices"], c["seq_lens"], c["extend_seq_lens"], c["extend_start_loc"],
+                        c["sm_scale"], logit_cap, c.get("kv_dtype"), c.get("k_scale"), c.get("v_scale"))
+
+
+@pytest.mark.parametrize("name", golden_names("extend"))
+def test_extend_matches_reference_golden(name):
+    g = load_golden(name)
+    c = dict(g, req_pool_indices=g["req_pool_indices"].long(), seq_lens=g["seq_lens"].long())
+    got = G.run_extend_case(c, logit_cap=g["logit_cap"], save_kv_cache=False)[0]
+    G.assert_close(got, g["out"], G.BF16_ABS, G.BF16_REL, name)
+
+
+CASES = [
+    # hq, hkv, d, prefix_lens, extend_lens
+    (8, 2, 64, [7, 0], [5, 9]),
+    (32, 8, 128, [130, 0, 64, 300], [1, 70, 129, 33]),          # 8B shapes, ragged, prefix 0, ext 1
+    (32, 8, 64, [63, 64, 65], [64, 63, 200]),                    # 1B shapes, tile-boundary prefixes
+    (8, 1, 128, [200, 5], [17, 300]),                            # g = 8 (70B TP8 shard)
+    (4, 4, 64, [33], [150]),                                     # MHA
+    (7, 1, 64, [40, 0], [30, 129]),                              # g = 7: 18 tokens x 7 heads per CTA, 2 dead rows
+    (6, 2, 128, [100], [90]),                                    # g = 3
+    (32, 8, 128, [1000, 2000, 17, 0], [1, 1, 1, 1]),             # MIXED-mode decode rows (ext_len 1, long prefix)
+]
+
+
+@pytest.mark.parametrize("hq,hkv,d,pre,ext", CASES)
+@pytest.mark.parametrize("kv", ["bf16", "fp8"])
+def test_extend_vs_oracle(hq, hkv, d, pre, ext, kv):
+    kv_dtype = torch.bfloat16 if kv == "bf16" else torch.float8_e4m3fn
+    tol = (G.BF16_ABS, G.BF16_REL) if kv == "bf16" else (G.FP8_ABS, G.FP8_REL)
+    c = G.random_extend_case(hq, hkv, d, pre, ext, seed=hq * 7 + hkv + d, kv_dtype=kv_dtype)
+    got = G.run_extend_case(c)[0]
+    G.assert_close(got, _oracle(c), *tol, what=f"{hq}/{hkv}/{d}/{kv}/{pre}/{ext}")
+
+
+@pytest.mark.parametrize("idx_dtype", [torch.int32, torch.int64])
+def test_extend_index_dtypes_logit_cap_mixed_mode(idx_dtype):
+    c = G.random_extend_case(16, 4, 128, [50, 0, 129], [40, 65, 1], seed=3)
+    got = G.run_extend_case(c, logit_cap=30.0, idx_dtype=idx_dtype, forward_mode=ForwardMode.MIXED)[0]
+    G.assert_close(got, _oracle(c, 30.0), G.BF16_ABS, G.BF16_REL)
+
+
+def test_extend_writes_kv_then_matches_redundant_attention():
+    """save_kv_cache=True stores the new tokens (bit-exact) and extend == full causal attention over the
+    pool sliced to the new rows (the reference's redundant_attention fixture, extend_attention.py:330-364)."""
+    c = G.random_extend_case(32, 8, 64, [64, 0, 33], [100, 31, 257], seed=4)
+    got, runner = G.run_extend_case(c, save_kv_cache=True)
+    kb, vb = c["k_buf"].clone(), c["v_buf"].clone()
+    O.set_kv_buffer_ref(kb, vb, c["out_cache_loc"], c["k_new"], c["v_new"], torch.bfloat16)
+    pool = runner.token_to_kv_pool
+    assert torch.equal(pool.k_buffer[0].cpu().view(torch.int16), kb.view(torch.int16))
+    assert torch.equal(pool.v_buffer[0].cpu().view(torch.int16), vb.view(torch.int16))
+    red = O.redundant_attention_ref(c["q"], kb, vb, c["req_to_token"], c["req_pool_indices"], c["seq_lens"],
+                                    c["extend_seq_lens"], c["extend_start_loc"], c["sm_scale"])
+    G.assert_close(got, red, G.BF16_ABS, G.BF16_REL, "extend vs redundant attention")
+
+
+def test_extend_long_prefix_chunk_vs_decode_consistency():
+    """Size-independent property: the last row of an extend over (prefix P, ext E) equals a decode over the
+    P+E tokens once they are in the pool."""
+    c = G.random_extend_case(32, 8, 128, [1500], [600], seed=5)
+    got, runner = G.run_extend_case(c, save_kv_cache=True)
+    kb, vb = c["k_buf"].clone(), c["v_buf"].clone()
+    O.set_kv_buffer_ref(kb, vb, c["out_cache_loc"], c["k_new"], c["v_new"], torch.bfloat16)
+    dec = G.run_decode_case(c["q"][-1:], kb, vb, c["req_to_token"], c["req_pool_indices"], c["seq_lens"],
+                            c["sm_scale"])[0]
+    G.assert_close(got[-1:], dec, G.BF16_ABS, G.BF16_REL, "extend last row vs decode")
+    G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, "extend vs oracle")

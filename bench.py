@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--kv-layout", default="auto", choices=["auto", "split", "fused"],
+                    help="split: the reference's separate k/v buffers; fused: K|V rows of a token adjacent "
+                         "(pool option of this backend); auto: fused when a per-buffer token row is < 256 B")
     ap.add_argument("--shard", type=int, default=1,
                     help="development aid: run the per-GPU shard shapes of a (gpus*shard)-way head split on this GPU")
     return ap.parse_args()
@@ -181,7 +184,9 @@ def build_state(args, rank, world):
     assert w.hkv_total % world == 0 and w.hq_total % world == 0, "kv heads must divide over the GPUs"
     gen = torch.Generator().manual_seed(args.seed)  # same page table on every rank (TP replicas)
     seq_lens = synth.workload_seq_lens(w, gen)
-    hkv_l, hq_l = w.hkv_total // world, w.hq_total // world
+    from scratchpad_b200.sharding import head_shard
+    sh = head_shard(w.hq_total, w.hkv_total, world, rank % world)
+    hkv_l, hq_l = sh.hkv_local, sh.hq_local
     shared = w.shared_prefix
     need = shared + sum(n - shared if shared and n >= shared else n for n in seq_lens)
     pool_tokens = need + 64
@@ -189,9 +194,11 @@ def build_state(args, rank, world):
     per_layer = 2 * (pool_tokens + 1) * hkv_l * w.head_dim * kv_elt
     layers = pick_layers(per_layer, args.layers, w.layers_total)
     dev = f"cuda:{torch.cuda.current_device()}"
+    row_bytes = hkv_l * w.head_dim * kv_elt
+    fused = args.kv_layout == "fused" or (args.kv_layout == "auto" and row_bytes < 256)
     runner = synth.make_model_runner(w.hq_total, w.hkv_total, w.head_dim, tp_size=world, layer_num=layers,
                                      pool_tokens=pool_tokens, max_reqs=w.batch, context_len=max(seq_lens) + 1,
-                                     kv_dtype=w.kv_dtype, device=dev)
+                                     kv_dtype=w.kv_dtype, device=dev, fused_kv=fused)
     fill_pool(runner.token_to_kv_pool, 1000 + rank % max(world, 1))
     backend = CudaB200AttnBackend(runner)
     fb = synth.make_decode_batch(runner, seq_lens, gen, mode=args.index_mode, shared_prefix=shared,
@@ -200,7 +207,8 @@ def build_state(args, rank, world):
     algo_bytes = O.decode_algorithmic_bytes(seq_lens, hq_l, hkv_l, w.head_dim, w.head_dim, kv_elt)
     uniq_tokens = need
     return dict(w=w, seq_lens=seq_lens, runner=runner, backend=backend, fb=fb, layers=lay, L=layers,
-                hq=hq_l, hkv=hkv_l, d=w.head_dim, algo_bytes=algo_bytes, kv_elt=kv_elt,
+                hq=hq_l, hkv=hkv_l, d=w.head_dim, algo_bytes=algo_bytes, kv_elt=kv_elt, fused_kv=fused,
+                row_bytes=row_bytes,
                 unique_kv_bytes=uniq_tokens * hkv_l * 2 * w.head_dim * kv_elt, per_layer_bytes=per_layer)
 
 
@@ -304,6 +312,9 @@ def workload_config(w, world, args, st):
     if st is not None:
         cfg.update({
             "layers": st["L"], "sum_seq_len": int(sum(st["seq_lens"])), "mode": args.mode,
+            "kv_layout": ("fused [P+1,2,Hkv,D] (K|V rows adjacent)" if st["fused_kv"] else
+                          "split k_buffer/v_buffer [P+1,Hkv,D] (reference layout)"),
+            "token_row_bytes_per_buffer": st["row_bytes"],
             "l2": f"inputs larger than L2: {st['L']} per-layer KV pools of {st['per_layer_bytes'] / 1e9:.2f} GB "
                   "rotated step to step",
         })

@@ -31,6 +31,31 @@ __device__ __forceinline__ const uint8_t* kv_row_ptr(const uint8_t* buf, int32_t
   return buf + static_cast<int64_t>(slot) * stride_t_bytes;
 }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------
+// Every kernel of the path is launched with programmaticStreamSerializationAllowed and starts with
+// griddepcontrol.wait (returns once the preceding grid has completed and flushed), so the launch
+// latency and CTA scheduling of kernel N+1 overlap the tail of kernel N.  No-ops without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess) return 1000 + static_cast<int>(e);
+  return B200_OK;
+}
+
 // ---- PTX wrappers ------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -43,7 +43,7 @@ constexpr int kPlanMagic = 0x62323030;  // "b200"
 constexpr int kHdrInts = 16;
 
 struct WsLayout {
-  size_t tile_off, seq_len, req_idx, part_lse, part_o, total;
+  size_t tile_off, seq_len, req_idx, cta_b0, part_lse, part_o, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -56,7 +56,9 @@ static WsLayout ws_layout(int max_bs, int grid, int nsub, int hq, int dv) {
   L.seq_len = off;
   off = align_up(off + (size_t)max_bs * sizeof(int), 16);
   L.req_idx = off;
-  off = align_up(off + (size_t)max_bs * sizeof(int), 256);
+  off = align_up(off + (size_t)max_bs * sizeof(int), 16);
+  L.cta_b0 = off;  // request holding the first tile of each CTA
+  off = align_up(off + (size_t)grid * sizeof(int), 256);
   size_t nparts = (size_t)(grid + max_bs) * nsub * hq;
   L.part_lse = off;
   off = align_up(off + nparts * sizeof(float), 256);
@@ -71,10 +73,13 @@ static WsLayout ws_layout(int max_bs, int grid, int nsub, int hq, int dv) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* __restrict__ tile_off,
                                                     int* __restrict__ seq32, int* __restrict__ req32,
+                                                    int* __restrict__ cta_b0,
                                                     const void* __restrict__ req, const void* __restrict__ seq,
                                                     int idx64, int bs, int tile_tokens, int grid) {
   __shared__ int warp_sums[32];
   __shared__ int s_running;
+  pdl_wait();
+  pdl_launch_dependents();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_running = 0;
   __syncthreads();
@@ -113,6 +118,23 @@ __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* 
     if (tid == 1023) s_running = incl;
     __syncthreads();
   }
+  {
+    // first request of every CTA's tile range: last b with tile_off[b] <= c * tpc (removes a
+    // dependent-load binary search from the decode kernel's prologue)
+    const int total = s_running;
+    int tpc = (total + grid - 1) / grid;
+    if (tpc < 1) tpc = 1;
+    for (int c = tid; c < grid; c += 1024) {
+      const int gt = c * tpc;
+      int lo = 0, hi = bs;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (tile_off[mid] <= gt) lo = mid;  // written above by this CTA, ordered by the __syncthreads
+        else hi = mid;
+      }
+      cta_b0[c] = lo;
+    }
+  }
   if (tid == 0) {
     const int total = s_running;
     tile_off[bs] = total;
@@ -143,6 +165,7 @@ struct DecodeArgs {
   const int* tile_off;
   const int* seq_len;
   const int* req_idx;
+  const int* cta_b0;
   float* part_o;
   float* part_lse;
   int hq, hkv, g;
@@ -211,19 +234,14 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x;
   const int h0 = blockIdx.y * HPC;  // first kv head of this CTA
+  pdl_wait();               // everything below reads what earlier launches (plan, kv store, qkv GEMM) wrote
+  pdl_launch_dependents();  // let the merge grid get scheduled behind us; it waits for our completion
 
   const int total = __ldg(a.hdr + 0), tpc = __ldg(a.hdr + 1), bs = __ldg(a.hdr + 3);
   const int gt_begin = cta * tpc;
   const int gt_end = min(gt_begin + tpc, total);
   if (gt_begin >= gt_end) return;
-
-  // request containing the first tile: last b with tile_off[b] <= gt_begin
-  int lo = 0, hi = bs;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(a.tile_off + mid) <= gt_begin) lo = mid;
-    else hi = mid;
-  }
+  const int lo = __ldg(a.cta_b0 + cta);
   Cursor pc;  // producer cursor
   pc.gt = gt_begin;
   pc.gt_end = gt_end;
@@ -409,7 +427,10 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
   };
 
   // one partial per (cta, request, sub-slice): slot = cta + b is unique along the
-  // monotone staircase of (cta, request) pairs
+  // monotone staircase of (cta, request) pairs.  (A fused "last CTA to arrive merges" variant was
+  // measured in round 1 and was slower -- 184 vs 169 us at C2: the fence + atomic round trip + merge
+  // reads stall the copy pipeline at every request boundary -- so the merge stays a separate,
+  // programmatically-dependent launch.)
   auto flush = [&](int b) {
     float l0 = l[0], l1 = l[1];
 #pragma unroll
@@ -490,35 +511,62 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
 
 // ---------------------------------------------------------------------------
 // merge: o[b, h, :] = sum_i w_i * O_i,  w_i = 2^(lse_i - max) / sum_j 2^(lse_j - max)
+// One warp per (request, q head): lanes own DV/32 consecutive dims; the <= few partial
+// slots of the pair are consecutive ((c + b) * nsub + sub), still L2-resident.
 // ---------------------------------------------------------------------------
 template <int DV>
-__global__ void __launch_bounds__(DV) merge_kernel(const int* __restrict__ hdr, const int* __restrict__ tile_off,
-                                                   const float* __restrict__ part_o,
-                                                   const float* __restrict__ part_lse, __nv_bfloat16* __restrict__ o,
-                                                   int64_t o_st, int64_t o_sh, int hq, int nsub) {
-  const int b = blockIdx.x, h = blockIdx.y, d = threadIdx.x;
+__global__ void __launch_bounds__(256) merge_kernel(const int* __restrict__ hdr, const int* __restrict__ tile_off,
+                                                    const float* __restrict__ part_o,
+                                                    const float* __restrict__ part_lse, __nv_bfloat16* __restrict__ o,
+                                                    int64_t o_st, int64_t o_sh, int bs, int hq, int nsub) {
+  pdl_wait();
+  pdl_launch_dependents();
+  constexpr int VPL = DV / 32;  // floats per lane
+  const int lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pair >= bs * hq) return;
+  const int b = pair / hq, h = pair % hq;
   const int tpc = __ldg(hdr + 1);
   const int t0 = __ldg(tile_off + b), t1 = __ldg(tile_off + b + 1);
-  __nv_bfloat16* op = o + static_cast<int64_t>(b) * o_st + static_cast<int64_t>(h) * o_sh + d;
-  if (t1 <= t0) {  // seq_len == 0
-    *op = __float2bfloat16(0.f);
-    return;
-  }
-  const int c0 = t0 / tpc, c1 = (t1 - 1) / tpc;
-  const int64_t first = static_cast<int64_t>(c0 + b) * nsub;
-  const int n = (c1 - c0 + 1) * nsub;  // consecutive slots (c + b) * nsub + sub
-  float mx = -INFINITY;
-  for (int i = 0; i < n; ++i) mx = fmaxf(mx, __ldg(part_lse + (first + i) * hq + h));
-  float acc = 0.f, den = 0.f;
-  if (mx > -INFINITY) {
-    for (int i = 0; i < n; ++i) {
-      const int64_t pi = (first + i) * hq + h;
-      const float w = ex2(__ldg(part_lse + pi) - mx);
-      den += w;
-      acc += w * __ldg(part_o + pi * DV + d);
+  __nv_bfloat16* op = o + static_cast<int64_t>(b) * o_st + static_cast<int64_t>(h) * o_sh + lane * VPL;
+  float acc[VPL];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) acc[j] = 0.f;
+  float den = 0.f;
+  if (t1 > t0) {
+    const int c0 = t0 / tpc, c1 = (t1 - 1) / tpc;
+    const int64_t first = static_cast<int64_t>(c0 + b) * nsub;
+    const int n = (c1 - c0 + 1) * nsub;
+    float mx = -INFINITY;
+    for (int i = lane; i < n; i += 32) mx = fmaxf(mx, __ldcg(part_lse + (first + i) * hq + h));
+#pragma unroll
+    for (int x = 16; x > 0; x >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, x));
+    if (mx > -INFINITY) {
+      for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const float w_lane = i < n ? ex2(__ldcg(part_lse + (first + i) * hq + h) - mx) : 0.f;
+        const int cnt = min(32, n - base);
+        for (int j = 0; j < cnt; ++j) {
+          const float w = __shfl_sync(0xffffffffu, w_lane, j);
+          den += w;
+          const float* src = part_o + ((first + base + j) * hq + h) * DV + lane * VPL;
+          if constexpr (VPL == 4) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(src));
+            acc[0] += w * v.x; acc[1] += w * v.y; acc[2] += w * v.z; acc[3] += w * v.w;
+          } else {
+            const float2 v = __ldcg(reinterpret_cast<const float2*>(src));
+            acc[0] += w * v.x; acc[1] += w * v.y;
+          }
+        }
+      }
     }
   }
-  *op = __float2bfloat16(den > 0.f ? acc / den : 0.f);
+  const float r = den > 0.f ? 1.f / den : 0.f;  // seq_len == 0 -> zeros
+  if constexpr (VPL == 4) {
+    *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16x2(acc[0] * r, acc[1] * r), pack_bf16x2(acc[2] * r, acc[3] * r));
+  } else {
+    *reinterpret_cast<uint32_t*>(op) = pack_bf16x2(acc[0] * r, acc[1] * r);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -635,9 +683,7 @@ static int launch_decode_t(const DecodeArgs& a, int grid_x, int grid_y, cudaStre
     B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, C::NT, C::SMEM_BYTES));
     return B200_OK;
   }
-  kern<<<dim3(grid_x, grid_y), C::NT, C::SMEM_BYTES, st>>>(a);
-  B200_CUDA_TRY(cudaGetLastError());
-  return B200_OK;
+  return launch_pdl(kern, dim3(grid_x, grid_y), dim3(C::NT), C::SMEM_BYTES, st, a);
 }
 
 template <int D, bool FP8>
@@ -737,7 +783,7 @@ int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs, co
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   plan_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<int*>(ws), reinterpret_cast<int*>(ws + L.tile_off), reinterpret_cast<int*>(ws + L.seq_len),
-      reinterpret_cast<int*>(ws + L.req_idx), req_pool_indices, seq_lens, idx_dtype == B200_IDX_I64, bs,
+      reinterpret_cast<int*>(ws + L.req_idx), reinterpret_cast<int*>(ws + L.cta_b0), req_pool_indices, seq_lens, idx_dtype == B200_IDX_I64, bs,
       cfg.tile_tokens, cfg.grid_ctas);
   B200_CUDA_TRY(cudaGetLastError());
   return B200_OK;
@@ -753,7 +799,8 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
   // 16-byte vector access on pool rows, 8-byte on q
   if ((p->k_stride_t * elt) % 16 || (p->v_stride_t * elt) % 16 || p->q_stride_t % 4 || p->q_stride_h % 4 ||
       (reinterpret_cast<uintptr_t>(p->k_buf) & 15) || (reinterpret_cast<uintptr_t>(p->v_buf) & 15) ||
-      (reinterpret_cast<uintptr_t>(p->q) & 7))
+      (reinterpret_cast<uintptr_t>(p->q) & 7) || (reinterpret_cast<uintptr_t>(p->o) & 15) || p->o_stride_t % 8 ||
+      p->o_stride_h % 8)
     return B200_ERR_INVALID;
   b200_attn_config cfg;
   rc = get_config(p->max_bs, p->hq, p->hkv, p->d, p->dv, p->kv_dtype, p->force_path, &cfg);
@@ -775,6 +822,7 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
   a.tile_off = reinterpret_cast<const int*>(ws + L.tile_off);
   a.seq_len = reinterpret_cast<const int*>(ws + L.seq_len);
   a.req_idx = reinterpret_cast<const int*>(ws + L.req_idx);
+  a.cta_b0 = reinterpret_cast<const int*>(ws + L.cta_b0);
   a.part_lse = reinterpret_cast<float*>(ws + L.part_lse);
   a.part_o = reinterpret_cast<float*>(ws + L.part_o);
   a.hq = p->hq;
@@ -790,12 +838,16 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
   if (rc) return rc;
   if (p->ev_kernel_end) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(p->ev_kernel_end), st));
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p->o);
+  const dim3 mgrid((p->bs * p->hq + 7) / 8);
   if (p->dv == 64)
-    merge_kernel<64><<<dim3(p->bs, p->hq), 64, 0, st>>>(a.hdr, a.tile_off, a.part_o, a.part_lse, o, p->o_stride_t, p->o_stride_h, p->hq, cfg.sub_splits);
-  else
-    merge_kernel<128><<<dim3(p->bs, p->hq), 128, 0, st>>>(a.hdr, a.tile_off, a.part_o, a.part_lse, o, p->o_stride_t, p->o_stride_h, p->hq, cfg.sub_splits);
-  B200_CUDA_TRY(cudaGetLastError());
-  return B200_OK;
+    return launch_pdl(merge_kernel<64>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
+                      static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
+                      static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
+                      static_cast<int>(cfg.sub_splits));
+  return launch_pdl(merge_kernel<128>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
+                    static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
+                    static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
+                    static_cast<int>(cfg.sub_splits));
 }
 
 int b200_debug_gather(const void* buf, int64_t stride_t_bytes, int32_t row_bytes, const int32_t* req_to_token,

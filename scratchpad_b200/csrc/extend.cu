@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(kExtNT, 1) extend_mma_kernel(const ExtendArgs 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, cid = lane & 3;
   const int b = blockIdx.z, kvh = blockIdx.y;
+  pdl_wait();
+  pdl_launch_dependents();
   const int G = a.g, bm_t = a.bm_t;
 
   const int ext = __ldg(a.ext_lens + b);
@@ -374,9 +376,7 @@ static int launch_extend_t(const ExtendArgs& a, dim3 grid, cudaStream_t st) {
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<grid, kExtNT, C::SMEM_BYTES, st>>>(a);
-  B200_CUDA_TRY(cudaGetLastError());
-  return B200_OK;
+  return launch_pdl(kern, grid, dim3(kExtNT), C::SMEM_BYTES, st, a);
 }
 
 }  // namespace b200

@@ -25,6 +25,8 @@ __global__ void __launch_bounds__(256) kv_store_kernel(uint8_t* __restrict__ kbu
                                                        int num_tokens, int hkv, int d, int dv,
                                                        const float* __restrict__ k_scale,
                                                        const float* __restrict__ v_scale) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int vk = d / 8, vv = dv / 8;          // 8-element vectors per head row
   const int per_tok = hkv * (vk + vv);
   const int64_t total = static_cast<int64_t>(num_tokens) * per_tok;
@@ -81,18 +83,11 @@ extern "C" int b200_kv_store(void* k_buf, void* v_buf, int64_t k_stride_t, int64
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (fp8)
-    kv_store_kernel<true><<<blocks, 256, 0, st>>>(static_cast<uint8_t*>(k_buf), static_cast<uint8_t*>(v_buf),
-                                                  k_stride_t * elt, v_stride_t * elt, loc, loc_dtype == B200_IDX_I64,
-                                                  static_cast<const uint16_t*>(k), static_cast<const uint16_t*>(v),
-                                                  k_src_stride_t, k_src_stride_h, v_src_stride_t, v_src_stride_h,
-                                                  num_tokens, hkv, d, dv, k_scale, v_scale);
-  else
-    kv_store_kernel<false><<<blocks, 256, 0, st>>>(static_cast<uint8_t*>(k_buf), static_cast<uint8_t*>(v_buf),
-                                                   k_stride_t * elt, v_stride_t * elt, loc, loc_dtype == B200_IDX_I64,
-                                                   static_cast<const uint16_t*>(k), static_cast<const uint16_t*>(v),
-                                                   k_src_stride_t, k_src_stride_h, v_src_stride_t, v_src_stride_h,
-                                                   num_tokens, hkv, d, dv, k_scale, v_scale);
-  B200_CUDA_TRY(cudaGetLastError());
-  return B200_OK;
+  auto kern = fp8 ? kv_store_kernel<true> : kv_store_kernel<false>;
+  return launch_pdl(kern, dim3(blocks), dim3(256), 0, st, static_cast<uint8_t*>(k_buf), static_cast<uint8_t*>(v_buf),
+                    static_cast<int64_t>(k_stride_t * elt), static_cast<int64_t>(v_stride_t * elt), loc,
+                    static_cast<int>(loc_dtype == B200_IDX_I64), static_cast<const uint16_t*>(k),
+                    static_cast<const uint16_t*>(v), k_src_stride_t, k_src_stride_h, v_src_stride_t, v_src_stride_h,
+                    static_cast<int>(num_tokens), static_cast<int>(hkv), static_cast<int>(d), static_cast<int>(dv),
+                    k_scale, v_scale);
 }

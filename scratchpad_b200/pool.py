@@ -112,6 +112,7 @@ class MHATokenToKVPool:
         device: str,
         enable_memory_saver: bool = False,
         v_head_dim: Optional[int] = None,
+        fused_kv: bool = False,
     ):
         if page_size != 1:
             raise NotImplementedError("page_size > 1 is not supported (model_runner.py:431-432)")
@@ -125,14 +126,30 @@ class MHATokenToKVPool:
         self.v_head_dim = v_head_dim or head_dim
         self.layer_num = layer_num
         # [size + page_size, head_num, head_dim] per layer; slot 0 = padded tokens
-        self.k_buffer = [
-            torch.zeros((size + page_size, head_num, head_dim), dtype=self.store_dtype, device=device)
-            for _ in range(layer_num)
-        ]
-        self.v_buffer = [
-            torch.zeros((size + page_size, head_num, self.v_head_dim), dtype=self.store_dtype, device=device)
-            for _ in range(layer_num)
-        ]
+        self.fused_kv = bool(fused_kv)
+        if self.fused_kv:
+            # Layout option of the cuda_b200 backend: K and V rows of a token are adjacent in one
+            # [size + page, 2, head_num, head_dim] allocation, exposed as strided k_buffer/v_buffer views
+            # (same slot indexing, token stride doubled).  At TP8 a token row is only 128 B per buffer
+            # (fp8 D=128 / bf16 D=64); random 128 B gathers cap at ~5.0 TB/s on B200 while 256 B ones
+            # reach ~7.1 TB/s (tools/gather_bw.cu), so fusing the rows lifts the gather roofline.
+            if self.v_head_dim != head_dim:
+                raise ValueError("fused_kv needs head_dim == v_head_dim")
+            self.kv_buffer = [
+                torch.zeros((size + page_size, 2, head_num, head_dim), dtype=self.store_dtype, device=device)
+                for _ in range(layer_num)
+            ]
+            self.k_buffer = [kv[:, 0] for kv in self.kv_buffer]
+            self.v_buffer = [kv[:, 1] for kv in self.kv_buffer]
+        else:
+            self.k_buffer = [
+                torch.zeros((size + page_size, head_num, head_dim), dtype=self.store_dtype, device=device)
+                for _ in range(layer_num)
+            ]
+            self.v_buffer = [
+                torch.zeros((size + page_size, head_num, self.v_head_dim), dtype=self.store_dtype, device=device)
+                for _ in range(layer_num)
+            ]
         # fp8 metadata: x ~= x_hat * scale[layer, head]
         self.k_scale = self.v_scale = None
         if dtype in FP8_DTYPES:

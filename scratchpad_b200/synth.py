@@ -77,7 +77,7 @@ def workload_seq_lens(w: Workload, gen: torch.Generator) -> List[int]:
 
 def make_model_runner(hq_total: int, hkv_total: int, head_dim: int, tp_size: int = 1, layer_num: int = 1,
                       pool_tokens: int = 4096, max_reqs: int = 64, context_len: int = 4096,
-                      kv_dtype: torch.dtype = torch.bfloat16, device: str = "cuda"):
+                      kv_dtype: torch.dtype = torch.bfloat16, device: str = "cuda", fused_kv: bool = False):
     """The attributes AttentionBackend.__init__ may read over freshly allocated pools."""
     hkv_local = max(1, hkv_total // tp_size)  # ModelConfig.get_num_kv_heads (model_config.py:159-166)
     model_config = SimpleNamespace(
@@ -85,7 +85,7 @@ def make_model_runner(hq_total: int, hkv_total: int, head_dim: int, tp_size: int
         get_num_kv_heads=lambda tp: max(1, hkv_total // tp),
     )
     r2t = ReqToTokenPool(max_reqs + 1, context_len + 4, device)
-    kv = MHATokenToKVPool(pool_tokens, 1, kv_dtype, hkv_local, head_dim, layer_num, device)
+    kv = MHATokenToKVPool(pool_tokens, 1, kv_dtype, hkv_local, head_dim, layer_num, device, fused_kv=fused_kv)
     return SimpleNamespace(
         model_config=model_config, tp_size=tp_size, device=device, dtype=torch.bfloat16,
         kv_cache_dtype="auto" if kv_dtype == torch.bfloat16 else "fp8_e4m3",

@@ -23,11 +23,15 @@ def assert_close(got, ref, abs_tol, rel_tol, what=""):
     return mx, rl
 
 
+FUSED_KV = False  # tests flip this to run every helper over the fused [P+1, 2, Hkv, D] pool layout
+
+
 def make_runner_from_case(k_buf, v_buf, r2t, kv_dtype, k_scale=None, v_scale=None, tp_hq=None):
     """Pools on the GPU holding exactly the CPU case's bytes."""
     p1, hkv, d = k_buf.shape
     runner = synth.make_model_runner(tp_hq, hkv, d, tp_size=1, layer_num=1, pool_tokens=p1 - 1,
-                                     max_reqs=r2t.shape[0] - 1, context_len=r2t.shape[1] - 4, kv_dtype=kv_dtype)
+                                     max_reqs=r2t.shape[0] - 1, context_len=r2t.shape[1] - 4, kv_dtype=kv_dtype,
+                                     fused_kv=FUSED_KV)
     pool = runner.token_to_kv_pool
     pool.k_buffer[0].copy_(k_buf.view(pool.store_dtype))
     pool.v_buffer[0].copy_(v_buf.view(pool.store_dtype))

@@ -231,3 +231,31 @@ def test_unsupported_configs_raise():
     runner = synth.make_model_runner(32, 2, 64, pool_tokens=64, max_reqs=4, context_len=64)  # g = 16
     with pytest.raises(_lib.B200AttnError):
         CudaB200AttnBackend(runner)
+
+
+@pytest.mark.parametrize("kv", ["bf16", "fp8"])
+def test_fused_kv_pool_layout_decode_store_extend(kv, monkeypatch):
+    """The fused [P+1, 2, Hkv, D] pool option (strided k/v views, same slot indexing) gives identical results."""
+    monkeypatch.setattr(G, "FUSED_KV", True)
+    kv_dtype = torch.bfloat16 if kv == "bf16" else torch.float8_e4m3fn
+    tol = (G.BF16_ABS, G.BF16_REL) if kv == "bf16" else (G.FP8_ABS, G.FP8_REL)
+    for hq, hkv, d in ((8, 1, 128), (4, 1, 64), (32, 8, 64)):
+        c = G.random_decode_case(hq, hkv, d, [129, 1, 700, 64], seed=51, kv_dtype=kv_dtype)
+        got, backend, runner, fb, layer = G.run_decode_case(
+            c["q"], c["k_buf"], c["v_buf"], c["req_to_token"], c["req_pool_indices"], c["seq_lens"], c["sm_scale"],
+            0.0, kv_dtype, c["k_scale"], c["v_scale"])
+        pool = runner.token_to_kv_pool
+        assert pool.fused_kv and pool.k_buffer[0].stride(0) == 2 * hkv * d
+        assert pool.v_buffer[0].data_ptr() - pool.k_buffer[0].data_ptr() == hkv * d * pool.k_buffer[0].element_size()
+        G.assert_close(got, _oracle(c), *tol, what=f"fused decode {hq}/{hkv}/{d}")
+    ce = G.random_extend_case(8, 1, 128, [100, 0], [37, 70], seed=52, kv_dtype=kv_dtype)
+    got, runner = G.run_extend_case(ce, save_kv_cache=True)
+    ref = O.extend_ref(ce["q"], ce["k_new"], ce["v_new"], ce["k_buf"], ce["v_buf"], ce["req_to_token"],
+                       ce["req_pool_indices"], ce["seq_lens"], ce["extend_seq_lens"], ce["extend_start_loc"],
+                       ce["sm_scale"], 0.0, kv_dtype, ce["k_scale"], ce["v_scale"])
+    G.assert_close(got, ref, *tol, what="fused extend")
+    kb, vb = ce["k_buf"].clone(), ce["v_buf"].clone()
+    O.set_kv_buffer_ref(kb, vb, ce["out_cache_loc"], ce["k_new"], ce["v_new"], kv_dtype, ce["k_scale"], ce["v_scale"])
+    pool = runner.token_to_kv_pool
+    assert torch.equal(pool.k_buffer[0].cpu().contiguous().view(torch.uint8), kb.view(torch.uint8))
+    assert torch.equal(pool.v_buffer[0].cpu().contiguous().view(torch.uint8), vb.view(torch.uint8))

@@ -284,6 +284,10 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
     }
   };
 
+  // (Round-1 experiment, removed: prefetch.global.L2 / cp.async.bulk.prefetch.L2 of the rows 2-16
+  // tiles ahead of the cp.async front, meant to keep more bytes in flight than shared memory allows.
+  // Measured slower at every distance -- C2 169 -> 187 us at 2 tiles, 295 us at 8 -- so it is gone.)
+
   // ---- consumer: warp -> (kv head, token sub-slice) ---------------------------
   const int w_head = warp % HPC;
   const int w_sub = warp / HPC;
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
       if (pstage >= kStages) pstage -= kStages;
       if (cursor_valid(pc)) {
         issue_tile(pc, pstage);
-        cursor_advance(pc, a);
+          cursor_advance(pc, a);
         if (cursor_valid(pc)) prefetch_slots(pc);
       }
       cp_async_commit();

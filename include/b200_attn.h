@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define B200_ATTN_ABI_VERSION 4
+#define B200_ATTN_ABI_VERSION 5
 
 /* kv_dtype */
 #define B200_KV_BF16 0
@@ -44,8 +44,8 @@ extern "C" {
 #define B200_IDX_I32 0
 #define B200_IDX_I64 1
 /* compute path (b200_attn_config.path) */
-#define B200_PATH_MMA 0  /* GQA-packed tensor-core path (mma.sync m16n8k16) */
-#define B200_PATH_SIMT 1 /* CUDA-core path for small group sizes */
+#define B200_PATH_MMA 0  /* GQA-packed register-level tensor-core path (mma.sync m16n8k16): decode, generic extend */
+#define B200_PATH_TC 1   /* extend only: tcgen05 + TMEM path (head_dim 128, bf16 pool) */
 
 /* error codes (cuda errors are reported as 1000 + cudaError_t) */
 #define B200_OK 0
@@ -128,6 +128,8 @@ typedef struct b200_extend_params {
   float logit_cap;
   const float* k_scale;
   const float* v_scale;
+  int32_t force_path;           /* -1 auto, else B200_PATH_MMA / B200_PATH_TC (tests, bench) */
+  int32_t reserved;
 } b200_extend_params;
 
 int b200_attn_abi_version(void);

@@ -15,11 +15,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libb200attn.so")
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 KV_BF16, KV_FP8_E4M3 = 0, 1
 IDX_I32, IDX_I64 = 0, 1
-PATH_AUTO, PATH_MMA, PATH_SIMT = -1, 0, 1
+PATH_AUTO, PATH_MMA, PATH_TC = -1, 0, 1
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_NOT_PLANNED = 0, 1, 2, 3, 4
 
@@ -85,6 +85,7 @@ class ExtendParams(C.Structure):
         ("kv_dtype", C.c_int32),
         ("sm_scale", C.c_float), ("logit_cap", C.c_float),
         ("k_scale", C.c_void_p), ("v_scale", C.c_void_p),
+        ("force_path", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

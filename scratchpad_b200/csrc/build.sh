@@ -10,7 +10,7 @@ FLAGS=(-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a
        -I"$root/include" -I"$here" ${B200_PTXAS_V:+-Xptxas -v})
 objs=()
 pids=()
-for f in decode store extend; do
+for f in decode store extend extend_tc; do
   "$NVCC" "${FLAGS[@]}" -c "$here/$f.cu" -o "$here/$f.o" &
   pids+=($!)
   objs+=("$here/$f.o")

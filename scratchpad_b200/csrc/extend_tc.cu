@@ -1,0 +1,534 @@
+// Extend / chunked-prefill attention on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// The Blackwell-native path of b200_attn_extend for head_dim 128, bf16 pools (the shape of
+// BASELINE.json config 4: Llama-3.1-8B, 8 x 2048 new tokens on an 8192-token cached prefix).
+// Same semantics as extend.cu / the reference's extend_attention_fwd
+// (scratchpad/nn/attention/triton_attn/extend_attention.py:53-226): query row t of request i sees
+// the gathered prefix slots req_to_token[r, :pre_i] (non-causal) and k_new/v_new[start_i : start_i+t+1].
+//
+// One CTA per SM, 13 warps, warp-specialised:
+//   warps 0-3 / 4-7 : softmax warpgroups for Q tile 0 / 1 (thread = one query row = one TMEM lane)
+//   warp  8         : MMA issuer (one elected thread issues every tcgen05.mma / tcgen05.commit)
+//   warps 9-12      : producers -- gather K/V token rows through the page table with 16-byte cp.async
+//                     straight into the UMMA SWIZZLE_128B canonical layout (page size is 1, so a TMA
+//                     box would be one row; LDGSTS lets 128 threads gather 128 rows at once)
+// A CTA owns 256 query rows = 2 tiles x (128/g tokens x g q-heads of one kv head): GQA packing makes
+// every staged K/V tile serve the whole group and halves K/V shared-memory traffic per flop.
+// TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each; P (bf16) overwrites S in place and is
+// the A operand of the P.V MMA straight from TMEM, so P never touches shared memory or registers of
+// another thread.  Ping-pong schedule on the tensor pipe:
+//   S0(j) S1(j) | PV0(j) S0(j+1) | PV1(j) S1(j+1) | ...
+// so the pipe works on tile 1 while warpgroup 0 does softmax and vice versa.  The O rescale is lazy
+// (only when a row maximum grows by more than 2^8), done by the softmax threads themselves.
+// K/V ring: 5 x 32 KiB slots (K_j, V_j alternate), mbarrier full/empty, freed by tcgen05.commit.
+
+#include "common.cuh"
+
+namespace b200 {
+namespace tc {
+
+constexpr int kD = 128;
+constexpr int kBN = 128;                   // keys per tile
+constexpr int kTileRows = 128;             // rows per Q tile (UMMA M)
+constexpr int kRows = 2 * kTileRows;       // query rows per CTA
+constexpr int kSlots = 5;
+constexpr int kTileBytes = kBN * kD * 2;   // 32 KiB: one K or V tile, or one Q tile
+constexpr int kColBlockBytes = 128 * 128;  // [128 rows x 64 elements] SWIZZLE_128B block
+constexpr int kSoftmaxWarps = 8;
+constexpr int kMmaWarp = 8;
+constexpr int kProdWarp0 = 9;
+constexpr int kProdThreads = 128;
+constexpr int kThreads = (kSoftmaxWarps + 1 + 4) * 32;  // 416
+constexpr int kLag = 2;                    // cp.async groups a producer thread keeps in flight
+
+constexpr int kSmemQ = 0;
+constexpr int kSmemRing = 2 * kTileBytes;
+constexpr int kSmemBar = kSmemRing + kSlots * kTileBytes;  // 229376
+constexpr int kNumBars = 2 * kSlots + 1 + 2 + 2 + 2;
+constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
+constexpr int kSmemBytes = kSmemTmemPtr + 16 + 1024;       // + alignment slack
+
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 384;
+constexpr float kRescaleThreshold = 8.0f;  // log2 domain
+
+// ---- PTX: mbarrier ------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ---- PTX: tcgen05 ---------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// this thread's TMEM lane, 32 consecutive 32-bit columns
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
+// ---- UMMA descriptors (cute/arch/mma_sm100_desc.hpp layout of the bit fields) ----------------------
+// shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3fffu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version
+  d |= static_cast<uint64_t>(2) << 61;  // LayoutType::SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: bf16 x bf16 -> fp32, M x N, A K-major, B K-major or MN-major
+__host__ __device__ constexpr uint32_t instr_desc(int m, int n, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+struct Args {
+  const __nv_bfloat16* q;
+  int64_t q_st, q_sh;
+  const __nv_bfloat16* k_new;
+  const __nv_bfloat16* v_new;
+  int64_t kn_st, kn_sh, vn_st, vn_sh;
+  const uint8_t* kbuf;
+  const uint8_t* vbuf;
+  int64_t k_st_bytes, v_st_bytes;
+  __nv_bfloat16* o;
+  int64_t o_st, o_sh;
+  const int32_t* r2t;
+  int64_t r2t_stride;
+  const void* req_idx;
+  const void* seq_lens;
+  int idx64;
+  const int32_t* ext_lens;
+  const int32_t* ext_start;
+  int hq, hkv, g, bm_t;  // bm_t = tokens per CTA = 256 / g
+  float sm_scale, logit_cap;
+};
+
+// byte offset of 16-byte chunk (row r, element block cb of 64, chunk c of 8) inside a [128 x 128] bf16 tile
+__device__ __forceinline__ uint32_t tile_off(int r, int cb, int c) {
+  return cb * kColBlockBytes + r * 128 + ((c ^ (r & 7)) << 4);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  const int b = blockIdx.z, kvh = blockIdx.y;
+  const int G = a.g, bm_t = a.bm_t;
+  const int ext = __ldg(a.ext_lens + b);
+  const int nqb = (ext + bm_t - 1) / bm_t;
+  const int qb = nqb - 1 - static_cast<int>(blockIdx.x);  // heavy (late) blocks first
+  if (qb < 0) return;
+  const int seq = static_cast<int>(load_idx(a.seq_lens, a.idx64, b));
+  const int pre = seq - ext;
+  const int start = __ldg(a.ext_start + b);
+  const int32_t* row = a.r2t + load_idx(a.req_idx, a.idx64, b) * a.r2t_stride;
+  const int t0 = qb * bm_t;
+  const int t_end = min(ext, t0 + bm_t);
+  const int kv_len = pre + t_end;
+  const int nt = (kv_len + kBN - 1) / kBN;
+  const int live_rows = (t_end - t0) * G;
+
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-byte alignment
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar0 = sbase + kSmemBar;
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (kSlots + s); };
+  const uint32_t bar_q = bar0 + 8u * (2 * kSlots);
+  auto bar_s = [&](int i) { return bar0 + 8u * (2 * kSlots + 1 + i); };
+  auto bar_p = [&](int i) { return bar0 + 8u * (2 * kSlots + 3 + i); };
+  auto bar_pv = [&](int i) { return bar0 + 8u * (2 * kSlots + 5 + i); };
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sgen + kSmemTmemPtr);
+
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      for (int s = 0; s < kSlots; ++s) {
+        mbar_init(bar_full(s), kProdThreads);
+        mbar_init(bar_empty(s), 1);
+      }
+      mbar_init(bar_q, kProdThreads);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_s(i), 1);
+        mbar_init(bar_p(i), 128);
+        mbar_init(bar_pv(i), 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmemTmemPtr), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (warp >= kProdWarp0) {
+    // =========================== producers ===========================================================
+    const int pt = tid - kProdWarp0 * 32;  // 0..127
+    // Q tiles: row R = i*128 + r -> (token t0 + R/G, head kvh*G + R%G)
+    for (int idx = pt; idx < kRows * 16; idx += kProdThreads) {
+      const int R = idx >> 4, ch = idx & 15;
+      const bool live = R < live_rows;
+      const int t = t0 + (live ? R / G : 0), h = kvh * G + (live ? R % G : 0);
+      const __nv_bfloat16* src = a.q + static_cast<int64_t>(start + t) * a.q_st + static_cast<int64_t>(h) * a.q_sh + ch * 8;
+      cp_async16(sbase + kSmemQ + (R >> 7) * kTileBytes + tile_off(R & 127, ch >> 3, ch & 7), src, live ? 16 : 0);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    fence_proxy_async();
+    mbar_arrive(bar_q);
+
+    int slot_cur[4], slot_nxt[4];
+    auto load_slots = [&](int j, int (&dst)[4]) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = j * kBN + u * 32 + lane;
+        dst[u] = (p < pre) ? __ldg(row + p) : 0;
+      }
+    };
+    load_slots(0, slot_cur);
+    const int64_t head_off = static_cast<int64_t>(kvh) * (kD * 2);
+    const int total = 2 * nt;
+    for (int n = 0; n < total; ++n) {
+      const int j = n >> 1, is_v = n & 1, s = n % kSlots;
+      if (!is_v) load_slots(j + 1, slot_nxt);  // one tile of lookahead for the page-table reads
+      mbar_wait(bar_empty(s), ((n / kSlots) & 1) ^ 1);
+      const uint32_t dst0 = sbase + kSmemRing + s * kTileBytes;
+      const uint8_t* pool = is_v ? a.vbuf : a.kbuf;
+      const int64_t pool_st = is_v ? a.v_st_bytes : a.k_st_bytes;
+      const __nv_bfloat16* fresh = is_v ? a.v_new : a.k_new;
+      const int64_t f_st = is_v ? a.vn_st : a.kn_st, f_sh = is_v ? a.vn_sh : a.kn_sh;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int idx = pt + i * kProdThreads;
+        const int r = idx >> 4, ch = idx & 15;  // row r (key), 16-byte chunk ch of its 256-byte head row
+        const int p = j * kBN + r;
+        int sreg = slot_cur[0];
+#pragma unroll
+        for (int u = 1; u < 4; ++u)
+          if ((r >> 5) == u) sreg = slot_cur[u];
+        const int slot = __shfl_sync(0xffffffffu, sreg, r & 31);
+        const void* src;
+        if (p < pre) {
+          src = kv_row_ptr(pool, slot, pool_st) + head_off + ch * 16;
+        } else {
+          const int64_t nidx = start + min(p, kv_len - 1) - pre;
+          src = fresh + nidx * f_st + static_cast<int64_t>(kvh) * f_sh + ch * 8;
+        }
+        cp_async16(dst0 + tile_off(r, ch >> 3, ch & 7), src, p < kv_len ? 16 : 0);
+      }
+      cp_async_commit();
+      if (is_v) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) slot_cur[u] = slot_nxt[u];
+      }
+      if (n >= kLag) {
+        cp_async_wait<kLag>();
+        fence_proxy_async();
+        mbar_arrive(bar_full((n - kLag) % kSlots));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int n = max(total - kLag, 0); n < total; ++n) mbar_arrive(bar_full(n % kSlots));
+  } else if (warp == kMmaWarp) {
+    // =========================== MMA issuer ============================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = instr_desc(kTileRows, kBN, false);
+      constexpr uint32_t idesc_pv = instr_desc(kTileRows, kD, true);
+      const uint32_t q_base = sbase + kSmemQ;
+      const uint32_t ring = sbase + kSmemRing;
+      auto issue_qk = [&](int i, uint32_t k_base) {  // S_i = Q_i . K^T
+        const uint32_t d = tmem + (i ? kColS1 : kColS0);
+#pragma unroll
+        for (int kc = 0; kc < kD / 16; ++kc) {
+          const uint32_t off = (kc >> 2) * kColBlockBytes + (kc & 3) * 32;
+          tc_mma_ss(d, smem_desc(q_base + i * kTileBytes + off, 16, 1024), smem_desc(k_base + off, 16, 1024), idesc_qk,
+                    kc > 0);
+        }
+        tc_commit(bar_s(i));
+      };
+      auto issue_pv = [&](int i, uint32_t v_base, bool first) {  // O_i (+)= P_i . V
+        const uint32_t d = tmem + (i ? kColO1 : kColO0);
+        const uint32_t p = tmem + (i ? kColS1 : kColS0);
+#pragma unroll
+        for (int ks = 0; ks < kBN / 16; ++ks)
+          tc_mma_ts(d, p + ks * 8, smem_desc(v_base + ks * 2048, kColBlockBytes, 1024), idesc_pv, !(first && ks == 0));
+        tc_commit(bar_pv(i));
+      };
+      auto slot_of = [&](int n) { return n % kSlots; };
+      auto wait_full = [&](int n) {
+        mbar_wait(bar_full(slot_of(n)), (n / kSlots) & 1);
+        tc_fence_after();
+      };
+      mbar_wait(bar_q, 0);
+      tc_fence_after();
+      wait_full(0);
+      issue_qk(0, ring + slot_of(0) * kTileBytes);
+      issue_qk(1, ring + slot_of(0) * kTileBytes);
+      tc_commit(bar_empty(slot_of(0)));
+      for (int j = 0; j < nt; ++j) {
+        const int nv = 2 * j + 1, nk = 2 * j + 2;
+        const bool more = j + 1 < nt;
+        wait_full(nv);
+        const uint32_t v_base = ring + slot_of(nv) * kTileBytes;
+        mbar_wait(bar_p(0), j & 1);
+        tc_fence_after();
+        issue_pv(0, v_base, j == 0);
+        if (more) {
+          wait_full(nk);
+          issue_qk(0, ring + slot_of(nk) * kTileBytes);
+        }
+        mbar_wait(bar_p(1), j & 1);
+        tc_fence_after();
+        issue_pv(1, v_base, j == 0);
+        tc_commit(bar_empty(slot_of(nv)));
+        if (more) {
+          issue_qk(1, ring + slot_of(nk) * kTileBytes);
+          tc_commit(bar_empty(slot_of(nk)));
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== softmax warpgroups =======================================================
+    const int i = warp >> 2;                       // Q tile
+    const int r = (warp & 3) * 32 + lane;          // row inside the tile == TMEM lane
+    const int R = i * kTileRows + r;
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t s_addr = lane_base + (i ? kColS1 : kColS0);
+    const uint32_t o_addr = lane_base + (i ? kColO1 : kColO0);
+    const int lim = pre + min(t0 + R / G, t_end - 1);  // causal limit (dead rows behave like the last live token)
+    const float cap = a.logit_cap;
+    const float sc_log2 = a.sm_scale * kLog2e;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(bar_s(i), j & 1);
+      tc_fence_after();
+      const int climit = lim - j * kBN;  // columns <= climit are visible
+      const bool masked = climit < kBN - 1;
+      // pass 1: row maximum of the raw scores
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t v[32];
+        tc_ld32(s_addr + c4 * 32, v);
+        tc_wait_ld();
+        if (masked) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (c4 * 32 + k <= climit) mx = fmaxf(mx, __uint_as_float(v[k]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(v[k]));
+        }
+      }
+      // softcap is monotone, so the maximum of the capped scores is the capped maximum
+      float mxs = cap > 0.f ? softcap(mx * a.sm_scale, cap) * kLog2e : mx * sc_log2;
+      if (j == 0) {
+        m = mxs;  // key 0 is visible to every row, so this is finite
+      } else {
+        const bool need = mxs > m + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          // lazy rescale: O_i *= 2^(m_old - m_new); P.V(j-1) must have landed, P.V(j) waits for our arrive
+          mbar_wait(bar_pv(i), (j - 1) & 1);
+          tc_fence_after();
+          const float mn = fmaxf(m, mxs);
+          const float alpha = ex2(m - mn);
+          m = mn;
+          l *= alpha;
+#pragma unroll 1
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint32_t v[32];
+            tc_ld32(o_addr + c4 * 32, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) * alpha);
+            tc_st32(o_addr + c4 * 32, v);
+          }
+          tc_wait_st();
+        }
+      }
+      // pass 2: P = 2^(s - m) -> bf16, written over S in place (chunk c4 of P lands on columns S chunk <= c4 has left)
+#pragma unroll 1
+      for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t v[32];
+        tc_ld32(s_addr + c4 * 32, v);
+        tc_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          float x0 = __uint_as_float(v[k]), x1 = __uint_as_float(v[k + 1]);
+          float p0, p1;
+          if (cap > 0.f) {
+            p0 = ex2(softcap(x0 * a.sm_scale, cap) * kLog2e - m);
+            p1 = ex2(softcap(x1 * a.sm_scale, cap) * kLog2e - m);
+          } else {
+            p0 = ex2(fmaf(x0, sc_log2, -m));
+            p1 = ex2(fmaf(x1, sc_log2, -m));
+          }
+          if (masked) {
+            if (c4 * 32 + k > climit) p0 = 0.f;
+            if (c4 * 32 + k + 1 > climit) p1 = 0.f;
+          }
+          l += p0 + p1;
+          pk[k >> 1] = pack_bf16x2(p0, p1);
+        }
+        tc_st16(s_addr + c4 * 16, pk);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_p(i));
+    }
+    // epilogue: O_i / l -> bf16 -> global (thread = row)
+    mbar_wait(bar_pv(i), (nt - 1) & 1);
+    tc_fence_after();
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    const bool live = R < live_rows;
+    __nv_bfloat16* op = a.o + static_cast<int64_t>(start + t0 + (live ? R / G : 0)) * a.o_st +
+                        static_cast<int64_t>(kvh * G + (live ? R % G : 0)) * a.o_sh;
+#pragma unroll 1
+    for (int c4 = 0; c4 < 4; ++c4) {
+      uint32_t v[32];
+      tc_ld32(o_addr + c4 * 32, v);
+      tc_wait_ld();
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(v[k]) * inv, __uint_as_float(v[k + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(v[k + 2]) * inv, __uint_as_float(v[k + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(v[k + 4]) * inv, __uint_as_float(v[k + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(v[k + 6]) * inv, __uint_as_float(v[k + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + c4 * 32 + k) = w;
+        }
+      }
+    }
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace tc
+
+// Called by b200_attn_extend (extend.cu) for head_dim 128 / bf16 pools.  Strides and pointers have been validated there.
+int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
+  tc::Args a;
+  a.q = static_cast<const __nv_bfloat16*>(p->q);
+  a.q_st = p->q_stride_t;
+  a.q_sh = p->q_stride_h;
+  a.k_new = static_cast<const __nv_bfloat16*>(p->k_new);
+  a.v_new = static_cast<const __nv_bfloat16*>(p->v_new);
+  a.kn_st = p->kn_stride_t;
+  a.kn_sh = p->kn_stride_h;
+  a.vn_st = p->vn_stride_t;
+  a.vn_sh = p->vn_stride_h;
+  a.kbuf = static_cast<const uint8_t*>(p->k_buf);
+  a.vbuf = static_cast<const uint8_t*>(p->v_buf);
+  a.k_st_bytes = p->k_stride_t * 2;
+  a.v_st_bytes = p->v_stride_t * 2;
+  a.o = static_cast<__nv_bfloat16*>(p->o);
+  a.o_st = p->o_stride_t;
+  a.o_sh = p->o_stride_h;
+  a.r2t = p->req_to_token;
+  a.r2t_stride = p->req_to_token_stride;
+  a.req_idx = p->req_pool_indices;
+  a.seq_lens = p->seq_lens;
+  a.idx64 = p->idx_dtype == B200_IDX_I64;
+  a.ext_lens = p->extend_seq_lens;
+  a.ext_start = p->extend_start_loc;
+  a.hq = p->hq;
+  a.hkv = p->hkv;
+  a.g = p->hq / p->hkv;
+  a.bm_t = tc::kRows / a.g;
+  a.sm_scale = p->sm_scale;
+  a.logit_cap = p->logit_cap;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_TRY(cudaFuncSetAttribute(tc::extend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+    attr_set = true;
+  }
+  const int nqb = (p->max_extend_len + a.bm_t - 1) / a.bm_t;
+  return launch_pdl(tc::extend_tc_kernel, dim3(nqb, p->hkv, p->bs), dim3(tc::kThreads), tc::kSmemBytes, st, a);
+}
+
+}  // namespace b200

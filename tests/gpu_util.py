@@ -130,14 +130,14 @@ def random_extend_case(hq, hkv, d, prefix_lens, extend_lens, seed, kv_dtype=torc
 
 
 def run_extend_case(c, logit_cap=0.0, idx_dtype=torch.int64, save_kv_cache=True, qkv_slices=True,
-                    forward_mode=ForwardMode.EXTEND):
+                    forward_mode=ForwardMode.EXTEND, force_path=-1):
     """Runs one extend case through CudaB200AttnBackend.forward_extend.  Returns (o [T,Hq,Dv] cpu, runner)."""
     t, hq, d = c["q"].shape
     hkv = c["k_buf"].shape[1]
     kv_dtype = c.get("kv_dtype", torch.bfloat16)
     runner = make_runner_from_case(c["k_buf"], c["v_buf"], c["req_to_token"], kv_dtype, c.get("k_scale"),
                                    c.get("v_scale"), tp_hq=hq)
-    backend = CudaB200AttnBackend(runner)
+    backend = CudaB200AttnBackend(runner, force_path=force_path)
     layer = synth.make_layer(runner, 0, logit_cap)
     layer.scaling = c["sm_scale"]
     el = c["extend_seq_lens"].to(torch.int32)

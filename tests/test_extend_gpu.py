@@ -84,3 +84,47 @@ def test_extend_long_prefix_chunk_vs_decode_consistency():
                             c["sm_scale"])[0]
     G.assert_close(got[-1:], dec, G.BF16_ABS, G.BF16_REL, "extend last row vs decode")
     G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, "extend vs oracle")
+
+
+# ---- tcgen05 / TMEM path (head_dim 128, bf16 pool), forced so that small cases reach it too ----------------
+TC_CASES = [
+    (8, 2, 128, [130, 64, 1], [1, 33, 140]),                     # the golden shape family
+    (32, 8, 128, [130, 0, 64, 300], [1, 70, 129, 33]),           # 8B shapes, ragged, prefix 0, ext 1
+    (8, 1, 128, [200, 5], [17, 300]),                            # g = 8
+    (4, 4, 128, [33], [300]),                                    # MHA, several query blocks
+    (6, 2, 128, [100, 256], [90, 128]),                          # g = 3 (dead rows), tile-aligned prefix/extend
+    (32, 8, 128, [1000, 17], [1, 1]),                            # MIXED-mode decode rows
+    (32, 8, 128, [640], [1030]),                                 # many tiles: ring wrap-around, lazy rescale
+]
+
+
+@pytest.mark.parametrize("hq,hkv,d,pre,ext", TC_CASES)
+def test_extend_tcgen05_path_vs_oracle(hq, hkv, d, pre, ext):
+    from scratchpad_b200 import _lib
+    c = G.random_extend_case(hq, hkv, d, pre, ext, seed=hq * 11 + hkv + len(pre))
+    got = G.run_extend_case(c, force_path=_lib.PATH_TC)[0]
+    G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, what=f"tc {hq}/{hkv}/{d}/{pre}/{ext}")
+    ref_path = G.run_extend_case(c, force_path=_lib.PATH_MMA)[0]
+    G.assert_close(got, ref_path, G.BF16_ABS, G.BF16_REL, what="tcgen05 vs mma.sync path")
+
+
+def test_extend_tcgen05_golden_and_logit_cap():
+    from scratchpad_b200 import _lib
+    g = load_golden("extend_gqa4_d128")
+    c = dict(g, req_pool_indices=g["req_pool_indices"].long(), seq_lens=g["seq_lens"].long())
+    got = G.run_extend_case(c, logit_cap=g["logit_cap"], save_kv_cache=False, force_path=_lib.PATH_TC)[0]
+    G.assert_close(got, g["out"], G.BF16_ABS, G.BF16_REL, "tc golden")
+    c = G.random_extend_case(16, 4, 128, [50, 0, 129], [40, 65, 1], seed=3)
+    got = G.run_extend_case(c, logit_cap=30.0, idx_dtype=torch.int32, force_path=_lib.PATH_TC)[0]
+    G.assert_close(got, _oracle(c, 30.0), G.BF16_ABS, G.BF16_REL, "tc logit cap")
+
+
+def test_extend_tcgen05_large_outliers_trigger_rescale():
+    """Scores grow along the sequence so that row maxima jump by more than the lazy-rescale threshold."""
+    from scratchpad_b200 import _lib
+    c = G.random_extend_case(8, 2, 128, [512], [256], seed=9)
+    ramp = torch.linspace(0.2, 3.0, c["k_new"].shape[0]).view(-1, 1, 1)
+    c["k_new"] = (c["k_new"].float() * ramp).to(torch.bfloat16)
+    c["q"] = (c["q"].float() * 2.0).to(torch.bfloat16)
+    got = G.run_extend_case(c, force_path=_lib.PATH_TC)[0]
+    G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, "tc rescale")

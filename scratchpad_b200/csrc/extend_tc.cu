@@ -51,6 +51,7 @@ constexpr int kSmemBytes = kSmemTmemPtr + 16 + 1024;       // + alignment slack
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 384;
 constexpr float kRescaleThreshold = 8.0f;  // log2 domain
+constexpr uint32_t kSuspendHintNs = 20000;  // a waiting thread sleeps in hardware until the phase flips (or this long)
 
 // ---- PTX: mbarrier ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -64,12 +65,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"(kSuspendHintNs)
       : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -133,6 +134,29 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16])
       "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
       "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
+}
+
+// ---- packed fp32 pairs (FFMA2 / FADD2 on sm_100) ---------------------------------------------------
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
+  return d;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  uint32_t a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+  lo = __uint_as_float(a);
+  hi = __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
 // ---- UMMA descriptors (cute/arch/mma_sm100_desc.hpp layout of the bit fields) ----------------------
@@ -271,24 +295,23 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       const int64_t pool_st = is_v ? a.v_st_bytes : a.k_st_bytes;
       const __nv_bfloat16* fresh = is_v ? a.v_new : a.k_new;
       const int64_t f_st = is_v ? a.vn_st : a.kn_st, f_sh = is_v ? a.vn_sh : a.kn_sh;
-#pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        const int idx = pt + i * kProdThreads;
-        const int r = idx >> 4, ch = idx & 15;  // row r (key), 16-byte chunk ch of its 256-byte head row
-        const int p = j * kBN + r;
-        int sreg = slot_cur[0];
 #pragma unroll
-        for (int u = 1; u < 4; ++u)
-          if ((r >> 5) == u) sreg = slot_cur[u];
-        const int slot = __shfl_sync(0xffffffffu, sreg, r & 31);
-        const void* src;
-        if (p < pre) {
-          src = kv_row_ptr(pool, slot, pool_st) + head_off + ch * 16;
-        } else {
-          const int64_t nidx = start + min(p, kv_len - 1) - pre;
-          src = fresh + nidx * f_st + static_cast<int64_t>(kvh) * f_sh + ch * 8;
+      for (int u = 0; u < 4; ++u) {  // rows 32u .. 32u+31: their slot ids live in slot_cur[u]
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int idx = pt + (4 * u + i4) * kProdThreads;
+          const int r = idx >> 4, ch = idx & 15;  // row r (key), 16-byte chunk ch of its 256-byte head row
+          const int p = j * kBN + r;
+          const int slot = __shfl_sync(0xffffffffu, slot_cur[u], r & 31);
+          const void* src;
+          if (p < pre) {
+            src = kv_row_ptr(pool, slot, pool_st) + head_off + ch * 16;
+          } else {
+            const int64_t nidx = start + min(p, kv_len - 1) - pre;
+            src = fresh + nidx * f_st + static_cast<int64_t>(kvh) * f_sh + ch * 8;
+          }
+          cp_async16(dst0 + tile_off(r, ch >> 3, ch & 7), src, p < kv_len ? 16 : 0);
         }
-        cp_async16(dst0 + tile_off(r, ch >> 3, ch & 7), src, p < kv_len ? 16 : 0);
       }
       cp_async_commit();
       if (is_v) {
@@ -380,6 +403,9 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       tc_fence_after();
       const int climit = lim - j * kBN;  // columns <= climit are visible
       const bool masked = climit < kBN - 1;
+      // interior tile for the whole warp: no mask, no soft cap.  Must be warp-uniform: both branches
+      // below issue .sync.aligned tcgen05.ld/st, which a divergent warp would deadlock on.
+      const bool fast = !__any_sync(0xffffffffu, masked) && !(cap > 0.f);
       // pass 1: row maximum of the raw scores
       float mx = -INFINITY;
 #pragma unroll 1
@@ -392,8 +418,13 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
           for (int k = 0; k < 32; ++k)
             if (c4 * 32 + k <= climit) mx = fmaxf(mx, __uint_as_float(v[k]));
         } else {
+          float m0 = mx, m1 = -INFINITY;
 #pragma unroll
-          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(v[k]));
+          for (int k = 0; k < 32; k += 4) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[k]), __uint_as_float(v[k + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])));
+          }
+          mx = fmaxf(m0, m1);
         }
       }
       // softcap is monotone, so the maximum of the capped scores is the capped maximum
@@ -423,31 +454,54 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
         }
       }
       // pass 2: P = 2^(s - m) -> bf16, written over S in place (chunk c4 of P lands on columns S chunk <= c4 has left)
+      if (fast) {
+        const uint64_t sc2 = pack_f32x2(sc_log2, sc_log2), nm2 = pack_f32x2(-m, -m);
+        uint64_t l2 = pack_f32x2(l, 0.f);
 #pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t v[32];
-        tc_ld32(s_addr + c4 * 32, v);
-        tc_wait_ld();
-        uint32_t pk[16];
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t v[32];
+          tc_ld32(s_addr + c4 * 32, v);
+          tc_wait_ld();
+          uint32_t pk[16];
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          float x0 = __uint_as_float(v[k]), x1 = __uint_as_float(v[k + 1]);
-          float p0, p1;
-          if (cap > 0.f) {
-            p0 = ex2(softcap(x0 * a.sm_scale, cap) * kLog2e - m);
-            p1 = ex2(softcap(x1 * a.sm_scale, cap) * kLog2e - m);
-          } else {
-            p0 = ex2(fmaf(x0, sc_log2, -m));
-            p1 = ex2(fmaf(x1, sc_log2, -m));
+          for (int k = 0; k < 32; k += 2) {
+            const uint64_t y = fma_f32x2(pack_f32x2(__uint_as_float(v[k]), __uint_as_float(v[k + 1])), sc2, nm2);
+            float y0, y1;
+            unpack_f32x2(y, y0, y1);
+            const float p0 = ex2(y0), p1 = ex2(y1);
+            l2 = add_f32x2(l2, pack_f32x2(p0, p1));
+            pk[k >> 1] = pack_bf16x2(p0, p1);
           }
-          if (masked) {
+          tc_st16(s_addr + c4 * 16, pk);
+        }
+        float la, lb;
+        unpack_f32x2(l2, la, lb);
+        l = la + lb;
+      } else {
+#pragma unroll 1
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t v[32];
+          tc_ld32(s_addr + c4 * 32, v);
+          tc_wait_ld();
+          uint32_t pk[16];
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            float x0 = __uint_as_float(v[k]), x1 = __uint_as_float(v[k + 1]);
+            float p0, p1;
+            if (cap > 0.f) {
+              p0 = ex2(softcap(x0 * a.sm_scale, cap) * kLog2e - m);
+              p1 = ex2(softcap(x1 * a.sm_scale, cap) * kLog2e - m);
+            } else {
+              p0 = ex2(fmaf(x0, sc_log2, -m));
+              p1 = ex2(fmaf(x1, sc_log2, -m));
+            }
             if (c4 * 32 + k > climit) p0 = 0.f;
             if (c4 * 32 + k + 1 > climit) p1 = 0.f;
+            l += p0 + p1;
+            pk[k >> 1] = pack_bf16x2(p0, p1);
           }
-          l += p0 + p1;
-          pk[k >> 1] = pack_bf16x2(p0, p1);
+          tc_st16(s_addr + c4 * 16, pk);
         }
-        tc_st16(s_addr + c4 * 16, pk);
       }
       tc_wait_st();
       tc_fence_before();

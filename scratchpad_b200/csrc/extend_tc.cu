@@ -6,12 +6,22 @@
 // (scratchpad/nn/attention/triton_attn/extend_attention.py:53-226): query row t of request i sees
 // the gathered prefix slots req_to_token[r, :pre_i] (non-causal) and k_new/v_new[start_i : start_i+t+1].
 //
-// One CTA per SM, 13 warps, warp-specialised:
-//   warps 0-3 / 4-7 : softmax warpgroups for Q tile 0 / 1 (thread = one query row = one TMEM lane)
+// One CTA per SM, 10 warps, warp-specialised:
+//   warps 0-3 / 4-7 : softmax warpgroups for Q tile 0 / 1 (thread = one query row = one TMEM lane);
+//                     a thread holds its whole 128-column S row in registers (one TMEM read per tile)
 //   warp  8         : MMA issuer (one elected thread issues every tcgen05.mma / tcgen05.commit)
-//   warps 9-12      : producers -- gather K/V token rows through the page table with 16-byte cp.async
-//                     straight into the UMMA SWIZZLE_128B canonical layout (page size is 1, so a TMA
-//                     box would be one row; LDGSTS lets 128 threads gather 128 rows at once)
+//   warps 9-11      : idle (they only pad warpgroup 2 so that setmaxnreg can move its registers)
+//   warps 12-15     : producers -- gather K/V token rows through the page table with 16-byte cp.async
+//                     (LDGSTS) straight into the UMMA SWIZZLE_128B canonical layout.  Page size is 1, so
+//                     the gather unit is one 256-byte (token, kv-head) row; 16 lanes cover a row, a thread
+//                     always works on rows with the same (row & 7), so its swizzled destination is a
+//                     per-thread constant + 1 KiB per row and a copy costs ~3 instructions.
+//                     (The TMA row gather, cp.async.bulk.tensor.2d.tile::gather4 + SWIZZLE_128B, was built
+//                     and measured first: correct -- tools/gather4_probe.cu -- but the TMA unit retires one
+//                     128-byte row segment per ~18 clk, 4500 clk per 32 KiB tile, 2x slower than the whole
+//                     K/V budget of a tile; see DESIGN.md.)
+// Registers: 512 threads x 128 at launch; setmaxnreg gives the softmax warpgroups 192 and leaves 64 to the
+// MMA/producer warpgroups.
 // A CTA owns 256 query rows = 2 tiles x (128/g tokens x g q-heads of one kv head): GQA packing makes
 // every staged K/V tile serve the whole group and halves K/V shared-memory traffic per flop.
 // TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each; P (bf16) overwrites S in place and is
@@ -20,7 +30,7 @@
 //   S0(j) S1(j) | PV0(j) S0(j+1) | PV1(j) S1(j+1) | ...
 // so the pipe works on tile 1 while warpgroup 0 does softmax and vice versa.  The O rescale is lazy
 // (only when a row maximum grows by more than 2^8), done by the softmax threads themselves.
-// K/V ring: 5 x 32 KiB slots (K_j, V_j alternate), mbarrier full/empty, freed by tcgen05.commit.
+// K/V ring: 5 x 32 KiB slots (K_j, V_j alternate), mbarrier full (TMA complete_tx) / empty (tcgen05.commit).
 
 #include "common.cuh"
 
@@ -36,10 +46,11 @@ constexpr int kTileBytes = kBN * kD * 2;   // 32 KiB: one K or V tile, or one Q 
 constexpr int kColBlockBytes = 128 * 128;  // [128 rows x 64 elements] SWIZZLE_128B block
 constexpr int kSoftmaxWarps = 8;
 constexpr int kMmaWarp = 8;
-constexpr int kProdWarp0 = 9;
+constexpr int kProdWarp0 = 12;
 constexpr int kProdThreads = 128;
-constexpr int kThreads = (kSoftmaxWarps + 1 + 4) * 32;  // 416
+constexpr int kThreads = 512;              // 4 warpgroups: softmax 0, softmax 1, MMA (+3 idle warps), producers
 constexpr int kLag = 2;                    // cp.async groups a producer thread keeps in flight
+constexpr int kRegsSoftmax = 192, kRegsOther = 64;  // 256*192 + 256*64 = 64 Ki registers
 
 constexpr int kSmemQ = 0;
 constexpr int kSmemRing = 2 * kTileBytes;
@@ -107,7 +118,7 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       : "memory");
 }
 // this thread's TMEM lane, 32 consecutive 32-bit columns
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -118,7 +129,7 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* v) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
       "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
@@ -128,7 +139,7 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32])
       "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
-__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* v) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
       "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
@@ -170,11 +181,36 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= static_cast<uint64_t>(2) << 61;  // LayoutType::SWIZZLE_128B
   return d;
 }
+// the same descriptor split in two words: low = start address | LBO (advancing the start address by
+// `bytes` is low + (bytes >> 4); shared-memory addresses stay below the 14-bit field), high = SBO | version | swizzle
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3fffu) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
+}
+__device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t sbo_bytes) {
+  const uint32_t hi = ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14) | (2u << 29);
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
 // instruction descriptor: bf16 x bf16 -> fp32, M x N, A K-major, B K-major or MN-major
 __host__ __device__ constexpr uint32_t instr_desc(int m, int n, bool b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
+
+// ---- optional timeline trace of CTA (0,0,0) (build with -DB200_TC_TRACE; tools/tc_trace.py) ----------------
+#ifdef B200_TC_TRACE
+constexpr int kTraceEvents = 12, kTraceLen = 128;
+__device__ long long g_trace[kTraceEvents][kTraceLen];
+#define TC_TRACE(ev, idx)                                                                                  \
+  do {                                                                                                     \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx) < kTraceLen) g_trace[ev][idx] = clock64(); \
+  } while (0)
+#else
+#define TC_TRACE(ev, idx) \
+  do {                    \
+  } while (0)
+#endif
 
 struct Args {
   const __nv_bfloat16* q;
@@ -242,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
         mbar_init(bar_full(s), kProdThreads);
         mbar_init(bar_empty(s), 1);
       }
-      mbar_init(bar_q, kProdThreads);
+      mbar_init(bar_q, kSoftmaxWarps * 32);
       for (int i = 0; i < 2; ++i) {
         mbar_init(bar_s(i), 1);
         mbar_init(bar_p(i), 128);
@@ -261,63 +297,40 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
 
   if (warp >= kProdWarp0) {
     // =========================== producers ===========================================================
-    const int pt = tid - kProdWarp0 * 32;  // 0..127
-    // Q tiles: row R = i*128 + r -> (token t0 + R/G, head kvh*G + R%G)
-    for (int idx = pt; idx < kRows * 16; idx += kProdThreads) {
-      const int R = idx >> 4, ch = idx & 15;
-      const bool live = R < live_rows;
-      const int t = t0 + (live ? R / G : 0), h = kvh * G + (live ? R % G : 0);
-      const __nv_bfloat16* src = a.q + static_cast<int64_t>(start + t) * a.q_st + static_cast<int64_t>(h) * a.q_sh + ch * 8;
-      cp_async16(sbase + kSmemQ + (R >> 7) * kTileBytes + tile_off(R & 127, ch >> 3, ch & 7), src, live ? 16 : 0);
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    fence_proxy_async();
-    mbar_arrive(bar_q);
-
-    int slot_cur[4], slot_nxt[4];
-    auto load_slots = [&](int j, int (&dst)[4]) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int p = j * kBN + u * 32 + lane;
-        dst[u] = (p < pre) ? __ldg(row + p) : 0;
-      }
-    };
-    load_slots(0, slot_cur);
-    const int64_t head_off = static_cast<int64_t>(kvh) * (kD * 2);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
+    // lanes 0-15 / 16-31 of warp pw copy the 16 chunks of rows 8q + 2pw / 8q + 2pw + 1, q = 0..15
+    const int pw = warp - kProdWarp0, ch = lane & 15;
+    const int r7 = 2 * pw + (lane >> 4);  // (row & 7) of every row this thread copies
+    const uint32_t dst_thread = (ch >> 3) * kColBlockBytes + r7 * 128 + (((ch & 7) ^ r7) << 4);
+    const int64_t col_bytes = static_cast<int64_t>(kvh) * (kD * 2) + ch * 16;
     const int total = 2 * nt;
     for (int n = 0; n < total; ++n) {
       const int j = n >> 1, is_v = n & 1, s = n % kSlots;
-      if (!is_v) load_slots(j + 1, slot_nxt);  // one tile of lookahead for the page-table reads
-      mbar_wait(bar_empty(s), ((n / kSlots) & 1) ^ 1);
-      const uint32_t dst0 = sbase + kSmemRing + s * kTileBytes;
-      const uint8_t* pool = is_v ? a.vbuf : a.kbuf;
+      const uint8_t* pool = (is_v ? a.vbuf : a.kbuf) + col_bytes;
       const int64_t pool_st = is_v ? a.v_st_bytes : a.k_st_bytes;
-      const __nv_bfloat16* fresh = is_v ? a.v_new : a.k_new;
-      const int64_t f_st = is_v ? a.vn_st : a.kn_st, f_sh = is_v ? a.vn_sh : a.kn_sh;
+      const int p0 = j * kBN + r7;
+      mbar_wait(bar_empty(s), ((n / kSlots) & 1) ^ 1);
+      if (tid == kProdWarp0 * 32) TC_TRACE(0, n);
+      const uint32_t dst0 = sbase + kSmemRing + s * kTileBytes + dst_thread;
+      if ((j + 1) * kBN <= pre) {
+        // tile of cached-prefix keys only: page-table lookup (L1-resident after the first touch) + one copy
+        int slot[16];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {  // rows 32u .. 32u+31: their slot ids live in slot_cur[u]
+        for (int q = 0; q < 16; ++q) slot[q] = __ldg(row + p0 + 8 * q);
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          const int idx = pt + (4 * u + i4) * kProdThreads;
-          const int r = idx >> 4, ch = idx & 15;  // row r (key), 16-byte chunk ch of its 256-byte head row
-          const int p = j * kBN + r;
-          const int slot = __shfl_sync(0xffffffffu, slot_cur[u], r & 31);
-          const void* src;
-          if (p < pre) {
-            src = kv_row_ptr(pool, slot, pool_st) + head_off + ch * 16;
-          } else {
-            const int64_t nidx = start + min(p, kv_len - 1) - pre;
-            src = fresh + nidx * f_st + static_cast<int64_t>(kvh) * f_sh + ch * 8;
-          }
-          cp_async16(dst0 + tile_off(r, ch >> 3, ch & 7), src, p < kv_len ? 16 : 0);
+        for (int q = 0; q < 16; ++q) cp_async16(dst0 + q * 1024, kv_row_ptr(pool, slot[q], pool_st), 16);
+      } else {
+        const uint8_t* fresh = reinterpret_cast<const uint8_t*>(is_v ? a.v_new : a.k_new) + col_bytes;
+        const int64_t f_st = (is_v ? a.vn_st : a.kn_st) * 2;
+#pragma unroll 4
+        for (int q = 0; q < 16; ++q) {
+          const int p = p0 + 8 * q, pc = min(p, kv_len - 1);
+          const uint8_t* src = pc < pre ? kv_row_ptr(pool, __ldg(row + pc), pool_st) : fresh + static_cast<int64_t>(start + pc - pre) * f_st;
+          cp_async16(dst0 + q * 1024, src, p < kv_len ? 16 : 0);
         }
       }
       cp_async_commit();
-      if (is_v) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) slot_cur[u] = slot_nxt[u];
-      }
+      if (tid == kProdWarp0 * 32) TC_TRACE(1, n);
       if (n >= kLag) {
         cp_async_wait<kLag>();
         fence_proxy_async();
@@ -329,27 +342,37 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     for (int n = max(total - kLag, 0); n < total; ++n) mbar_arrive(bar_full(n % kSlots));
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ============================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
     if (lane == 0) {
       constexpr uint32_t idesc_qk = instr_desc(kTileRows, kBN, false);
       constexpr uint32_t idesc_pv = instr_desc(kTileRows, kD, true);
       const uint32_t q_base = sbase + kSmemQ;
       const uint32_t ring = sbase + kSmemRing;
+      // Descriptors are rebuilt from one opaque base per issue (an add per MMA) instead of being kept
+      // live across the loop: this warp runs on 64 registers and a spilled descriptor is an LDL on the
+      // single issuing thread.
+      auto opaque = [](uint32_t x) {
+        uint32_t y;
+        asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+        return y;
+      };
       auto issue_qk = [&](int i, uint32_t k_base) {  // S_i = Q_i . K^T
         const uint32_t d = tmem + (i ? kColS1 : kColS0);
+        const uint32_t qlo = desc_lo(opaque(q_base + i * kTileBytes), 16), klo = desc_lo(opaque(k_base), 16);
 #pragma unroll
         for (int kc = 0; kc < kD / 16; ++kc) {
-          const uint32_t off = (kc >> 2) * kColBlockBytes + (kc & 3) * 32;
-          tc_mma_ss(d, smem_desc(q_base + i * kTileBytes + off, 16, 1024), smem_desc(k_base + off, 16, 1024), idesc_qk,
-                    kc > 0);
+          const uint32_t off16 = ((kc >> 2) * kColBlockBytes + (kc & 3) * 32) >> 4;
+          tc_mma_ss(d, desc_from(qlo + off16, 1024), desc_from(klo + off16, 1024), idesc_qk, kc > 0);
         }
         tc_commit(bar_s(i));
       };
       auto issue_pv = [&](int i, uint32_t v_base, bool first) {  // O_i (+)= P_i . V
         const uint32_t d = tmem + (i ? kColO1 : kColO0);
         const uint32_t p = tmem + (i ? kColS1 : kColS0);
+        const uint32_t vlo = desc_lo(opaque(v_base), kColBlockBytes);
 #pragma unroll
         for (int ks = 0; ks < kBN / 16; ++ks)
-          tc_mma_ts(d, p + ks * 8, smem_desc(v_base + ks * 2048, kColBlockBytes, 1024), idesc_pv, !(first && ks == 0));
+          tc_mma_ts(d, p + ks * 8, desc_from(vlo + ((ks * 2048) >> 4), 1024), idesc_pv, !(first && ks == 0));
         tc_commit(bar_pv(i));
       };
       auto slot_of = [&](int n) { return n % kSlots; };
@@ -367,16 +390,20 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
         const int nv = 2 * j + 1, nk = 2 * j + 2;
         const bool more = j + 1 < nt;
         wait_full(nv);
+        TC_TRACE(2, j);
         const uint32_t v_base = ring + slot_of(nv) * kTileBytes;
         mbar_wait(bar_p(0), j & 1);
         tc_fence_after();
+        TC_TRACE(3, j);
         issue_pv(0, v_base, j == 0);
         if (more) {
           wait_full(nk);
+          TC_TRACE(4, j);
           issue_qk(0, ring + slot_of(nk) * kTileBytes);
         }
         mbar_wait(bar_p(1), j & 1);
         tc_fence_after();
+        TC_TRACE(5, j);
         issue_pv(1, v_base, j == 0);
         tc_commit(bar_empty(slot_of(nv)));
         if (more) {
@@ -386,8 +413,25 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       }
     }
     __syncwarp();
+  } else if (warp > kMmaWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));  // idle padding warps of warpgroup 2
   } else {
     // =========================== softmax warpgroups =======================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
+    // Q tiles first (the 256 softmax threads are idle until the first S lands):
+    // row R = i*128 + r -> (token t0 + R/G, head kvh*G + R%G)
+    for (int idx = tid; idx < kRows * 16; idx += kSoftmaxWarps * 32) {
+      const int R = idx >> 4, ch = idx & 15;
+      const bool live = R < live_rows;
+      const int t = t0 + (live ? R / G : 0), h = kvh * G + (live ? R % G : 0);
+      const __nv_bfloat16* src = a.q + static_cast<int64_t>(start + t) * a.q_st + static_cast<int64_t>(h) * a.q_sh + ch * 8;
+      cp_async16(sbase + kSmemQ + (R >> 7) * kTileBytes + tile_off(R & 127, ch >> 3, ch & 7), src, live ? 16 : 0);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    fence_proxy_async();
+    mbar_arrive(bar_q);
+
     const int i = warp >> 2;                       // Q tile
     const int r = (warp & 3) * 32 + lane;          // row inside the tile == TMEM lane
     const int R = i * kTileRows + r;
@@ -401,31 +445,35 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     for (int j = 0; j < nt; ++j) {
       mbar_wait(bar_s(i), j & 1);
       tc_fence_after();
+      if (r == 0) TC_TRACE(6 + 3 * i, j);
       const int climit = lim - j * kBN;  // columns <= climit are visible
       const bool masked = climit < kBN - 1;
       // interior tile for the whole warp: no mask, no soft cap.  Must be warp-uniform: both branches
       // below issue .sync.aligned tcgen05.ld/st, which a divergent warp would deadlock on.
       const bool fast = !__any_sync(0xffffffffu, masked) && !(cap > 0.f);
-      // pass 1: row maximum of the raw scores
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t v[32];
-        tc_ld32(s_addr + c4 * 32, v);
-        tc_wait_ld();
-        if (masked) {
+      uint32_t v[kBN];  // this row of S, raw scores
+      tc_ld32(s_addr, v);
+      tc_ld32(s_addr + 32, v + 32);
+      tc_ld32(s_addr + 64, v + 64);
+      tc_ld32(s_addr + 96, v + 96);
+      tc_wait_ld();
+      if (r == 0) TC_TRACE(7 + 3 * i, j);
+      float mx;
+      if (masked) {
+        mx = -INFINITY;
 #pragma unroll
-          for (int k = 0; k < 32; ++k)
-            if (c4 * 32 + k <= climit) mx = fmaxf(mx, __uint_as_float(v[k]));
-        } else {
-          float m0 = mx, m1 = -INFINITY;
+        for (int k = 0; k < kBN; ++k)
+          if (k <= climit) mx = fmaxf(mx, __uint_as_float(v[k]));
+      } else {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-          for (int k = 0; k < 32; k += 4) {
-            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[k]), __uint_as_float(v[k + 1])));
-            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])));
-          }
-          mx = fmaxf(m0, m1);
+        for (int k = 0; k < kBN; k += 8) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(v[k]), __uint_as_float(v[k + 1])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])));
+          m2 = fmaxf(m2, fmaxf(__uint_as_float(v[k + 4]), __uint_as_float(v[k + 5])));
+          m3 = fmaxf(m3, fmaxf(__uint_as_float(v[k + 6]), __uint_as_float(v[k + 7])));
         }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
       // softcap is monotone, so the maximum of the capped scores is the capped maximum
       float mxs = cap > 0.f ? softcap(mx * a.sm_scale, cap) * kLog2e : mx * sc_log2;
@@ -443,29 +491,27 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
           l *= alpha;
 #pragma unroll 1
           for (int c4 = 0; c4 < 4; ++c4) {
-            uint32_t v[32];
-            tc_ld32(o_addr + c4 * 32, v);
+            uint32_t w[32];
+            tc_ld32(o_addr + c4 * 32, w);
             tc_wait_ld();
 #pragma unroll
-            for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) * alpha);
-            tc_st32(o_addr + c4 * 32, v);
+            for (int k = 0; k < 32; ++k) w[k] = __float_as_uint(__uint_as_float(w[k]) * alpha);
+            tc_st32(o_addr + c4 * 32, w);
           }
           tc_wait_st();
         }
       }
-      // pass 2: P = 2^(s - m) -> bf16, written over S in place (chunk c4 of P lands on columns S chunk <= c4 has left)
+      // P = 2^(s - m) -> bf16, written over S in place (P is the TMEM A operand of the P.V MMA)
       if (fast) {
         const uint64_t sc2 = pack_f32x2(sc_log2, sc_log2), nm2 = pack_f32x2(-m, -m);
         uint64_t l2 = pack_f32x2(l, 0.f);
-#pragma unroll 1
+#pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
-          uint32_t v[32];
-          tc_ld32(s_addr + c4 * 32, v);
-          tc_wait_ld();
           uint32_t pk[16];
 #pragma unroll
           for (int k = 0; k < 32; k += 2) {
-            const uint64_t y = fma_f32x2(pack_f32x2(__uint_as_float(v[k]), __uint_as_float(v[k + 1])), sc2, nm2);
+            const uint64_t y =
+                fma_f32x2(pack_f32x2(__uint_as_float(v[c4 * 32 + k]), __uint_as_float(v[c4 * 32 + k + 1])), sc2, nm2);
             float y0, y1;
             unpack_f32x2(y, y0, y1);
             const float p0 = ex2(y0), p1 = ex2(y1);
@@ -478,15 +524,12 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
         unpack_f32x2(l2, la, lb);
         l = la + lb;
       } else {
-#pragma unroll 1
+#pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
-          uint32_t v[32];
-          tc_ld32(s_addr + c4 * 32, v);
-          tc_wait_ld();
           uint32_t pk[16];
 #pragma unroll
           for (int k = 0; k < 32; k += 2) {
-            float x0 = __uint_as_float(v[k]), x1 = __uint_as_float(v[k + 1]);
+            float x0 = __uint_as_float(v[c4 * 32 + k]), x1 = __uint_as_float(v[c4 * 32 + k + 1]);
             float p0, p1;
             if (cap > 0.f) {
               p0 = ex2(softcap(x0 * a.sm_scale, cap) * kLog2e - m);
@@ -506,6 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p(i));
+      if (r == 0) TC_TRACE(8 + 3 * i, j);
     }
     // epilogue: O_i / l -> bf16 -> global (thread = row)
     mbar_wait(bar_pv(i), (nt - 1) & 1);
@@ -516,18 +560,18 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
                         static_cast<int64_t>(kvh * G + (live ? R % G : 0)) * a.o_sh;
 #pragma unroll 1
     for (int c4 = 0; c4 < 4; ++c4) {
-      uint32_t v[32];
-      tc_ld32(o_addr + c4 * 32, v);
+      uint32_t w[32];
+      tc_ld32(o_addr + c4 * 32, w);
       tc_wait_ld();
       if (live) {
 #pragma unroll
         for (int k = 0; k < 32; k += 8) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(v[k]) * inv, __uint_as_float(v[k + 1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(v[k + 2]) * inv, __uint_as_float(v[k + 3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(v[k + 4]) * inv, __uint_as_float(v[k + 5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(v[k + 6]) * inv, __uint_as_float(v[k + 7]) * inv);
-          *reinterpret_cast<uint4*>(op + c4 * 32 + k) = w;
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(w[k]) * inv, __uint_as_float(w[k + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(w[k + 2]) * inv, __uint_as_float(w[k + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(w[k + 4]) * inv, __uint_as_float(w[k + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(w[k + 6]) * inv, __uint_as_float(w[k + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + c4 * 32 + k) = u;
         }
       }
     }
@@ -543,6 +587,12 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
 }
 
 }  // namespace tc
+
+#ifdef B200_TC_TRACE
+extern "C" int b200_debug_tc_trace_read(long long* host_dst) {
+  return cudaMemcpyFromSymbol(host_dst, tc::g_trace, sizeof(tc::g_trace)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 // Called by b200_attn_extend (extend.cu) for head_dim 128 / bf16 pools.  Strides and pointers have been validated there.
 int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {

@@ -50,6 +50,13 @@ constexpr int kProdWarp0 = 12;
 constexpr int kProdThreads = 128;
 constexpr int kThreads = 512;              // 4 warpgroups: softmax 0, softmax 1, MMA (+3 idle warps), producers
 constexpr int kLag = 2;                    // cp.async groups a producer thread keeps in flight
+#ifndef B200_TC_POLY
+#define B200_TC_POLY 0
+#endif
+// of every 4 score pairs, this many take the FMA-pipe exp2.  Measured on C4 (gpurun_out/r1s,r1t,r1u): 0 -> 1049,
+// 1 -> 1021, 2 -> 940 TFLOP/s: FFMA2/FADD2 retire 2 clk per warp instruction, so the polynomial costs the FMA
+// pipe what the MUFU saves; kept as a build option (B200_TC_POLY) for re-tuning.
+constexpr int kPolyPairsOf4 = B200_TC_POLY;
 constexpr int kRegsSoftmax = 192, kRegsOther = 64;  // 256*192 + 256*64 = 64 Ki registers
 
 constexpr int kSmemQ = 0;
@@ -170,6 +177,30 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   return d;
 }
 
+// 2^x for a pair, on the FMA pipe instead of the MUFU: x = n + f with n = round(x), f in [-0.5, 0.5];
+// 2^f by a degree-3 minimax polynomial (relative error 7.5e-5, 50x below the bf16 rounding of P) and
+// 2^n by adding n to the exponent field.  The MUFU retires 4 ex2 per clock and SM sub-partition, which
+// for head_dim 128 is exactly as many clocks as the two MMAs of the tile take; moving a share of the
+// exponentials to the (otherwise idle) FMA pipe takes the softmax off the critical path.
+// x must be <= ~120 (it is <= kRescaleThreshold) and is clamped to >= -126 here.
+__device__ __forceinline__ void exp2_poly_x2(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  x2 = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t magic = pack_f32x2(12582912.f, 12582912.f);  // 1.5 * 2^23: x + magic has round(x) in its low mantissa bits
+  const uint64_t t = add_f32x2(x2, magic);
+  const uint64_t nf = add_f32x2(t, pack_f32x2(-12582912.f, -12582912.f));
+  const uint64_t f = fma_f32x2(nf, pack_f32x2(-1.f, -1.f), x2);
+  uint64_t p = fma_f32x2(f, pack_f32x2(0.0551716685f, 0.0551716685f), pack_f32x2(0.2426111251f, 0.2426111251f));
+  p = fma_f32x2(p, f, pack_f32x2(0.6932609678f, 0.6932609678f));
+  p = fma_f32x2(p, f, pack_f32x2(0.9999280572f, 0.9999280572f));
+  float t0, t1, q0, q1;
+  unpack_f32x2(t, t0, t1);
+  unpack_f32x2(p, q0, q1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+
 // ---- UMMA descriptors (cute/arch/mma_sm100_desc.hpp layout of the bit fields) ----------------------
 // shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -200,7 +231,7 @@ __host__ __device__ constexpr uint32_t instr_desc(int m, int n, bool b_mn_major)
 
 // ---- optional timeline trace of CTA (0,0,0) (build with -DB200_TC_TRACE; tools/tc_trace.py) ----------------
 #ifdef B200_TC_TRACE
-constexpr int kTraceEvents = 12, kTraceLen = 128;
+constexpr int kTraceEvents = 16, kTraceLen = 128;
 __device__ long long g_trace[kTraceEvents][kTraceLen];
 #define TC_TRACE(ev, idx)                                                                                  \
   do {                                                                                                     \
@@ -343,37 +374,32 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ============================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
-    if (lane == 0) {
+    // The whole warp runs this loop so that every address / descriptor is warp-uniform (uniform registers,
+    // no R2UR in front of each UTCHMMA); only the tcgen05.mma / tcgen05.commit themselves are issued by lane 0.
+    const bool leader = lane == 0;
+    {
       constexpr uint32_t idesc_qk = instr_desc(kTileRows, kBN, false);
       constexpr uint32_t idesc_pv = instr_desc(kTileRows, kD, true);
       const uint32_t q_base = sbase + kSmemQ;
       const uint32_t ring = sbase + kSmemRing;
-      // Descriptors are rebuilt from one opaque base per issue (an add per MMA) instead of being kept
-      // live across the loop: this warp runs on 64 registers and a spilled descriptor is an LDL on the
-      // single issuing thread.
-      auto opaque = [](uint32_t x) {
-        uint32_t y;
-        asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
-        return y;
-      };
       auto issue_qk = [&](int i, uint32_t k_base) {  // S_i = Q_i . K^T
         const uint32_t d = tmem + (i ? kColS1 : kColS0);
-        const uint32_t qlo = desc_lo(opaque(q_base + i * kTileBytes), 16), klo = desc_lo(opaque(k_base), 16);
+        const uint32_t qlo = desc_lo(q_base + i * kTileBytes, 16), klo = desc_lo(k_base, 16);
 #pragma unroll
         for (int kc = 0; kc < kD / 16; ++kc) {
           const uint32_t off16 = ((kc >> 2) * kColBlockBytes + (kc & 3) * 32) >> 4;
-          tc_mma_ss(d, desc_from(qlo + off16, 1024), desc_from(klo + off16, 1024), idesc_qk, kc > 0);
+          if (leader) tc_mma_ss(d, desc_from(qlo + off16, 1024), desc_from(klo + off16, 1024), idesc_qk, kc > 0);
         }
-        tc_commit(bar_s(i));
+        if (leader) tc_commit(bar_s(i));
       };
       auto issue_pv = [&](int i, uint32_t v_base, bool first) {  // O_i (+)= P_i . V
         const uint32_t d = tmem + (i ? kColO1 : kColO0);
         const uint32_t p = tmem + (i ? kColS1 : kColS0);
-        const uint32_t vlo = desc_lo(opaque(v_base), kColBlockBytes);
+        const uint32_t vlo = desc_lo(v_base, kColBlockBytes);
 #pragma unroll
         for (int ks = 0; ks < kBN / 16; ++ks)
-          tc_mma_ts(d, p + ks * 8, desc_from(vlo + ((ks * 2048) >> 4), 1024), idesc_pv, !(first && ks == 0));
-        tc_commit(bar_pv(i));
+          if (leader) tc_mma_ts(d, p + ks * 8, desc_from(vlo + ((ks * 2048) >> 4), 1024), idesc_pv, !(first && ks == 0));
+        if (leader) tc_commit(bar_pv(i));
       };
       auto slot_of = [&](int n) { return n % kSlots; };
       auto wait_full = [&](int n) {
@@ -385,30 +411,30 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       wait_full(0);
       issue_qk(0, ring + slot_of(0) * kTileBytes);
       issue_qk(1, ring + slot_of(0) * kTileBytes);
-      tc_commit(bar_empty(slot_of(0)));
+      if (leader) tc_commit(bar_empty(slot_of(0)));
       for (int j = 0; j < nt; ++j) {
         const int nv = 2 * j + 1, nk = 2 * j + 2;
         const bool more = j + 1 < nt;
         wait_full(nv);
-        TC_TRACE(2, j);
+        if (leader) TC_TRACE(2, j);
         const uint32_t v_base = ring + slot_of(nv) * kTileBytes;
         mbar_wait(bar_p(0), j & 1);
         tc_fence_after();
-        TC_TRACE(3, j);
+        if (leader) TC_TRACE(3, j);
         issue_pv(0, v_base, j == 0);
         if (more) {
           wait_full(nk);
-          TC_TRACE(4, j);
+          if (leader) TC_TRACE(4, j);
           issue_qk(0, ring + slot_of(nk) * kTileBytes);
         }
         mbar_wait(bar_p(1), j & 1);
         tc_fence_after();
-        TC_TRACE(5, j);
+        if (leader) TC_TRACE(5, j);
         issue_pv(1, v_base, j == 0);
-        tc_commit(bar_empty(slot_of(nv)));
+        if (leader) tc_commit(bar_empty(slot_of(nv)));
         if (more) {
           issue_qk(1, ring + slot_of(nk) * kTileBytes);
-          tc_commit(bar_empty(slot_of(nk)));
+          if (leader) tc_commit(bar_empty(slot_of(nk)));
         }
       }
     }
@@ -475,6 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
         }
         mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
+      if (R == 0) TC_TRACE(12, j);
       // softcap is monotone, so the maximum of the capped scores is the capped maximum
       float mxs = cap > 0.f ? softcap(mx * a.sm_scale, cap) * kLog2e : mx * sc_log2;
       if (j == 0) {
@@ -501,6 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
           tc_wait_st();
         }
       }
+      if (R == 0) TC_TRACE(13, j);
       // P = 2^(s - m) -> bf16, written over S in place (P is the TMEM A operand of the P.V MMA)
       if (fast) {
         const uint64_t sc2 = pack_f32x2(sc_log2, sc_log2), nm2 = pack_f32x2(-m, -m);
@@ -512,9 +540,15 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
           for (int k = 0; k < 32; k += 2) {
             const uint64_t y =
                 fma_f32x2(pack_f32x2(__uint_as_float(v[c4 * 32 + k]), __uint_as_float(v[c4 * 32 + k + 1])), sc2, nm2);
-            float y0, y1;
-            unpack_f32x2(y, y0, y1);
-            const float p0 = ex2(y0), p1 = ex2(y1);
+            float p0, p1;
+            if ((k >> 1) % 4 < kPolyPairsOf4) {
+              exp2_poly_x2(y, p0, p1);
+            } else {
+              float y0, y1;
+              unpack_f32x2(y, y0, y1);
+              p0 = ex2(y0);
+              p1 = ex2(y1);
+            }
             l2 = add_f32x2(l2, pack_f32x2(p0, p1));
             pk[k >> 1] = pack_bf16x2(p0, p1);
           }
@@ -546,7 +580,9 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
           tc_st16(s_addr + c4 * 16, pk);
         }
       }
+      if (R == 0) TC_TRACE(14, j);
       tc_wait_st();
+      if (R == 0) TC_TRACE(15, j);
       tc_fence_before();
       mbar_arrive(bar_p(i));
       if (r == 0) TC_TRACE(8 + 3 * i, j);

@@ -6,5 +6,5 @@ timeout -s KILL 150 python -m pytest tests/test_extend_gpu.py -m gpu -q -x 2>&1 
 timeout -s KILL 100 python bench.py --workload C4 > $out/${tag}_c4.json 2> $out/${tag}_c4.err; tail -2 $out/${tag}_c4.err
 python tools/bench_table.py $out/${tag}_c4.json
 if [ "$rows" != "0" ]; then
-  timeout -s KILL 150 python tools/tc_trace.py $rows > $out/${tag}_trace.txt 2>&1; tail -n $((rows + 2)) $out/${tag}_trace.txt | cut -c1-200
+  timeout -s KILL 150 python tools/tc_trace.py $rows > $out/${tag}_trace.txt 2>&1; tail -n $((rows + 2)) $out/${tag}_trace.txt | cut -c1-260
 fi

@@ -17,16 +17,16 @@ nrows = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 sys.argv = ["bench.py", "--workload", "C4", "--steps", "3", "--warmup", "3", "--layers", "1", "--no-e2e", "--no-cpu-baseline"]
 bench.main()
 torch.cuda.synchronize()
-buf = np.zeros((12, 128), dtype=np.int64)
+buf = np.zeros((16, 128), dtype=np.int64)
 rc = lib.b200_debug_tc_trace_read(buf.ctypes.data_as(C.c_void_p))
 assert rc == 0
 names = ["prod:empty", "prod:issued", "mma:fullV", "mma:P0", "mma:fullK", "mma:P1", "sm0:S", "sm0:ld", "sm0:Pdone", "sm1:S",
-         "sm1:ld", "sm1:Pdone"]
+         "sm1:ld", "sm1:Pdone", "sm0:max", "sm0:resc", "sm0:exp", "sm0:st"]
 t0 = buf[buf > 0].min()
 np.set_printoptions(linewidth=250)
 print("clock offsets from the first event; rows = KV tile j (producer rows: n = 2j / 2j+1 shown as K,V)")
 print("j   " + " ".join(f"{n:>11s}" for n in ["prodK:empty", "prodK:iss", "prodV:empty", "prodV:iss"] + names[2:]))
 for j in range(nrows):
     row = [buf[0, 2 * j], buf[1, 2 * j], buf[0, 2 * j + 1], buf[1, 2 * j + 1]] if 2 * j + 1 < 128 else [0, 0, 0, 0]
-    row += [buf[e, j] for e in range(2, 12)]
+    row += [buf[e, j] for e in range(2, 16)]
     print(f"{j:3d} " + " ".join(f"{(x - t0) if x > 0 else -1:11d}" for x in row))

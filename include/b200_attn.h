@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define B200_ATTN_ABI_VERSION 5
+#define B200_ATTN_ABI_VERSION 6
 
 /* kv_dtype */
 #define B200_KV_BF16 0
@@ -96,6 +96,8 @@ typedef struct b200_decode_params {
   int32_t force_path;       /* -1 auto, else B200_PATH_* (tests) */
   void* ev_kernel_begin;    /* optional cudaEvent_t pair recorded on `stream` around the */
   void* ev_kernel_end;      /* split-KV kernel alone (bench.py roofline timing); NULL = off */
+  int32_t cascade;          /* must equal the `cascade` b200_attn_plan was called with for this batch */
+  int32_t reserved;
 } b200_decode_params;
 
 /* One layer's extend / chunked-prefill attention over prefix-cached chunks
@@ -146,10 +148,18 @@ int b200_attn_get_config(int32_t max_bs, int32_t hq, int32_t hkv, int32_t d, int
  * attn_logits allocation, triton_backend.py:48-68, and FlashInfer's kv_indices
  * flatten + host-side plan, flashinfer_backend.py:623-670): normalises the index
  * dtypes and balances KV tiles over the persistent grid, entirely on device. */
+/* cascade != 0 additionally looks for a prefix the WHOLE batch shares: the common prefix of the
+ * req_to_token rows (RadixAttention gives requests with a common prompt the same slot ids,
+ * memory/radix_cache.py:105-135), rounded down to 128 tokens and used when >= 1024.  b200_attn_decode then
+ * computes that prefix once per kv head as a dense tcgen05 contraction over all queries of the batch and
+ * only the per-request suffixes through the split-KV kernel; the LSE merge combines both.  Detection is
+ * on device (no host sync, CUDA-graph safe); head_dim 128 only, otherwise the flag is ignored.
+ * req_to_token may be NULL when cascade == 0. */
 int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs,
                    const void* req_pool_indices, const void* seq_lens, int32_t idx_dtype,
                    int32_t bs, int32_t hq, int32_t hkv, int32_t d, int32_t dv, int32_t kv_dtype,
-                   int32_t force_path, b200_stream_t stream);
+                   int32_t force_path, const int32_t* req_to_token, int64_t req_to_token_stride,
+                   int32_t cascade, b200_stream_t stream);
 
 int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream);
 int b200_attn_extend(const b200_extend_params* p, b200_stream_t stream);

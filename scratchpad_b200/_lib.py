@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libb200attn.so")
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 KV_BF16, KV_FP8_E4M3 = 0, 1
 IDX_I32, IDX_I64 = 0, 1
@@ -65,6 +65,7 @@ class DecodeParams(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
         ("max_bs", C.c_int32), ("force_path", C.c_int32),
         ("ev_kernel_begin", C.c_void_p), ("ev_kernel_end", C.c_void_p),
+        ("cascade", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -137,7 +138,7 @@ def load() -> C.CDLL:
                               f"({lib.b200_attn_struct_size(which)} B)")
     i32, i64, u64, vp, f = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p, C.c_float
     lib.b200_attn_get_config.argtypes = [i32, i32, i32, i32, i32, i32, i32, C.POINTER(AttnConfig)]
-    lib.b200_attn_plan.argtypes = [vp, u64, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.b200_attn_plan.argtypes = [vp, u64, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, i32, vp]
     lib.b200_attn_decode.argtypes = [C.POINTER(DecodeParams), vp]
     lib.b200_attn_extend.argtypes = [C.POINTER(ExtendParams), vp]
     lib.b200_kv_store.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp, i64, i64, i64, i64, i32, i32, i32, i32, i32, vp, vp, vp]

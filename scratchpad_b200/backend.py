@@ -75,7 +75,7 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 class CudaB200AttnBackend(AttentionBackend):
-    def __init__(self, model_runner, force_path: int = _lib.PATH_AUTO):
+    def __init__(self, model_runner, force_path: int = _lib.PATH_AUTO, cascade: Optional[bool] = None):
         super().__init__()
         self.lib = _lib.load()  # raises when the extension is not built
         cfg = model_runner.model_config
@@ -92,6 +92,12 @@ class CudaB200AttnBackend(AttentionBackend):
         self.v_head_dim = self.token_to_kv_pool.get_value_buffer(0).shape[-1]
         self.kv_dtype = self.token_to_kv_pool.kv_dtype_code()
         self.force_path = force_path
+        # Shared-prefix cascade decode: the prefix every request of a decode batch shares (same slot ids in
+        # req_to_token, which is how RadixAttention represents a shared system prompt) is attended once per
+        # kv head as a dense tcgen05 contraction; detection is on device, so it costs nothing to leave on.
+        if cascade is None:
+            cascade = bool(getattr(model_runner.server_args, "b200_shared_prefix_cascade", True))
+        self.cascade = 1 if cascade else 0
         if getattr(model_runner, "sliding_window_size", None) not in (None, -1):
             raise NotImplementedError("cuda_b200 backend: sliding-window attention is not supported")
         if model_runner.dtype != torch.bfloat16:
@@ -125,7 +131,9 @@ class CudaB200AttnBackend(AttentionBackend):
             self.workspace.data_ptr(), self.workspace.numel(), self.max_bs,
             req_pool_indices.data_ptr(), seq_lens.data_ptr(), _idx_code(req_pool_indices), bs,
             self.num_head, self.num_kv_head, self.head_dim, self.v_head_dim, self.kv_dtype,
-            self.force_path, torch.cuda.current_stream().cuda_stream,
+            self.force_path, self.req_to_token_pool.req_to_token.data_ptr(),
+            self.req_to_token_pool.req_to_token.stride(0), self.cascade,
+            torch.cuda.current_stream().cuda_stream,
         )
         _lib.check(rc, "b200_attn_plan")
         self._planned_for = bs
@@ -204,7 +212,7 @@ class CudaB200AttnBackend(AttentionBackend):
             sm_scale=float(layer.scaling), logit_cap=self._logit_cap(layer),
             k_scale=_ptr(ks), v_scale=_ptr(vs),
             workspace=self.workspace.data_ptr(), workspace_bytes=self.workspace.numel(),
-            max_bs=self.max_bs, force_path=self.force_path,
+            max_bs=self.max_bs, force_path=self.force_path, cascade=self.cascade,
         )
         if self.profile_events is not None:
             p.ev_kernel_begin, p.ev_kernel_end = self.profile_events

@@ -41,9 +41,16 @@ namespace b200 {
 constexpr int kStages = 3;
 constexpr int kPlanMagic = 0x62323030;  // "b200"
 constexpr int kHdrInts = 16;
+// header words: 0 total tiles, 1 tiles per CTA, 2 CTAs used, 3 bs, 4 tile tokens, 5 grid, 6 magic,
+// 7 shared-prefix length in use (multiple of 128, 0 = none), 8 raw common-prefix length (lcp_kernel)
+constexpr int kHdrShared = 7, kHdrLcp = 8;
+constexpr int kMaxCasSplits = 8;     // KV splits of the shared-prefix leg (workspace is sized for this many)
+constexpr int kCasTile = 128;        // its key-tile size (extend_tc.cu)
+constexpr int kMinShared = 1024;     // shorter common prefixes stay on the split-KV kernel
+constexpr int kMinCasRows = 64;      // bs * g below this: the dense leg would be mostly padding
 
 struct WsLayout {
-  size_t tile_off, seq_len, req_idx, cta_b0, part_lse, part_o, total;
+  size_t tile_off, seq_len, req_idx, cta_b0, part_lse, part_o, cas_lse, cas_o, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -64,8 +71,48 @@ static WsLayout ws_layout(int max_bs, int grid, int nsub, int hq, int dv) {
   off = align_up(off + nparts * sizeof(float), 256);
   L.part_o = off;
   off = align_up(off + nparts * dv * sizeof(float), 256);
+  // shared-prefix ("cascade") partials: [split, request, q head]
+  const size_t ncas = (size_t)kMaxCasSplits * max_bs * hq;
+  L.cas_lse = off;
+  off = align_up(off + ncas * sizeof(float), 256);
+  L.cas_o = off;
+  off = align_up(off + ncas * dv * sizeof(float), 256);
   L.total = off;
   return L;
+}
+
+// ---------------------------------------------------------------------------
+// shared-prefix detection: hdr[kHdrLcp] = min over the batch of the length of the common prefix of
+// req_to_token[req_b, :seq_b] and req_to_token[req_0, :seq_0] (RadixAttention makes requests that share
+// a prompt prefix share its slot ids -- memory/radix_cache.py:105-135 -- so equal slot ids ARE the sharing
+// information, and reading it here needs nothing from the scheduler).  One CTA per request; hdr[kHdrLcp]
+// is preset to a large value by a memset node.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lcp_kernel(int* __restrict__ hdr, const int32_t* __restrict__ r2t, int64_t r2t_stride,
+                                                  const void* __restrict__ req, const void* __restrict__ seq, int idx64) {
+  __shared__ int s_first;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  int64_t n = min(load_idx(seq, idx64, b), load_idx(seq, idx64, 0));
+  if (n < 0) n = 0;
+  const int32_t* mine = r2t + load_idx(req, idx64, b) * r2t_stride;
+  const int32_t* ref = r2t + load_idx(req, idx64, 0) * r2t_stride;
+  if (tid == 0) s_first = static_cast<int>(n);
+  __syncthreads();
+  if (b != 0) {
+    for (int base = 0; base < n; base += 256 * 8) {
+      int first = 0x7fffffff;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int t = base + u * 256 + tid;
+        if (t < n && __ldg(mine + t) != __ldg(ref + t)) first = min(first, t);
+      }
+      if (first != 0x7fffffff) atomicMin(&s_first, first);
+      __syncthreads();
+      if (s_first < base + 256 * 8) break;  // a mismatch inside this block of positions: done
+    }
+  }
+  __syncthreads();
+  if (tid == 0) atomicMin(hdr + kHdrLcp, s_first);
 }
 
 // ---------------------------------------------------------------------------
@@ -75,13 +122,20 @@ __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* 
                                                     int* __restrict__ seq32, int* __restrict__ req32,
                                                     int* __restrict__ cta_b0,
                                                     const void* __restrict__ req, const void* __restrict__ seq,
-                                                    int idx64, int bs, int tile_tokens, int grid) {
+                                                    int idx64, int bs, int tile_tokens, int grid, int cascade) {
   __shared__ int warp_sums[32];
   __shared__ int s_running;
   pdl_wait();
   pdl_launch_dependents();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_running = 0;
+  // prefix shared by the whole batch (lcp_kernel ran before us): handled by the dense tcgen05 leg, so the
+  // split-KV tiles of every request start behind it
+  int shared = 0;
+  if (cascade) {
+    shared = hdr[kHdrLcp] / kCasTile * kCasTile;
+    if (shared < kMinShared) shared = 0;
+  }
   __syncthreads();
   for (int base = 0; base < bs; base += 1024) {
     const int i = base + tid;
@@ -91,7 +145,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* 
       if (s < 0) s = 0;
       seq32[i] = static_cast<int>(s);
       req32[i] = static_cast<int>(load_idx(req, idx64, i));
-      n = static_cast<int>((s + tile_tokens - 1) / tile_tokens);
+      n = static_cast<int>((s - shared + tile_tokens - 1) / tile_tokens);  // shared <= every s
     }
     int x = n;
 #pragma unroll
@@ -147,6 +201,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* 
     hdr[4] = tile_tokens;
     hdr[5] = grid;
     hdr[6] = kPlanMagic;
+    hdr[kHdrShared] = shared;
   }
 }
 
@@ -180,13 +235,15 @@ struct Cursor {
   int b_begin, b_end;  // tile range of request b
   int seq_len;
   const int32_t* row;  // req_to_token row of request b
+  int shared;          // length of the batch-shared prefix the cascade leg handles (0 = none)
 };
 
 __device__ __forceinline__ void cursor_load_req(Cursor& c, const DecodeArgs& a) {
   c.b_begin = __ldg(a.tile_off + c.b);
   c.b_end = __ldg(a.tile_off + c.b + 1);
-  c.seq_len = __ldg(a.seq_len + c.b);
-  c.row = a.r2t + static_cast<int64_t>(__ldg(a.req_idx + c.b)) * a.r2t_stride;
+  // positions are relative to the end of the batch-shared prefix (0 unless the cascade leg handles it)
+  c.seq_len = __ldg(a.seq_len + c.b) - c.shared;
+  c.row = a.r2t + static_cast<int64_t>(__ldg(a.req_idx + c.b)) * a.r2t_stride + c.shared;
 }
 __device__ __forceinline__ bool cursor_valid(const Cursor& c) { return c.gt < c.gt_end; }
 __device__ __forceinline__ void cursor_advance(Cursor& c, const DecodeArgs& a) {
@@ -246,6 +303,7 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
   pc.gt = gt_begin;
   pc.gt_end = gt_end;
   pc.b = lo;
+  pc.shared = __ldg(a.hdr + kHdrShared);
   cursor_load_req(pc, a);
   Cursor cc = pc;  // consumer cursor
 
@@ -522,7 +580,9 @@ template <int DV>
 __global__ void __launch_bounds__(256) merge_kernel(const int* __restrict__ hdr, const int* __restrict__ tile_off,
                                                     const float* __restrict__ part_o,
                                                     const float* __restrict__ part_lse, __nv_bfloat16* __restrict__ o,
-                                                    int64_t o_st, int64_t o_sh, int bs, int hq, int nsub) {
+                                                    int64_t o_st, int64_t o_sh, int bs, int hq, int nsub,
+                                                    const float* __restrict__ cas_o, const float* __restrict__ cas_lse,
+                                                    int cas_splits) {
   pdl_wait();
   pdl_launch_dependents();
   constexpr int VPL = DV / 32;  // floats per lane
@@ -532,37 +592,47 @@ __global__ void __launch_bounds__(256) merge_kernel(const int* __restrict__ hdr,
   const int b = pair / hq, h = pair % hq;
   const int tpc = __ldg(hdr + 1);
   const int t0 = __ldg(tile_off + b), t1 = __ldg(tile_off + b + 1);
+  // partials of the shared-prefix leg (one per KV split), present when the plan found a shared prefix
+  const int ncas = (cas_splits > 0 && __ldg(hdr + kHdrShared) > 0) ? cas_splits : 0;
   __nv_bfloat16* op = o + static_cast<int64_t>(b) * o_st + static_cast<int64_t>(h) * o_sh + lane * VPL;
   float acc[VPL];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) acc[j] = 0.f;
   float den = 0.f;
+  int64_t first = 0;
+  int n = 0;
   if (t1 > t0) {
     const int c0 = t0 / tpc, c1 = (t1 - 1) / tpc;
-    const int64_t first = static_cast<int64_t>(c0 + b) * nsub;
-    const int n = (c1 - c0 + 1) * nsub;
-    float mx = -INFINITY;
-    for (int i = lane; i < n; i += 32) mx = fmaxf(mx, __ldcg(part_lse + (first + i) * hq + h));
+    first = static_cast<int64_t>(c0 + b) * nsub;
+    n = (c1 - c0 + 1) * nsub;
+  }
+  float mx = -INFINITY;
+  for (int i = lane; i < n; i += 32) mx = fmaxf(mx, __ldcg(part_lse + (first + i) * hq + h));
+  const int64_t cas_i = static_cast<int64_t>(b) * hq + h, cas_st = static_cast<int64_t>(bs) * hq;
+  if (lane < ncas) mx = fmaxf(mx, __ldcg(cas_lse + lane * cas_st + cas_i));
 #pragma unroll
-    for (int x = 16; x > 0; x >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, x));
-    if (mx > -INFINITY) {
-      for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        const float w_lane = i < n ? ex2(__ldcg(part_lse + (first + i) * hq + h) - mx) : 0.f;
-        const int cnt = min(32, n - base);
-        for (int j = 0; j < cnt; ++j) {
-          const float w = __shfl_sync(0xffffffffu, w_lane, j);
-          den += w;
-          const float* src = part_o + ((first + base + j) * hq + h) * DV + lane * VPL;
-          if constexpr (VPL == 4) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(src));
-            acc[0] += w * v.x; acc[1] += w * v.y; acc[2] += w * v.z; acc[3] += w * v.w;
-          } else {
-            const float2 v = __ldcg(reinterpret_cast<const float2*>(src));
-            acc[0] += w * v.x; acc[1] += w * v.y;
-          }
-        }
-      }
+  for (int x = 16; x > 0; x >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, x));
+  auto fold = [&](float w, const float* src) {
+    den += w;
+    if constexpr (VPL == 4) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(src));
+      acc[0] += w * v.x; acc[1] += w * v.y; acc[2] += w * v.z; acc[3] += w * v.w;
+    } else {
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(src));
+      acc[0] += w * v.x; acc[1] += w * v.y;
+    }
+  };
+  if (mx > -INFINITY) {
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const float w_lane = i < n ? ex2(__ldcg(part_lse + (first + i) * hq + h) - mx) : 0.f;
+      const int cnt = min(32, n - base);
+      for (int j = 0; j < cnt; ++j)
+        fold(__shfl_sync(0xffffffffu, w_lane, j), part_o + ((first + base + j) * hq + h) * DV + lane * VPL);
+    }
+    if (ncas > 0) {
+      const float w_lane = lane < ncas ? ex2(__ldcg(cas_lse + lane * cas_st + cas_i) - mx) : 0.f;
+      for (int j = 0; j < ncas; ++j) fold(__shfl_sync(0xffffffffu, w_lane, j), cas_o + (j * cas_st + cas_i) * DV + lane * VPL);
     }
   }
   const float r = den > 0.f ? 1.f / den : 0.f;  // seq_len == 0 -> zeros
@@ -740,6 +810,9 @@ static int get_config(int max_bs, int hq, int hkv, int d, int dv, int kv_dtype, 
   return B200_OK;
 }
 
+int launch_shared_prefix_tc(const b200_decode_params* p, const int* hdr, const int* req32, float* cas_o, float* cas_lse, int nsplit,
+                            cudaStream_t st);  // extend_tc.cu
+
 }  // namespace b200
 
 using namespace b200;
@@ -775,20 +848,35 @@ int b200_attn_get_config(int32_t max_bs, int32_t hq, int32_t hkv, int32_t d, int
   return get_config(max_bs, hq, hkv, d, dv, kv_dtype, force_path, out);
 }
 
+// cascade is honoured only where the dense leg exists and is worth launching
+static bool cascade_supported(int bs, int hq, int hkv, int d, int dv) {
+  return d == 128 && dv == 128 && hkv > 0 && 256 % (hq / hkv) == 0 && bs * (hq / hkv) >= kMinCasRows;
+}
+
 int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs, const void* req_pool_indices,
                    const void* seq_lens, int32_t idx_dtype, int32_t bs, int32_t hq, int32_t hkv, int32_t d, int32_t dv,
-                   int32_t kv_dtype, int32_t force_path, b200_stream_t stream) {
+                   int32_t kv_dtype, int32_t force_path, const int32_t* req_to_token, int64_t req_to_token_stride,
+                   int32_t cascade, b200_stream_t stream) {
   if (!workspace || !req_pool_indices || !seq_lens || bs <= 0 || bs > max_bs) return B200_ERR_INVALID;
+  if (cascade && !req_to_token) return B200_ERR_INVALID;
   b200_attn_config cfg;
   int rc = get_config(max_bs, hq, hkv, d, dv, kv_dtype, force_path, &cfg);
   if (rc) return rc;
   if (workspace_bytes < cfg.workspace_bytes) return B200_ERR_WORKSPACE;
   const WsLayout L = ws_layout(max_bs, cfg.grid_ctas, cfg.sub_splits, hq, dv);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  plan_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int use_cascade = cascade && cascade_supported(bs, hq, hkv, d, dv);
+  if (use_cascade) {
+    B200_CUDA_TRY(cudaMemsetAsync(reinterpret_cast<int*>(ws) + kHdrLcp, 0x7f, sizeof(int), st));
+    lcp_kernel<<<bs, 256, 0, st>>>(reinterpret_cast<int*>(ws), req_to_token, req_to_token_stride, req_pool_indices, seq_lens,
+                                   idx_dtype == B200_IDX_I64);
+    B200_CUDA_TRY(cudaGetLastError());
+  }
+  plan_kernel<<<1, 1024, 0, st>>>(
       reinterpret_cast<int*>(ws), reinterpret_cast<int*>(ws + L.tile_off), reinterpret_cast<int*>(ws + L.seq_len),
       reinterpret_cast<int*>(ws + L.req_idx), reinterpret_cast<int*>(ws + L.cta_b0), req_pool_indices, seq_lens, idx_dtype == B200_IDX_I64, bs,
-      cfg.tile_tokens, cfg.grid_ctas);
+      cfg.tile_tokens, cfg.grid_ctas, use_cascade);
   B200_CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }
@@ -837,6 +925,17 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
   a.k_scale = p->k_scale;
   a.v_scale = p->v_scale;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // shared-prefix leg first (it exits at once when the plan found nothing shared); must match what plan decided
+  int cas_splits = 0;
+  float* cas_o = reinterpret_cast<float*>(ws + L.cas_o);
+  float* cas_lse = reinterpret_cast<float*>(ws + L.cas_lse);
+  if (p->cascade && cascade_supported(p->bs, p->hq, p->hkv, p->d, p->dv)) {
+    const int g = p->hq / p->hkv, row_blocks = (p->bs * g + 255) / 256;
+    cas_splits = cfg.num_sms / (row_blocks * p->hkv);
+    cas_splits = cas_splits < 1 ? 1 : (cas_splits > kMaxCasSplits ? kMaxCasSplits : cas_splits);
+    rc = launch_shared_prefix_tc(p, a.hdr, a.req_idx, cas_o, cas_lse, cas_splits, st);
+    if (rc) return rc;
+  }
   if (p->ev_kernel_begin) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(p->ev_kernel_begin), st));
   rc = dispatch(kc, a, cfg.grid_ctas, p->hkv / kc.hpc, st, false, nullptr);
   if (rc) return rc;
@@ -847,11 +946,11 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
     return launch_pdl(merge_kernel<64>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
                       static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
                       static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
-                      static_cast<int>(cfg.sub_splits));
+                      static_cast<int>(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits);
   return launch_pdl(merge_kernel<128>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
                     static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
                     static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
-                    static_cast<int>(cfg.sub_splits));
+                    static_cast<int>(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits);
 }
 
 int b200_debug_gather(const void* buf, int64_t stride_t_bytes, int32_t row_bytes, const int32_t* req_to_token,

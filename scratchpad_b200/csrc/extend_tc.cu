@@ -91,6 +91,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity), "r"(kSuspendHintNs)
       : "memory");
 }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -224,8 +227,9 @@ __device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t sbo_bytes) {
   return d;
 }
 // instruction descriptor: bf16 x bf16 -> fp32, M x N, A K-major, B K-major or MN-major
-__host__ __device__ constexpr uint32_t instr_desc(int m, int n, bool b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
+__host__ __device__ constexpr uint32_t instr_desc(int m, int n, bool b_mn_major, bool f16 = false) {
+  const uint32_t ab = f16 ? 0u : 1u;  // operand format: 0 = f16, 1 = bf16
+  return (1u << 4) | (ab << 7) | (ab << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
@@ -261,35 +265,77 @@ struct Args {
   int idx64;
   const int32_t* ext_lens;
   const int32_t* ext_start;
-  int hq, hkv, g, bm_t;  // bm_t = tokens per CTA = 256 / g
+  int hq, hkv, g, bm_t;  // bm_t = tokens (extend) or requests (shared-prefix decode) per CTA = 256 / g
   float sm_scale, logit_cap;
+  // shared-prefix decode (kModeShared) only
+  const int* hdr;          // plan header: hdr[kHdrShared] = length of the prefix every request of the batch shares
+  const int* req32;        // normalised request rows (plan)
+  float* cas_o;            // [nsplit, bs, hq, 128] fp32 partial outputs, normalised
+  float* cas_lse;          // [nsplit, bs, hq] log2-domain log-sum-exp
+  const float* k_scale;    // per kv head (fp8 pools), or null
+  const float* v_scale;
+  int bs;
 };
+
+constexpr int kModeExtend = 0;  // causal extend over [gathered prefix | new tokens], bf16 out
+constexpr int kModeShared = 1;  // decode queries of the whole batch against the prefix they all share, fp32 partials out
+constexpr int kHdrShared = 7;   // index into the plan header (decode.cu)
 
 // byte offset of 16-byte chunk (row r, element block cb of 64, chunk c of 8) inside a [128 x 128] bf16 tile
 __device__ __forceinline__ uint32_t tile_off(int r, int cb, int c) {
   return cb * kColBlockBytes + r * 128 + ((c ^ (r & 7)) << 4);
 }
 
+// MODE kModeExtend: grid (query block, kv head, request).  MODE kModeShared: grid (block of 256/g requests, kv head,
+// KV split); F16 = the pool is fp8-e4m3: K/V are widened to f16 on their way into shared memory (exact), Q is
+// narrowed bf16 -> f16 (exact for |q| >= 2^-14) and the MMAs run as f16 x f16; k_scale folds into the softmax
+// scale and v_scale into the epilogue, like the split-KV kernel does.
+template <int MODE, bool F16>
 __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
+  static_assert(MODE == kModeShared || !F16, "extend over fp8 pools stays on the mma.sync kernel (extend.cu)");
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_wait();
   pdl_launch_dependents();
 
-  const int b = blockIdx.z, kvh = blockIdx.y;
+  const int kvh = blockIdx.y;
   const int G = a.g, bm_t = a.bm_t;
-  const int ext = __ldg(a.ext_lens + b);
-  const int nqb = (ext + bm_t - 1) / bm_t;
-  const int qb = nqb - 1 - static_cast<int>(blockIdx.x);  // heavy (late) blocks first
-  if (qb < 0) return;
-  const int seq = static_cast<int>(load_idx(a.seq_lens, a.idx64, b));
-  const int pre = seq - ext;
-  const int start = __ldg(a.ext_start + b);
-  const int32_t* row = a.r2t + load_idx(a.req_idx, a.idx64, b) * a.r2t_stride;
-  const int t0 = qb * bm_t;
-  const int t_end = min(ext, t0 + bm_t);
-  const int kv_len = pre + t_end;
-  const int nt = (kv_len + kBN - 1) / kBN;
+  // extend: token range [t0, t_end) of request b; shared: request range [t0, t_end) of the batch
+  int pre, start, t0, t_end, kv_len, nt, cas_split = 0;
+  const int32_t* row;
+  if constexpr (MODE == kModeExtend) {
+    const int b = blockIdx.z;
+    const int ext = __ldg(a.ext_lens + b);
+    const int nqb = (ext + bm_t - 1) / bm_t;
+    const int qb = nqb - 1 - static_cast<int>(blockIdx.x);  // heavy (late) blocks first
+    if (qb < 0) return;
+    const int seq = static_cast<int>(load_idx(a.seq_lens, a.idx64, b));
+    pre = seq - ext;
+    start = __ldg(a.ext_start + b);
+    row = a.r2t + load_idx(a.req_idx, a.idx64, b) * a.r2t_stride;
+    t0 = qb * bm_t;
+    t_end = min(ext, t0 + bm_t);
+    kv_len = pre + t_end;
+    nt = (kv_len + kBN - 1) / kBN;
+  } else {
+    const int shared = __ldg(a.hdr + kHdrShared);  // multiple of kBN, 0 = this batch shares nothing
+    if (shared <= 0) return;
+    t0 = static_cast<int>(blockIdx.x) * bm_t;
+    t_end = min(a.bs, t0 + bm_t);
+    if (t0 >= t_end) return;
+    cas_split = blockIdx.z;
+    const int ntot = shared / kBN, ns = gridDim.z;
+    const int j0 = static_cast<int>(static_cast<int64_t>(cas_split) * ntot / ns);
+    nt = static_cast<int>(static_cast<int64_t>(cas_split + 1) * ntot / ns) - j0;
+    row = a.r2t + static_cast<int64_t>(__ldg(a.req32)) * a.r2t_stride + j0 * kBN;  // request 0 holds the shared slots too
+    start = 0;
+    pre = kv_len = nt * kBN;
+    if (nt <= 0) {  // more splits than tiles (the plan never produces this): an empty partial
+      const int R = tid;
+      if (R < (t_end - t0) * G) a.cas_lse[(static_cast<int64_t>(cas_split) * a.bs + t0 + R / G) * a.hq + kvh * G + R % G] = -INFINITY;
+      return;
+    }
+  }
   const int live_rows = (t_end - t0) * G;
 
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-byte alignment
@@ -343,6 +389,33 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       mbar_wait(bar_empty(s), ((n / kSlots) & 1) ^ 1);
       if (tid == kProdWarp0 * 32) TC_TRACE(0, n);
       const uint32_t dst0 = sbase + kSmemRing + s * kTileBytes + dst_thread;
+      if constexpr (F16) {
+        // fp8-e4m3 pool: lane & 7 = 16-byte chunk of the 128-byte row (16 values -> two f16 chunks), rows
+        // 16q + 4pw + lane/8 (again a constant row & 7 per thread); widened in registers, stored with st.shared
+        const int c8 = lane & 7, rr = 4 * pw + (lane >> 3), rr7 = rr & 7;
+        const uint8_t* pool8 = (is_v ? a.vbuf : a.kbuf) + static_cast<int64_t>(kvh) * kD + c8 * 16;
+        const uint32_t d0 = sbase + kSmemRing + s * kTileBytes + (c8 >> 2) * kColBlockBytes + rr * 128;
+        const uint32_t o0 = (((2 * c8) & 7) ^ rr7) << 4, o1 = (((2 * c8 + 1) & 7) ^ rr7) << 4;
+        uint4 raw[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          raw[q] = __ldg(reinterpret_cast<const uint4*>(kv_row_ptr(pool8, __ldg(row + j * kBN + 16 * q + rr), pool_st)));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t w[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
+          uint32_t h[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            h[2 * e] = e4m3x2_to_f16x2(static_cast<uint16_t>(w[e] & 0xffffu));
+            h[2 * e + 1] = e4m3x2_to_f16x2(static_cast<uint16_t>(w[e] >> 16));
+          }
+          st_shared_v4(d0 + q * 2048 + o0, h[0], h[1], h[2], h[3]);
+          st_shared_v4(d0 + q * 2048 + o1, h[4], h[5], h[6], h[7]);
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_full(s));
+        continue;
+      }
       if ((j + 1) * kBN <= pre) {
         // tile of cached-prefix keys only: page-table lookup (L1-resident after the first touch) + one copy
         int slot[16];
@@ -368,9 +441,11 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
         mbar_arrive(bar_full((n - kLag) % kSlots));
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int n = max(total - kLag, 0); n < total; ++n) mbar_arrive(bar_full(n % kSlots));
+    if constexpr (!F16) {
+      cp_async_wait<0>();
+      fence_proxy_async();
+      for (int n = max(total - kLag, 0); n < total; ++n) mbar_arrive(bar_full(n % kSlots));
+    }
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ============================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
@@ -378,8 +453,8 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     // no R2UR in front of each UTCHMMA); only the tcgen05.mma / tcgen05.commit themselves are issued by lane 0.
     const bool leader = lane == 0;
     {
-      constexpr uint32_t idesc_qk = instr_desc(kTileRows, kBN, false);
-      constexpr uint32_t idesc_pv = instr_desc(kTileRows, kD, true);
+      constexpr uint32_t idesc_qk = instr_desc(kTileRows, kBN, false, F16);
+      constexpr uint32_t idesc_pv = instr_desc(kTileRows, kD, true, F16);
       const uint32_t q_base = sbase + kSmemQ;
       const uint32_t ring = sbase + kSmemRing;
       auto issue_qk = [&](int i, uint32_t k_base) {  // S_i = Q_i . K^T
@@ -451,7 +526,17 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       const bool live = R < live_rows;
       const int t = t0 + (live ? R / G : 0), h = kvh * G + (live ? R % G : 0);
       const __nv_bfloat16* src = a.q + static_cast<int64_t>(start + t) * a.q_st + static_cast<int64_t>(h) * a.q_sh + ch * 8;
-      cp_async16(sbase + kSmemQ + (R >> 7) * kTileBytes + tile_off(R & 127, ch >> 3, ch & 7), src, live ? 16 : 0);
+      const uint32_t dst = sbase + kSmemQ + (R >> 7) * kTileBytes + tile_off(R & 127, ch >> 3, ch & 7);
+      if constexpr (F16) {
+        uint4 x = live ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+        uint32_t h2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h2[e] = pack_f16x2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+        st_shared_v4(dst, h2[0], h2[1], h2[2], h2[3]);
+      } else {
+        cp_async16(dst, src, live ? 16 : 0);
+      }
     }
     cp_async_commit();
     cp_async_wait<0>();
@@ -464,9 +549,11 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const uint32_t s_addr = lane_base + (i ? kColS1 : kColS0);
     const uint32_t o_addr = lane_base + (i ? kColO1 : kColO0);
-    const int lim = pre + min(t0 + R / G, t_end - 1);  // causal limit (dead rows behave like the last live token)
+    // causal limit (dead rows behave like the last live token); the shared prefix is visible to every row
+    const int lim = MODE == kModeExtend ? pre + min(t0 + R / G, t_end - 1) : kv_len;
     const float cap = a.logit_cap;
-    const float sc_log2 = a.sm_scale * kLog2e;
+    const float sm_scale = (F16 && a.k_scale) ? a.sm_scale * __ldg(a.k_scale + kvh) : a.sm_scale;
+    const float sc_log2 = sm_scale * kLog2e;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < nt; ++j) {
       mbar_wait(bar_s(i), j & 1);
@@ -503,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       }
       if (R == 0) TC_TRACE(12, j);
       // softcap is monotone, so the maximum of the capped scores is the capped maximum
-      float mxs = cap > 0.f ? softcap(mx * a.sm_scale, cap) * kLog2e : mx * sc_log2;
+      float mxs = cap > 0.f ? softcap(mx * sm_scale, cap) * kLog2e : mx * sc_log2;
       if (j == 0) {
         m = mxs;  // key 0 is visible to every row, so this is finite
       } else {
@@ -550,7 +637,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
               p1 = ex2(y1);
             }
             l2 = add_f32x2(l2, pack_f32x2(p0, p1));
-            pk[k >> 1] = pack_bf16x2(p0, p1);
+            pk[k >> 1] = pack2<F16>(p0, p1);
           }
           tc_st16(s_addr + c4 * 16, pk);
         }
@@ -566,8 +653,8 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
             float x0 = __uint_as_float(v[c4 * 32 + k]), x1 = __uint_as_float(v[c4 * 32 + k + 1]);
             float p0, p1;
             if (cap > 0.f) {
-              p0 = ex2(softcap(x0 * a.sm_scale, cap) * kLog2e - m);
-              p1 = ex2(softcap(x1 * a.sm_scale, cap) * kLog2e - m);
+              p0 = ex2(softcap(x0 * sm_scale, cap) * kLog2e - m);
+              p1 = ex2(softcap(x1 * sm_scale, cap) * kLog2e - m);
             } else {
               p0 = ex2(fmaf(x0, sc_log2, -m));
               p1 = ex2(fmaf(x1, sc_log2, -m));
@@ -575,7 +662,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
             if (c4 * 32 + k > climit) p0 = 0.f;
             if (c4 * 32 + k + 1 > climit) p1 = 0.f;
             l += p0 + p1;
-            pk[k >> 1] = pack_bf16x2(p0, p1);
+            pk[k >> 1] = pack2<F16>(p0, p1);
           }
           tc_st16(s_addr + c4 * 16, pk);
         }
@@ -587,27 +674,48 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       mbar_arrive(bar_p(i));
       if (r == 0) TC_TRACE(8 + 3 * i, j);
     }
-    // epilogue: O_i / l -> bf16 -> global (thread = row)
+    // epilogue (thread = row): extend -> O_i / l as bf16; shared prefix -> fp32 partial (O_i v_scale / l, m + log2 l)
     mbar_wait(bar_pv(i), (nt - 1) & 1);
     tc_fence_after();
-    const float inv = l > 0.f ? 1.f / l : 0.f;
     const bool live = R < live_rows;
-    __nv_bfloat16* op = a.o + static_cast<int64_t>(start + t0 + (live ? R / G : 0)) * a.o_st +
-                        static_cast<int64_t>(kvh * G + (live ? R % G : 0)) * a.o_sh;
+    if constexpr (MODE == kModeExtend) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      __nv_bfloat16* op = a.o + static_cast<int64_t>(start + t0 + (live ? R / G : 0)) * a.o_st +
+                          static_cast<int64_t>(kvh * G + (live ? R % G : 0)) * a.o_sh;
 #pragma unroll 1
-    for (int c4 = 0; c4 < 4; ++c4) {
-      uint32_t w[32];
-      tc_ld32(o_addr + c4 * 32, w);
-      tc_wait_ld();
-      if (live) {
+      for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t w[32];
+        tc_ld32(o_addr + c4 * 32, w);
+        tc_wait_ld();
+        if (live) {
 #pragma unroll
-        for (int k = 0; k < 32; k += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(w[k]) * inv, __uint_as_float(w[k + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(w[k + 2]) * inv, __uint_as_float(w[k + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(w[k + 4]) * inv, __uint_as_float(w[k + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(w[k + 6]) * inv, __uint_as_float(w[k + 7]) * inv);
-          *reinterpret_cast<uint4*>(op + c4 * 32 + k) = u;
+          for (int k = 0; k < 32; k += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(w[k]) * inv, __uint_as_float(w[k + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(w[k + 2]) * inv, __uint_as_float(w[k + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(w[k + 4]) * inv, __uint_as_float(w[k + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(w[k + 6]) * inv, __uint_as_float(w[k + 7]) * inv);
+            *reinterpret_cast<uint4*>(op + c4 * 32 + k) = u;
+          }
+        }
+      }
+    } else {
+      const float vs = (F16 && a.v_scale) ? __ldg(a.v_scale + kvh) : 1.f;
+      const float inv = l > 0.f ? vs / l : 0.f;
+      const int64_t pi = (static_cast<int64_t>(cas_split) * a.bs + t0 + (live ? R / G : 0)) * a.hq + kvh * G + (live ? R % G : 0);
+      if (live) a.cas_lse[pi] = l > 0.f ? m + lg2(l) : -INFINITY;
+      float* op = a.cas_o + pi * kD;
+#pragma unroll 1
+      for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t w[32];
+        tc_ld32(o_addr + c4 * 32, w);
+        tc_wait_ld();
+        if (live) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 4)
+            *reinterpret_cast<float4*>(op + c4 * 32 + k) =
+                make_float4(__uint_as_float(w[k]) * inv, __uint_as_float(w[k + 1]) * inv, __uint_as_float(w[k + 2]) * inv,
+                            __uint_as_float(w[k + 3]) * inv);
         }
       }
     }
@@ -630,9 +738,20 @@ extern "C" int b200_debug_tc_trace_read(long long* host_dst) {
 }
 #endif
 
+template <int MODE, bool F16>
+static int launch_tc(const tc::Args& a, dim3 grid, cudaStream_t st) {
+  auto kern = tc::extend_tc_kernel<MODE, F16>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+    attr_set = true;
+  }
+  return launch_pdl(kern, grid, dim3(tc::kThreads), tc::kSmemBytes, st, a);
+}
+
 // Called by b200_attn_extend (extend.cu) for head_dim 128 / bf16 pools.  Strides and pointers have been validated there.
 int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
-  tc::Args a;
+  tc::Args a{};
   a.q = static_cast<const __nv_bfloat16*>(p->q);
   a.q_st = p->q_stride_t;
   a.q_sh = p->q_stride_h;
@@ -662,13 +781,44 @@ int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
   a.bm_t = tc::kRows / a.g;
   a.sm_scale = p->sm_scale;
   a.logit_cap = p->logit_cap;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_TRY(cudaFuncSetAttribute(tc::extend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
-    attr_set = true;
-  }
   const int nqb = (p->max_extend_len + a.bm_t - 1) / a.bm_t;
-  return launch_pdl(tc::extend_tc_kernel, dim3(nqb, p->hkv, p->bs), dim3(tc::kThreads), tc::kSmemBytes, st, a);
+  return launch_tc<tc::kModeExtend, false>(a, dim3(nqb, p->hkv, p->bs), st);
+}
+
+// Shared-prefix ("cascade") leg of b200_attn_decode (decode.cu): the decode queries of the whole batch against the
+// hdr[kHdrShared] leading tokens that every request shares (same slot ids), as one dense tcgen05 contraction per kv
+// head split `nsplit` ways along the keys; writes fp32 partials that merge_kernel folds in with the per-request
+// suffix partials.  head_dim 128 only; returns B200_ERR_UNSUPPORTED otherwise (the caller then leaves cascade off).
+int launch_shared_prefix_tc(const b200_decode_params* p, const int* hdr, const int* req32, float* cas_o, float* cas_lse, int nsplit,
+                            cudaStream_t st) {
+  const int g = p->hq / p->hkv;
+  if (p->d != 128 || p->dv != 128 || tc::kRows % g != 0) return B200_ERR_UNSUPPORTED;
+  const bool fp8 = p->kv_dtype == B200_KV_FP8_E4M3;
+  tc::Args a{};
+  a.q = static_cast<const __nv_bfloat16*>(p->q);
+  a.q_st = p->q_stride_t;
+  a.q_sh = p->q_stride_h;
+  a.kbuf = static_cast<const uint8_t*>(p->k_buf);
+  a.vbuf = static_cast<const uint8_t*>(p->v_buf);
+  a.k_st_bytes = p->k_stride_t * (fp8 ? 1 : 2);
+  a.v_st_bytes = p->v_stride_t * (fp8 ? 1 : 2);
+  a.r2t = p->req_to_token;
+  a.r2t_stride = p->req_to_token_stride;
+  a.hq = p->hq;
+  a.hkv = p->hkv;
+  a.g = g;
+  a.bm_t = tc::kRows / g;
+  a.sm_scale = p->sm_scale;
+  a.logit_cap = p->logit_cap;
+  a.hdr = hdr;
+  a.req32 = req32;
+  a.cas_o = cas_o;
+  a.cas_lse = cas_lse;
+  a.k_scale = p->k_scale;
+  a.v_scale = p->v_scale;
+  a.bs = p->bs;
+  const dim3 grid((p->bs + a.bm_t - 1) / a.bm_t, p->hkv, nsplit);
+  return fp8 ? launch_tc<tc::kModeShared, true>(a, grid, st) : launch_tc<tc::kModeShared, false>(a, grid, st);
 }
 
 }  // namespace b200

@@ -259,3 +259,65 @@ def test_fused_kv_pool_layout_decode_store_extend(kv, monkeypatch):
     pool = runner.token_to_kv_pool
     assert torch.equal(pool.k_buffer[0].cpu().contiguous().view(torch.uint8), kb.view(torch.uint8))
     assert torch.equal(pool.v_buffer[0].cpu().contiguous().view(torch.uint8), vb.view(torch.uint8))
+
+
+# ---- shared-prefix cascade: dense tcgen05 leg over the prefix the whole batch shares ----
+def _shared_len(backend):
+    return int(backend.workspace[:64].view(torch.int32)[7].item())
+
+
+def _run_full(c, **kw):
+    return G.run_decode_case(c["q"], c["k_buf"], c["v_buf"], c["req_to_token"], c["req_pool_indices"],
+                             c["seq_lens"], c["sm_scale"], 0.0, c.get("kv_dtype", torch.bfloat16),
+                             c.get("k_scale"), c.get("v_scale"), **kw)
+
+
+CASCADE_SHAPES = [
+    # hq, hkv, bs
+    (32, 8, 24),   # Llama-3.1-8B TP1, g=4: 96 query rows per kv head (one partial 256-row block)
+    (8, 1, 40),    # 70B TP8 shard, g=8: 320 rows -> two row blocks, the second partial
+    (4, 4, 70),    # MHA
+]
+
+
+@pytest.mark.parametrize("hq,hkv,bs", CASCADE_SHAPES)
+@pytest.mark.parametrize("kv", ["bf16", "fp8"])
+def test_decode_cascade_matches_oracle_and_split_kv(hq, hkv, bs, kv):
+    kv_dtype = torch.bfloat16 if kv == "bf16" else torch.float8_e4m3fn
+    tol = (G.BF16_ABS, G.BF16_REL) if kv == "bf16" else (G.FP8_ABS, G.FP8_REL)
+    shared = 1300  # -> 1280 tokens through the dense leg, 20 + suffix through the split-KV kernel
+    gen = torch.Generator().manual_seed(bs)
+    lens = [shared + int(x) for x in torch.randint(1, 400, (bs,), generator=gen)]
+    lens[0], lens[1] = shared + 1, shared + 333
+    c = G.random_decode_case(hq, hkv, 128, lens, seed=7 * hq + bs, kv_dtype=kv_dtype, shared_prefix=shared)
+    got, backend = _run_full(c, cascade=True)[:2]
+    assert _shared_len(backend) == 1280, "the shared prefix was not detected"
+    ref = _oracle(c)
+    G.assert_close(got, ref, *tol, what=f"cascade {hq}/{hkv}/{bs}/{kv}")
+    off, backend_off = _run_full(c, cascade=False)[:2]
+    assert _shared_len(backend_off) == 0
+    G.assert_close(got, off, *tol, what="cascade vs split-KV only")
+
+
+def test_decode_cascade_partial_sharing_and_off_cases():
+    # one request leaves the common prefix early: the detected length is the batch minimum, rounded down to 128
+    c = G.random_decode_case(32, 8, 128, [2100] * 20, seed=11, shared_prefix=2048)
+    r = int(c["req_pool_indices"][5])
+    c["req_to_token"][r, 1100:2048] = c["req_to_token"][r, 1100:2048].flip(0)  # same slots, other order: prefix ends at 1100
+    got, backend = _run_full(c, cascade=True)[:2]
+    assert _shared_len(backend) == 1024
+    G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, what="partial sharing")
+    # below the 1024-token threshold, or too few query rows, the cascade leaves the batch alone: bit-identical output
+    for lens, sp in (([900 + i for i in range(20)], 800), ([1500, 1501, 1502], 1408)):
+        c = G.random_decode_case(32, 8, 128, lens, seed=12, shared_prefix=sp)
+        on, backend = _run_full(c, cascade=True)[:2]
+        assert _shared_len(backend) == 0
+        assert torch.equal(on, _run_full(c, cascade=False)[0])
+
+
+def test_decode_cascade_logit_cap_and_int32_indices():
+    c = G.random_decode_case(32, 8, 128, [1200 + 7 * i for i in range(18)], seed=13, shared_prefix=1152)
+    got, backend = G.run_decode_case(c["q"], c["k_buf"], c["v_buf"], c["req_to_token"], c["req_pool_indices"],
+                                     c["seq_lens"], c["sm_scale"], 20.0, idx_dtype=torch.int32, cascade=True)[:2]
+    assert _shared_len(backend) == 1152
+    G.assert_close(got, _oracle(c, 20.0), G.BF16_ABS, G.BF16_REL, what="cascade + softcap")

@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--layers", type=int, default=0, help="distinct per-layer KV pools rotated (0 = auto)")
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="device-resident leg: replay one CUDA graph per layer-call (engine default) or eager calls")
+    ap.add_argument("--cascade", default="on", choices=["on", "off"],
+                    help="shared-prefix cascade decode (dense tcgen05 leg over the prefix the whole batch shares)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -200,7 +202,7 @@ def build_state(args, rank, world):
                                      pool_tokens=pool_tokens, max_reqs=w.batch, context_len=max(seq_lens) + 1,
                                      kv_dtype=w.kv_dtype, device=dev, fused_kv=fused)
     fill_pool(runner.token_to_kv_pool, 1000 + rank % max(world, 1))
-    backend = CudaB200AttnBackend(runner)
+    backend = CudaB200AttnBackend(runner, cascade=(args.cascade == "on"))
     fb = synth.make_decode_batch(runner, seq_lens, gen, mode=args.index_mode, shared_prefix=shared,
                                  idx_dtype=torch.int64, backend=backend)
     lay = [synth.make_layer(runner, i) for i in range(layers)]
@@ -422,7 +424,7 @@ def run_extend_bench(args, rank, world, local_rank, dist):
                        "step": "one forward_extend layer-call: fused KV store + causal extend attention over the "
                                "gathered prefix", "l2": "per-layer pools rotated; compute-bound"},
             "tokens_per_s": T * K / t_max,
-            "roofline": {"bound": "tensor", "kernel": "extend_mma_kernel", "achieved": ach, "peak": peak,
+            "roofline": {"bound": "tensor", "kernel": "extend_tc_kernel", "achieved": ach, "peak": peak,
                          "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                          "algorithmic_flops_per_launch": flops,
                          "peak_kind": "measured burst (MEASURED_PEAKS.json bf16_tflops)",
@@ -481,8 +483,10 @@ def main():
     from scratchpad_b200 import ForwardMode
 
     launches = {"n": 0}
-    KERNELS_PER_LAYER_CALL = 3  # kv_store_kernel, decode_mma_kernel, merge_kernel
-    KERNELS_PER_PLAN = 1        # plan_kernel
+    # the cascade leg is launched (and exits at once when nothing is shared) wherever it is supported
+    cascade_launched = bool(backend.cascade) and d == 128 and B * (hq // hkv) >= 64
+    KERNELS_PER_LAYER_CALL = 3 + int(cascade_launched)  # kv_store, [extend_tc<shared>], decode_mma, merge
+    KERNELS_PER_PLAN = 1 + int(cascade_launched)        # [lcp_kernel], plan_kernel
 
     def plan():
         backend.init_forward_metadata(fb)
@@ -661,16 +665,27 @@ def main():
         except Exception:
             pass
         achieved = st["algo_bytes"] / k_avg / 1e9
+        shared_len = int(backend.workspace[:64].view(torch.int32)[7].item())
+        cfg_out = workload_config(w, world * args.shard, args, st)
+        cfg_out["cascade"] = {"enabled": bool(backend.cascade), "launched": cascade_launched,
+                              "shared_prefix_tokens_detected": shared_len}
+        roof_kernel = "decode_mma_kernel"
+        roof_note = None
+        if shared_len > 0:
+            roof_kernel = "extend_tc_kernel<shared> + decode_mma_kernel"
+            roof_note = ("cascade active: the batch-shared prefix is read once per kv head by the dense tcgen05 leg, so "
+                         "GB/s on the logical (per-request) bytes exceeds the HBM peak by design; flops of the dense "
+                         f"leg per launch = {4 * d * hq * B * shared_len}")
         line = {
             "metric": "decode_attn_tokens_per_s", "value": B * K / t_max, "unit": "tokens/s per layer-call",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_max / K * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16" if w.kv_dtype == torch.bfloat16 else "fp8_e4m3", "data": "synthetic",
-            "config": workload_config(w, world * args.shard, args, st),
+            "config": cfg_out,
             "hbm_gbs_step": st["algo_bytes"] * world / (t_max / K) / 1e9,
             "hbm_frac_of_8tbs_per_gpu": st["algo_bytes"] / (t_max / K) / 8e12,
             "tokens_per_s_model": B * K / t_max / w.layers_total,
-            "roofline": {"bound": "hbm", "kernel": "decode_mma_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": roof_kernel, "note": roof_note, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "algorithmic_bytes_per_launch": st["algo_bytes"], "kernel_us_avg": k_avg * 1e6,
                          "kernel_us_median": k_med * 1e6, "launches_timed": len(kt), "peak_kind": peak_kind,

@@ -925,6 +925,8 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
   a.k_scale = p->k_scale;
   a.v_scale = p->v_scale;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the optional event pair brackets both attention legs (shared-prefix + split-KV), not the merge
+  if (p->ev_kernel_begin) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(p->ev_kernel_begin), st));
   // shared-prefix leg first (it exits at once when the plan found nothing shared); must match what plan decided
   int cas_splits = 0;
   float* cas_o = reinterpret_cast<float*>(ws + L.cas_o);
@@ -936,7 +938,6 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
     rc = launch_shared_prefix_tc(p, a.hdr, a.req_idx, cas_o, cas_lse, cas_splits, st);
     if (rc) return rc;
   }
-  if (p->ev_kernel_begin) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(p->ev_kernel_begin), st));
   rc = dispatch(kc, a, cfg.grid_ctas, p->hkv / kc.hpc, st, false, nullptr);
   if (rc) return rc;
   if (p->ev_kernel_end) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(p->ev_kernel_end), st));

@@ -94,6 +94,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t (&v)[4]) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -375,6 +378,63 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
   if (warp >= kProdWarp0) {
     // =========================== producers ===========================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
+    if constexpr (F16) {
+      // fp8-e4m3 pool (shared-prefix decode).  A 128-key tile is 16 KiB of e4m3 and 32 KiB of f16:
+      //  phase A  the raw rows are gathered with LDGSTS into the UPPER half of the tile's ring slot (row r at
+      //           16 KiB + 128 r), kLag tiles ahead, so the page-table and DRAM latencies overlap;
+      //  phase B  each thread widens the chunks it copied itself (cvt.rn.f16x2.e4m3x2, exact) and stores them
+      //           in the SWIZZLE_128B layout.  The f16 row r of element block 1 lands exactly on raw row r, which
+      //           the 8 lanes that share the row (same warp) have all read before any of them stores.
+      // lane & 7 = 16-byte chunk of the 128-byte raw row, rows 16q + 4pw + lane/8 (constant row & 7 per thread).
+      const int pw = warp - kProdWarp0, c8 = lane & 7, rr = 4 * pw + (lane >> 3), rr7 = rr & 7;
+      const int64_t col8 = static_cast<int64_t>(kvh) * kD + c8 * 16;
+      const uint32_t ring = sbase + kSmemRing;
+      const uint32_t raw_thread = kColBlockBytes + rr * 128 + c8 * 16;
+      const uint32_t out_thread = (c8 >> 2) * kColBlockBytes + rr * 128;
+      const uint32_t o0 = (((2 * c8) & 7) ^ rr7) << 4, o1 = (((2 * c8 + 1) & 7) ^ rr7) << 4;
+      auto widen = [&](int n) {
+        const uint32_t slot_base = ring + (n % kSlots) * kTileBytes;
+#pragma unroll
+        for (int q0 = 0; q0 < 8; q0 += 4) {  // 4 rows at a time: this warpgroup runs on 64 registers
+          uint32_t raw[4][4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ld_shared_v4(slot_base + raw_thread + (q0 + q) * 2048, raw[q]);
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t h[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              h[2 * e] = e4m3x2_to_f16x2(static_cast<uint16_t>(raw[q][e] & 0xffffu));
+              h[2 * e + 1] = e4m3x2_to_f16x2(static_cast<uint16_t>(raw[q][e] >> 16));
+            }
+            st_shared_v4(slot_base + out_thread + (q0 + q) * 2048 + o0, h[0], h[1], h[2], h[3]);
+            st_shared_v4(slot_base + out_thread + (q0 + q) * 2048 + o1, h[4], h[5], h[6], h[7]);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_full(n % kSlots));
+      };
+      const int total = 2 * nt;
+      for (int n = 0; n < total; ++n) {
+        const int j = n >> 1, is_v = n & 1, s = n % kSlots;
+        const uint8_t* pool8 = (is_v ? a.vbuf : a.kbuf) + col8;
+        const int64_t pool_st = is_v ? a.v_st_bytes : a.k_st_bytes;
+        mbar_wait(bar_empty(s), ((n / kSlots) & 1) ^ 1);
+        int slot[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) slot[q] = __ldg(row + j * kBN + 16 * q + rr);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cp_async16(ring + s * kTileBytes + raw_thread + q * 2048, kv_row_ptr(pool8, slot[q], pool_st), 16);
+        cp_async_commit();
+        if (n >= kLag) {
+          cp_async_wait<kLag>();
+          widen(n - kLag);
+        }
+      }
+      cp_async_wait<0>();
+      for (int n = max(total - kLag, 0); n < total; ++n) widen(n);
+    } else {
     // lanes 0-15 / 16-31 of warp pw copy the 16 chunks of rows 8q + 2pw / 8q + 2pw + 1, q = 0..15
     const int pw = warp - kProdWarp0, ch = lane & 15;
     const int r7 = 2 * pw + (lane >> 4);  // (row & 7) of every row this thread copies
@@ -389,33 +449,6 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       mbar_wait(bar_empty(s), ((n / kSlots) & 1) ^ 1);
       if (tid == kProdWarp0 * 32) TC_TRACE(0, n);
       const uint32_t dst0 = sbase + kSmemRing + s * kTileBytes + dst_thread;
-      if constexpr (F16) {
-        // fp8-e4m3 pool: lane & 7 = 16-byte chunk of the 128-byte row (16 values -> two f16 chunks), rows
-        // 16q + 4pw + lane/8 (again a constant row & 7 per thread); widened in registers, stored with st.shared
-        const int c8 = lane & 7, rr = 4 * pw + (lane >> 3), rr7 = rr & 7;
-        const uint8_t* pool8 = (is_v ? a.vbuf : a.kbuf) + static_cast<int64_t>(kvh) * kD + c8 * 16;
-        const uint32_t d0 = sbase + kSmemRing + s * kTileBytes + (c8 >> 2) * kColBlockBytes + rr * 128;
-        const uint32_t o0 = (((2 * c8) & 7) ^ rr7) << 4, o1 = (((2 * c8 + 1) & 7) ^ rr7) << 4;
-        uint4 raw[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          raw[q] = __ldg(reinterpret_cast<const uint4*>(kv_row_ptr(pool8, __ldg(row + j * kBN + 16 * q + rr), pool_st)));
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const uint32_t w[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
-          uint32_t h[8];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            h[2 * e] = e4m3x2_to_f16x2(static_cast<uint16_t>(w[e] & 0xffffu));
-            h[2 * e + 1] = e4m3x2_to_f16x2(static_cast<uint16_t>(w[e] >> 16));
-          }
-          st_shared_v4(d0 + q * 2048 + o0, h[0], h[1], h[2], h[3]);
-          st_shared_v4(d0 + q * 2048 + o1, h[4], h[5], h[6], h[7]);
-        }
-        fence_proxy_async();
-        mbar_arrive(bar_full(s));
-        continue;
-      }
       if ((j + 1) * kBN <= pre) {
         // tile of cached-prefix keys only: page-table lookup (L1-resident after the first touch) + one copy
         int slot[16];
@@ -441,11 +474,10 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
         mbar_arrive(bar_full((n - kLag) % kSlots));
       }
     }
-    if constexpr (!F16) {
-      cp_async_wait<0>();
-      fence_proxy_async();
-      for (int n = max(total - kLag, 0); n < total; ++n) mbar_arrive(bar_full(n % kSlots));
-    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int n = max(total - kLag, 0); n < total; ++n) mbar_arrive(bar_full(n % kSlots));
+    }  // !F16
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ============================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));

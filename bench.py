@@ -414,6 +414,12 @@ def run_extend_bench(args, rank, world, local_rank, dist):
             pass
         peak = float(peaks.get("bf16_tflops", 1590.0))
         ach = flops / (t_max / K) / 1e12
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get(f"{w.name}/{args.index_mode}/n{world}", {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         line = {
             "metric": "extend_attn_tflops", "value": ach * world, "unit": "TFLOP/s (algorithmic, causal half counted exactly)",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_max / K * 1e3, "higher_is_better": True,
@@ -425,7 +431,7 @@ def run_extend_bench(args, rank, world, local_rank, dist):
                                "gathered prefix", "l2": "per-layer pools rotated; compute-bound"},
             "tokens_per_s": T * K / t_max,
             "roofline": {"bound": "tensor", "kernel": "extend_tc_kernel", "achieved": ach, "peak": peak,
-                         "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                          "algorithmic_flops_per_launch": flops,
                          "peak_kind": "measured burst (MEASURED_PEAKS.json bf16_tflops)",
                          "note": "step time used (KV store + extend kernel); the store is <1% of the step"},

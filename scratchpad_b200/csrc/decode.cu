@@ -92,6 +92,9 @@ __global__ void __launch_bounds__(256) lcp_kernel(int* __restrict__ hdr, const i
                                                   const void* __restrict__ req, const void* __restrict__ seq, int idx64) {
   __shared__ int s_first;
   const int b = blockIdx.x, tid = threadIdx.x;
+  // rows the CUDA-graph runner pads the batch with (seq_len = fill value 1, cuda_graph_runner.py:457-465) do not
+  // take part: they get no suffix tiles and the merge leaves the shared leg out for them
+  if (b != 0 && load_idx(seq, idx64, b) <= 1) return;
   int64_t n = min(load_idx(seq, idx64, b), load_idx(seq, idx64, 0));
   if (n < 0) n = 0;
   const int32_t* mine = r2t + load_idx(req, idx64, b) * r2t_stride;
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* 
       if (s < 0) s = 0;
       seq32[i] = static_cast<int>(s);
       req32[i] = static_cast<int>(load_idx(req, idx64, i));
-      n = static_cast<int>((s - shared + tile_tokens - 1) / tile_tokens);  // shared <= every s
+      n = s > shared ? static_cast<int>((s - shared + tile_tokens - 1) / tile_tokens) : 0;  // padded rows: s = 1
     }
     int x = n;
 #pragma unroll
@@ -582,7 +585,7 @@ __global__ void __launch_bounds__(256) merge_kernel(const int* __restrict__ hdr,
                                                     const float* __restrict__ part_lse, __nv_bfloat16* __restrict__ o,
                                                     int64_t o_st, int64_t o_sh, int bs, int hq, int nsub,
                                                     const float* __restrict__ cas_o, const float* __restrict__ cas_lse,
-                                                    int cas_splits) {
+                                                    int cas_splits, const int* __restrict__ seq_len) {
   pdl_wait();
   pdl_launch_dependents();
   constexpr int VPL = DV / 32;  // floats per lane
@@ -593,7 +596,8 @@ __global__ void __launch_bounds__(256) merge_kernel(const int* __restrict__ hdr,
   const int tpc = __ldg(hdr + 1);
   const int t0 = __ldg(tile_off + b), t1 = __ldg(tile_off + b + 1);
   // partials of the shared-prefix leg (one per KV split), present when the plan found a shared prefix
-  const int ncas = (cas_splits > 0 && __ldg(hdr + kHdrShared) > 0) ? cas_splits : 0;
+  const int shared = cas_splits > 0 ? __ldg(hdr + kHdrShared) : 0;
+  const int ncas = (shared > 0 && __ldg(seq_len + b) >= shared) ? cas_splits : 0;  // graph-padding rows stay out
   __nv_bfloat16* op = o + static_cast<int64_t>(b) * o_st + static_cast<int64_t>(h) * o_sh + lane * VPL;
   float acc[VPL];
 #pragma unroll
@@ -947,11 +951,11 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
     return launch_pdl(merge_kernel<64>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
                       static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
                       static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
-                      static_cast<int>(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits);
+                      static_cast<int>(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, a.seq_len);
   return launch_pdl(merge_kernel<128>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
                     static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
                     static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
-                    static_cast<int>(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits);
+                    static_cast<int>(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, a.seq_len);
 }
 
 int b200_debug_gather(const void* buf, int64_t stride_t_bytes, int32_t row_bytes, const int32_t* req_to_token,

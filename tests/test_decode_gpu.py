@@ -321,3 +321,50 @@ def test_decode_cascade_logit_cap_and_int32_indices():
                                      c["seq_lens"], c["sm_scale"], 20.0, idx_dtype=torch.int32, cascade=True)[:2]
     assert _shared_len(backend) == 1152
     G.assert_close(got, _oracle(c, 20.0), G.BF16_ABS, G.BF16_REL, what="cascade + softcap")
+
+
+def test_decode_cascade_under_cuda_graph_with_padded_rows():
+    """One captured graph serves a batch that shares a prefix (cascade on, detected on device), with the rows the
+    graph runner pads the batch with (seq_len = fill value, req_pool_index 0), and then a batch that shares nothing."""
+    from scratchpad_b200 import CudaB200AttnBackend, ForwardBatch, ForwardMode, synth
+    hq, hkv, d, bs, real = 32, 8, 128, 24, 20
+    shared = 1300
+    lens_shared = [shared + 3 + 11 * i for i in range(real)]
+    c = G.random_decode_case(hq, hkv, d, lens_shared, seed=43, shared_prefix=shared)
+    runner = G.make_runner_from_case(c["k_buf"], c["v_buf"], c["req_to_token"], torch.bfloat16, tp_hq=hq)
+    backend = CudaB200AttnBackend(runner, cascade=True)
+    layer = synth.make_layer(runner)
+    layer.scaling = c["sm_scale"]
+    backend.init_cuda_graph_state(32)
+    s_rpi = torch.zeros(32, dtype=torch.int32, device="cuda")
+    s_sl = torch.full((32,), backend.get_cuda_graph_seq_len_fill_value(), dtype=torch.int32, device="cuda")
+    s_q = torch.zeros((bs, hq * d), dtype=torch.bfloat16, device="cuda")
+    fb = ForwardBatch(ForwardMode.DECODE, bs, s_rpi[:bs], s_sl[:bs], torch.zeros(bs, dtype=torch.int64, device="cuda"),
+                      req_to_token_pool=runner.req_to_token_pool, token_to_kv_pool=runner.token_to_kv_pool,
+                      attn_backend=backend)
+    backend.init_forward_metadata_capture_cuda_graph(bs, bs, s_rpi, s_sl, None, ForwardMode.DECODE, None)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            layer(s_q, None, None, fb, save_kv_cache=False)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        s_o = layer(s_q, None, None, fb, save_kv_cache=False)
+    lens_unshared = [40 + 37 * i for i in range(real)]  # prefixes of the same rows, shorter than the 1024-token threshold
+    for lens, want_shared in ((lens_shared, 1280), (lens_unshared, 0)):
+        s_rpi.zero_()
+        s_sl.fill_(backend.get_cuda_graph_seq_len_fill_value())
+        s_rpi[:real].copy_(c["req_pool_indices"].to(torch.int32))
+        s_sl[:real].copy_(torch.tensor(lens, dtype=torch.int32))
+        s_q.zero_()
+        s_q[:real].copy_(c["q"].reshape(real, -1))
+        backend.init_forward_metadata_replay_cuda_graph(bs, s_rpi, s_sl, sum(lens) + bs - real, None, ForwardMode.DECODE,
+                                                        None, seq_lens_cpu=None)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert _shared_len(backend) == want_shared
+        cc = dict(c, seq_lens=torch.tensor(lens))
+        G.assert_close(s_o.view(bs, hq, d)[:real].cpu(), _oracle(cc), G.BF16_ABS, G.BF16_REL, what=f"graph + cascade {want_shared}")
+        assert torch.isfinite(s_o.float()).all()

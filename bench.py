@@ -596,15 +596,29 @@ def main():
         h2d = h_qkv.numel() * 2 + h_sl.numel() * 8 + h_rpi.numel() * 8 + h_loc.numel() * 8
         d2h = h_o.numel() * 2
 
-        def e2e_step(i):
-            d_qkv.copy_(h_qkv, non_blocking=True)
-            fb.seq_lens.copy_(h_sl, non_blocking=True)
-            fb.req_pool_indices.copy_(h_rpi, non_blocking=True)
-            fb.out_cache_loc.copy_(h_loc, non_blocking=True)
-            backend.init_forward_metadata(fb)  # metadata depends on the step's seq_lens: once per call here
-            o = layers[i % L](dq, dk, dv_, fb, save_kv_cache=True)
-            h_o.copy_(o, non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the caller consumes the result
+        if graphs is not None:
+            # the engine's decode path (CudaGraphRunner.replay, cuda_graph_runner.py:443-510): copy the step's inputs
+            # into the static buffers the graph was captured on, refresh the metadata in place, replay, read o back
+            def e2e_step(i):
+                qkv.copy_(h_qkv, non_blocking=True)
+                fb.seq_lens.copy_(h_sl, non_blocking=True)
+                fb.req_pool_indices.copy_(h_rpi, non_blocking=True)
+                fb.out_cache_loc.copy_(h_loc, non_blocking=True)
+                backend.init_forward_metadata_replay_cuda_graph(B, fb.req_pool_indices, fb.seq_lens, fb.seq_lens_sum,
+                                                                None, ForwardMode.DECODE, None, seq_lens_cpu=None)
+                graphs[i % L].replay()
+                h_o.copy_(outs[i % L], non_blocking=True)
+                torch.cuda.current_stream().synchronize()  # the caller consumes the result
+        else:
+            def e2e_step(i):
+                d_qkv.copy_(h_qkv, non_blocking=True)
+                fb.seq_lens.copy_(h_sl, non_blocking=True)
+                fb.req_pool_indices.copy_(h_rpi, non_blocking=True)
+                fb.out_cache_loc.copy_(h_loc, non_blocking=True)
+                backend.init_forward_metadata(fb)  # metadata depends on the step's seq_lens: once per call here
+                o = layers[i % L](dq, dk, dv_, fb, save_kv_cache=True)
+                h_o.copy_(o, non_blocking=True)
+                torch.cuda.current_stream().synchronize()  # the caller consumes the result
 
         ke = min(K, 512)
         for i in range(min(W, 8)):
@@ -621,9 +635,10 @@ def main():
         e2e = {"value": B * ke / float(tte.item()), "unit": "tokens/s per layer-call",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke,
                "ms_per_step": float(tte.item()) / ke * 1e3,
-               "note": "pinned host q/k/v + batch metadata -> device, init_forward_metadata + forward_decode "
-                       "through the AttentionBackend surface, o -> pinned host, stream sync every step; "
-                       "KV pool and req_to_token stay device-resident (engine state)"}
+               "note": "pinned host q/k/v + batch metadata -> device, metadata hook + forward_decode through the "
+                       "AttentionBackend surface (" + ("CUDA-graph replay on static buffers, as the engine's decode "
+                       "path does" if graphs is not None else "eager launches") + "), o -> pinned host, stream sync "
+                       "every step; KV pool and req_to_token stay device-resident (engine state)"}
 
     # --- the untouched NCCL all-reduce after o_proj, timed only -----------------------------------
     allreduce_us = None

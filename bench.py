@@ -423,7 +423,8 @@ def run_extend_bench(args, rank, world, local_rank, dist):
         line = {
             "metric": "extend_attn_tflops", "value": ach * world, "unit": "TFLOP/s (algorithmic, causal half counted exactly)",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_max / K * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16" if w.kv_dtype == torch.bfloat16 else "f16 (fp8-e4m3 pool widened on chip)", "data": "synthetic",
             "config": {"workload": f"{w.name}: {w.description}", "batch": w.batch, "prefix_len": w.prefix_len,
                        "extend_len": w.extend_len, "hq_per_gpu": hq, "hkv_per_gpu": hkv, "head_dim": d,
                        "index": args.index_mode, "layers": L,

@@ -295,7 +295,6 @@ __device__ __forceinline__ uint32_t tile_off(int r, int cb, int c) {
 // scale and v_scale into the epilogue, like the split-KV kernel does.
 template <int MODE, bool F16>
 __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
-  static_assert(MODE == kModeShared || !F16, "extend over fp8 pools stays on the mma.sync kernel (extend.cu)");
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_wait();
@@ -379,37 +378,59 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     // =========================== producers ===========================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
     if constexpr (F16) {
-      // fp8-e4m3 pool (shared-prefix decode).  A 128-key tile is 16 KiB of e4m3 and 32 KiB of f16:
-      //  phase A  the raw rows are gathered with LDGSTS into the UPPER half of the tile's ring slot (row r at
-      //           16 KiB + 128 r), kLag tiles ahead, so the page-table and DRAM latencies overlap;
+      // fp8-e4m3 pool.  A 128-key tile is 16 KiB of e4m3 and 32 KiB of f16:
+      //  phase A  the raw pool rows are gathered with LDGSTS into the UPPER half of the tile's ring slot (row r
+      //           at 16 KiB + 128 r), kLag tiles ahead, so the page-table and DRAM latencies overlap;
       //  phase B  each thread widens the chunks it copied itself (cvt.rn.f16x2.e4m3x2, exact) and stores them
       //           in the SWIZZLE_128B layout.  The f16 row r of element block 1 lands exactly on raw row r, which
       //           the 8 lanes that share the row (same warp) have all read before any of them stores.
-      // lane & 7 = 16-byte chunk of the 128-byte raw row, rows 16q + 4pw + lane/8 (constant row & 7 per thread).
+      //  New tokens (extend mode; bf16, never read from the pool) are copied straight to their final place in
+      //  phase A and converted in place in phase B: bf16 -> x 1/scale -> f16, so that the per-head scale folds
+      //  into the softmax scale (K) and the epilogue (V) for pool rows and new rows alike.
+      // lane & 7 = 16-byte chunk of the 128-byte raw row = f16 chunks 2c, 2c+1; rows 16q + 4pw + lane/8
+      // (constant row & 7 per thread).
       const int pw = warp - kProdWarp0, c8 = lane & 7, rr = 4 * pw + (lane >> 3), rr7 = rr & 7;
       const int64_t col8 = static_cast<int64_t>(kvh) * kD + c8 * 16;
       const uint32_t ring = sbase + kSmemRing;
       const uint32_t raw_thread = kColBlockBytes + rr * 128 + c8 * 16;
       const uint32_t out_thread = (c8 >> 2) * kColBlockBytes + rr * 128;
       const uint32_t o0 = (((2 * c8) & 7) ^ rr7) << 4, o1 = (((2 * c8 + 1) & 7) ^ rr7) << 4;
+      const float inv_ks = a.k_scale ? 1.f / __ldg(a.k_scale + kvh) : 1.f;
+      const float inv_vs = a.v_scale ? 1.f / __ldg(a.v_scale + kvh) : 1.f;
       auto widen = [&](int n) {
         const uint32_t slot_base = ring + (n % kSlots) * kTileBytes;
+        const int p_base = (n >> 1) * kBN + rr;
+        const float inv = (n & 1) ? inv_vs : inv_ks;
 #pragma unroll
         for (int q0 = 0; q0 < 8; q0 += 4) {  // 4 rows at a time: this warpgroup runs on 64 registers
           uint32_t raw[4][4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) ld_shared_v4(slot_base + raw_thread + (q0 + q) * 2048, raw[q]);
+          for (int q = 0; q < 4; ++q)
+            if (MODE == kModeShared || p_base + 16 * (q0 + q) < pre) ld_shared_v4(slot_base + raw_thread + (q0 + q) * 2048, raw[q]);
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint32_t h[8];
+            const uint32_t dst = slot_base + out_thread + (q0 + q) * 2048;
+            if (MODE == kModeShared || p_base + 16 * (q0 + q) < pre) {
+              uint32_t h[8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              h[2 * e] = e4m3x2_to_f16x2(static_cast<uint16_t>(raw[q][e] & 0xffffu));
-              h[2 * e + 1] = e4m3x2_to_f16x2(static_cast<uint16_t>(raw[q][e] >> 16));
+              for (int e = 0; e < 4; ++e) {
+                h[2 * e] = e4m3x2_to_f16x2(static_cast<uint16_t>(raw[q][e] & 0xffffu));
+                h[2 * e + 1] = e4m3x2_to_f16x2(static_cast<uint16_t>(raw[q][e] >> 16));
+              }
+              st_shared_v4(dst + o0, h[0], h[1], h[2], h[3]);
+              st_shared_v4(dst + o1, h[4], h[5], h[6], h[7]);
+            } else {
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                uint32_t w[4];
+                ld_shared_v4(dst + (half ? o1 : o0), w);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  w[e] = pack_f16x2(__uint_as_float(w[e] << 16) * inv, __uint_as_float(w[e] & 0xffff0000u) * inv);
+                st_shared_v4(dst + (half ? o1 : o0), w[0], w[1], w[2], w[3]);
+              }
             }
-            st_shared_v4(slot_base + out_thread + (q0 + q) * 2048 + o0, h[0], h[1], h[2], h[3]);
-            st_shared_v4(slot_base + out_thread + (q0 + q) * 2048 + o1, h[4], h[5], h[6], h[7]);
           }
         }
         fence_proxy_async();
@@ -421,11 +442,29 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
         const uint8_t* pool8 = (is_v ? a.vbuf : a.kbuf) + col8;
         const int64_t pool_st = is_v ? a.v_st_bytes : a.k_st_bytes;
         mbar_wait(bar_empty(s), ((n / kSlots) & 1) ^ 1);
-        int slot[8];
+        const uint32_t slot_base = ring + s * kTileBytes;
+        if (MODE == kModeShared || (j + 1) * kBN <= pre) {
+          int slot[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) slot[q] = __ldg(row + j * kBN + 16 * q + rr);
+          for (int q = 0; q < 8; ++q) slot[q] = __ldg(row + j * kBN + 16 * q + rr);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) cp_async16(ring + s * kTileBytes + raw_thread + q * 2048, kv_row_ptr(pool8, slot[q], pool_st), 16);
+          for (int q = 0; q < 8; ++q) cp_async16(slot_base + raw_thread + q * 2048, kv_row_ptr(pool8, slot[q], pool_st), 16);
+        } else {
+          const uint8_t* fresh = reinterpret_cast<const uint8_t*>(is_v ? a.v_new : a.k_new) + static_cast<int64_t>(kvh) * (kD * 2) + c8 * 32;
+          const int64_t f_st = (is_v ? a.vn_st : a.kn_st) * 2;
+#pragma unroll 2
+          for (int q = 0; q < 8; ++q) {
+            const int p = j * kBN + 16 * q + rr, pc = min(p, kv_len - 1);
+            if (pc < pre) {
+              cp_async16(slot_base + raw_thread + q * 2048, kv_row_ptr(pool8, __ldg(row + pc), pool_st), 16);
+            } else {
+              const uint8_t* src = fresh + static_cast<int64_t>(start + pc - pre) * f_st;
+              const int nb = p < kv_len ? 16 : 0;  // keys past the end: zeros (masked by the softmax anyway)
+              cp_async16(slot_base + out_thread + q * 2048 + o0, src, nb);
+              cp_async16(slot_base + out_thread + q * 2048 + o1, src + 16, nb);
+            }
+          }
+        }
         cp_async_commit();
         if (n >= kLag) {
           cp_async_wait<kLag>();
@@ -711,7 +750,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     tc_fence_after();
     const bool live = R < live_rows;
     if constexpr (MODE == kModeExtend) {
-      const float inv = l > 0.f ? 1.f / l : 0.f;
+      const float inv = l > 0.f ? ((F16 && a.v_scale) ? __ldg(a.v_scale + kvh) : 1.f) / l : 0.f;
       __nv_bfloat16* op = a.o + static_cast<int64_t>(start + t0 + (live ? R / G : 0)) * a.o_st +
                           static_cast<int64_t>(kvh * G + (live ? R % G : 0)) * a.o_sh;
 #pragma unroll 1
@@ -781,8 +820,9 @@ static int launch_tc(const tc::Args& a, dim3 grid, cudaStream_t st) {
   return launch_pdl(kern, grid, dim3(tc::kThreads), tc::kSmemBytes, st, a);
 }
 
-// Called by b200_attn_extend (extend.cu) for head_dim 128 / bf16 pools.  Strides and pointers have been validated there.
+// Called by b200_attn_extend (extend.cu) for head_dim 128.  Strides and pointers have been validated there.
 int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
+  const bool fp8 = p->kv_dtype == B200_KV_FP8_E4M3;
   tc::Args a{};
   a.q = static_cast<const __nv_bfloat16*>(p->q);
   a.q_st = p->q_stride_t;
@@ -795,8 +835,10 @@ int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
   a.vn_sh = p->vn_stride_h;
   a.kbuf = static_cast<const uint8_t*>(p->k_buf);
   a.vbuf = static_cast<const uint8_t*>(p->v_buf);
-  a.k_st_bytes = p->k_stride_t * 2;
-  a.v_st_bytes = p->v_stride_t * 2;
+  a.k_st_bytes = p->k_stride_t * (fp8 ? 1 : 2);
+  a.v_st_bytes = p->v_stride_t * (fp8 ? 1 : 2);
+  a.k_scale = p->k_scale;
+  a.v_scale = p->v_scale;
   a.o = static_cast<__nv_bfloat16*>(p->o);
   a.o_st = p->o_stride_t;
   a.o_sh = p->o_stride_h;
@@ -814,7 +856,8 @@ int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
   a.sm_scale = p->sm_scale;
   a.logit_cap = p->logit_cap;
   const int nqb = (p->max_extend_len + a.bm_t - 1) / a.bm_t;
-  return launch_tc<tc::kModeExtend, false>(a, dim3(nqb, p->hkv, p->bs), st);
+  const dim3 grid(nqb, p->hkv, p->bs);
+  return fp8 ? launch_tc<tc::kModeExtend, true>(a, grid, st) : launch_tc<tc::kModeExtend, false>(a, grid, st);
 }
 
 // Shared-prefix ("cascade") leg of b200_attn_decode (decode.cu): the decode queries of the whole batch against the

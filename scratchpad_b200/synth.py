@@ -56,6 +56,12 @@ WORKLOADS = {
     "C4": Workload("C4", 32, 8, 128, 8, torch.bfloat16,
                    "Llama-3.1-8B chunked extend: 8x2k new tokens on 8k cached prefix, causal, bf16",
                    extend_len=2048, prefix_len=8192, layers_total=32),
+    "C4F": Workload("C4F", 32, 8, 128, 8, torch.float8_e4m3fn,
+                    "Llama-3.1-8B chunked extend: 8x2k new tokens on 8k cached prefix, causal, FP8-e4m3 KV pool",
+                    extend_len=2048, prefix_len=8192, layers_total=32),
+    "C4P": Workload("C4P", 32, 8, 128, 8, torch.bfloat16,
+                    "Llama-3.1-8B prefill without a cached prefix: 8x4k new tokens, causal, bf16",
+                    extend_len=4096, prefix_len=0, layers_total=32),
     "C5": Workload("C5", 64, 8, 128, 512, torch.float8_e4m3fn,
                    "Llama-3.1-70B decode TP=8, batch 512, mixed 1k-32k contexts, FP8 KV", ctx_min=1024,
                    ctx_max=32768, layers_total=80),

@@ -99,13 +99,25 @@ TC_CASES = [
 
 
 @pytest.mark.parametrize("hq,hkv,d,pre,ext", TC_CASES)
-def test_extend_tcgen05_path_vs_oracle(hq, hkv, d, pre, ext):
+@pytest.mark.parametrize("kv", ["bf16", "fp8"])
+def test_extend_tcgen05_path_vs_oracle(hq, hkv, d, pre, ext, kv):
     from scratchpad_b200 import _lib
-    c = G.random_extend_case(hq, hkv, d, pre, ext, seed=hq * 11 + hkv + len(pre))
+    kv_dtype = torch.bfloat16 if kv == "bf16" else torch.float8_e4m3fn
+    tol = (G.BF16_ABS, G.BF16_REL) if kv == "bf16" else (G.FP8_ABS, G.FP8_REL)
+    c = G.random_extend_case(hq, hkv, d, pre, ext, seed=hq * 11 + hkv + len(pre), kv_dtype=kv_dtype)
     got = G.run_extend_case(c, force_path=_lib.PATH_TC)[0]
-    G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, what=f"tc {hq}/{hkv}/{d}/{pre}/{ext}")
+    G.assert_close(got, _oracle(c), *tol, what=f"tc {hq}/{hkv}/{d}/{kv}/{pre}/{ext}")
     ref_path = G.run_extend_case(c, force_path=_lib.PATH_MMA)[0]
-    G.assert_close(got, ref_path, G.BF16_ABS, G.BF16_REL, what="tcgen05 vs mma.sync path")
+    G.assert_close(got, ref_path, *tol, what="tcgen05 vs mma.sync path")
+
+
+def test_extend_tcgen05_fp8_pool_per_tensor_scale_and_no_prefix():
+    """fp8-e4m3 pool on the tcgen05 path: per-tensor scales, a pure prefill (every key is a new bf16 token that is
+    rescaled by 1/scale on its way in) and a prefix|new boundary that is not a multiple of 16."""
+    from scratchpad_b200 import _lib
+    c = G.random_extend_case(32, 8, 128, [0, 77, 519], [260, 130, 9], seed=21, kv_dtype=torch.float8_e4m3fn, per_head=False)
+    got = G.run_extend_case(c, force_path=_lib.PATH_TC, save_kv_cache=True)[0]
+    G.assert_close(got, _oracle(c), G.FP8_ABS, G.FP8_REL, what="tc fp8 per-tensor")
 
 
 def test_extend_tcgen05_golden_and_logit_cap():

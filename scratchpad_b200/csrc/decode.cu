@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
 // slots of the pair are consecutive ((c + b) * nsub + sub), still L2-resident.
 // ---------------------------------------------------------------------------
 template <int DV>
-__global__ void __launch_bounds__(256) merge_kernel(const int* __restrict__ hdr, const int* __restrict__ tile_off,
+__global__ void __launch_bounds__(256, 4) merge_kernel(const int* __restrict__ hdr, const int* __restrict__ tile_off,
                                                     const float* __restrict__ part_o,
                                                     const float* __restrict__ part_lse, __nv_bfloat16* __restrict__ o,
                                                     int64_t o_st, int64_t o_sh, int bs, int hq, int nsub,
@@ -631,8 +631,35 @@ __global__ void __launch_bounds__(256) merge_kernel(const int* __restrict__ hdr,
       const int i = base + lane;
       const float w_lane = i < n ? ex2(__ldcg(part_lse + (first + i) * hq + h) - mx) : 0.f;
       const int cnt = min(32, n - base);
-      for (int j = 0; j < cnt; ++j)
-        fold(__shfl_sync(0xffffffffu, w_lane, j), part_o + ((first + base + j) * hq + h) * DV + lane * VPL);
+      // several partials per round trip: all loads of a group are issued before the first FMA consumes one (with one
+      // warp per (request, head) and few warps per SM at small shards, a load-use chain per partial was the
+      // whole kernel: 16-24 partials x L2 latency)
+      constexpr int kGroup = 32 / (VPL * 2);  // 16 registers of loads in flight: 8 partials (DV 64) or 4 (DV 128)
+      for (int j0 = 0; j0 < cnt; j0 += kGroup) {
+        float vbuf[kGroup][VPL];
+#pragma unroll
+        for (int u = 0; u < kGroup; ++u) {
+          if (j0 + u < cnt) {
+            const float* src = part_o + ((first + base + j0 + u) * hq + h) * DV + lane * VPL;
+            if constexpr (VPL == 4) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(src));
+              vbuf[u][0] = v.x; vbuf[u][1] = v.y; vbuf[u][2] = v.z; vbuf[u][3] = v.w;
+            } else {
+              const float2 v = __ldcg(reinterpret_cast<const float2*>(src));
+              vbuf[u][0] = v.x; vbuf[u][1] = v.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kGroup; ++u) {
+          if (j0 + u < cnt) {
+            const float w = __shfl_sync(0xffffffffu, w_lane, j0 + u);
+            den += w;
+#pragma unroll
+            for (int e = 0; e < VPL; ++e) acc[e] += w * vbuf[u][e];
+          }
+        }
+      }
     }
     if (ncas > 0) {
       const float w_lane = lane < ncas ? ex2(__ldcg(cas_lse + lane * cas_st + cas_i) - mx) : 0.f;

@@ -47,6 +47,8 @@ def parse_args():
                     help="device-resident leg: replay one CUDA graph per layer-call (engine default) or eager calls")
     ap.add_argument("--cascade", default="on", choices=["on", "off"],
                     help="shared-prefix cascade decode (dense tcgen05 leg over the prefix the whole batch shares)")
+    ap.add_argument("--force-path", default="auto", choices=["auto", "mma", "tc"],
+                    help="extend workloads: kernel family (mma = legacy mma.sync kernel, tc = tcgen05/TMEM kernel)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -342,7 +344,7 @@ def run_extend_bench(args, rank, world, local_rank, dist):
                                      max_reqs=w.batch, context_len=w.prefix_len + w.extend_len + 1,
                                      kv_dtype=w.kv_dtype, device=str(dev))
     fill_pool(runner.token_to_kv_pool, 1000 + rank % max(world, 1))
-    backend = CudaB200AttnBackend(runner)
+    backend = CudaB200AttnBackend(runner, force_path={"auto": -1, "mma": 0, "tc": 1}[args.force_path])
     gen = torch.Generator().manual_seed(args.seed)
     fb = synth.make_extend_batch(runner, pre, ext, gen, mode=args.index_mode, backend=backend)
     layers = [synth.make_layer(runner, i) for i in range(L)]
@@ -427,7 +429,7 @@ def run_extend_bench(args, rank, world, local_rank, dist):
             "dtype": "bf16" if w.kv_dtype == torch.bfloat16 else "f16 (fp8-e4m3 pool widened on chip)", "data": "synthetic",
             "config": {"workload": f"{w.name}: {w.description}", "batch": w.batch, "prefix_len": w.prefix_len,
                        "extend_len": w.extend_len, "hq_per_gpu": hq, "hkv_per_gpu": hkv, "head_dim": d,
-                       "index": args.index_mode, "layers": L,
+                       "index": args.index_mode, "layers": L, "kernel_family": args.force_path,
                        "step": "one forward_extend layer-call: fused KV store + causal extend attention over the "
                                "gathered prefix", "l2": "per-layer pools rotated; compute-bound"},
             "tokens_per_s": T * K / t_max,

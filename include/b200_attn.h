@@ -45,7 +45,7 @@ extern "C" {
 #define B200_IDX_I64 1
 /* compute path (b200_attn_config.path) */
 #define B200_PATH_MMA 0  /* GQA-packed register-level tensor-core path (mma.sync m16n8k16): decode, generic extend */
-#define B200_PATH_TC 1   /* extend only: tcgen05 + TMEM path (head_dim 128, bf16 pool) */
+#define B200_PATH_TC 1   /* extend only: tcgen05 + TMEM path (head_dim 128, bf16 or fp8 pool; head_dim 64, bf16 pool) */
 
 /* error codes (cuda errors are reported as 1000 + cudaError_t) */
 #define B200_OK 0
@@ -153,7 +153,7 @@ int b200_attn_get_config(int32_t max_bs, int32_t hq, int32_t hkv, int32_t d, int
  * memory/radix_cache.py:105-135), rounded down to 128 tokens and used when >= 1024.  b200_attn_decode then
  * computes that prefix once per kv head as a dense tcgen05 contraction over all queries of the batch and
  * only the per-request suffixes through the split-KV kernel; the LSE merge combines both.  Detection is
- * on device (no host sync, CUDA-graph safe); head_dim 128 only, otherwise the flag is ignored.
+ * on device (no host sync, CUDA-graph safe); head_dim 128, or 64 with a bf16 pool; otherwise the flag is ignored.
  * req_to_token may be NULL when cascade == 0. */
 int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs,
                    const void* req_pool_indices, const void* seq_lens, int32_t idx_dtype,

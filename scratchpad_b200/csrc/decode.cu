@@ -880,8 +880,9 @@ int b200_attn_get_config(int32_t max_bs, int32_t hq, int32_t hkv, int32_t d, int
 }
 
 // cascade is honoured only where the dense leg exists and is worth launching
-static bool cascade_supported(int bs, int hq, int hkv, int d, int dv) {
-  return d == 128 && dv == 128 && hkv > 0 && 256 % (hq / hkv) == 0 && bs * (hq / hkv) >= kMinCasRows;
+static bool cascade_supported(int bs, int hq, int hkv, int d, int dv, int kv_dtype) {
+  const bool shape_ok = d == dv && (d == 128 || (d == 64 && kv_dtype == B200_KV_BF16));
+  return shape_ok && hkv > 0 && 256 % (hq / hkv) == 0 && bs * (hq / hkv) >= kMinCasRows;
 }
 
 int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs, const void* req_pool_indices,
@@ -897,7 +898,7 @@ int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs, co
   const WsLayout L = ws_layout(max_bs, cfg.grid_ctas, cfg.sub_splits, hq, dv);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int use_cascade = cascade && cascade_supported(bs, hq, hkv, d, dv);
+  const int use_cascade = cascade && cascade_supported(bs, hq, hkv, d, dv, kv_dtype);
   if (use_cascade) {
     B200_CUDA_TRY(cudaMemsetAsync(reinterpret_cast<int*>(ws) + kHdrLcp, 0x7f, sizeof(int), st));
     lcp_kernel<<<bs, 256, 0, st>>>(reinterpret_cast<int*>(ws), req_to_token, req_to_token_stride, req_pool_indices, seq_lens,
@@ -962,7 +963,7 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
   int cas_splits = 0;
   float* cas_o = reinterpret_cast<float*>(ws + L.cas_o);
   float* cas_lse = reinterpret_cast<float*>(ws + L.cas_lse);
-  if (p->cascade && cascade_supported(p->bs, p->hq, p->hkv, p->d, p->dv)) {
+  if (p->cascade && cascade_supported(p->bs, p->hq, p->hkv, p->d, p->dv, p->kv_dtype)) {
     const int g = p->hq / p->hkv, row_blocks = (p->bs * g + 255) / 256;
     cas_splits = cfg.num_sms / (row_blocks * p->hkv);
     cas_splits = cas_splits < 1 ? 1 : (cas_splits > kMaxCasSplits ? kMaxCasSplits : cas_splits);

@@ -37,7 +37,7 @@
 namespace b200 {
 namespace tc {
 
-constexpr int kD = 128;
+constexpr int kD = 128;                    // widest head_dim; ring slots and Q regions are sized for it (head_dim 64 uses half)
 constexpr int kBN = 128;                   // keys per tile
 constexpr int kTileRows = 128;             // rows per Q tile (UMMA M)
 constexpr int kRows = 2 * kTileRows;       // query rows per CTA
@@ -293,8 +293,9 @@ __device__ __forceinline__ uint32_t tile_off(int r, int cb, int c) {
 // KV split); F16 = the pool is fp8-e4m3: K/V are widened to f16 on their way into shared memory (exact), Q is
 // narrowed bf16 -> f16 (exact for |q| >= 2^-14) and the MMAs run as f16 x f16; k_scale folds into the softmax
 // scale and v_scale into the epilogue, like the split-KV kernel does.
-template <int MODE, bool F16>
+template <int MODE, bool F16, int D>
 __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
+  static_assert(D == 128 || (D == 64 && !F16), "head_dim 64 over an fp8 pool stays on the mma.sync kernels");
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_wait();
@@ -474,35 +475,38 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       cp_async_wait<0>();
       for (int n = max(total - kLag, 0); n < total; ++n) widen(n);
     } else {
-    // lanes 0-15 / 16-31 of warp pw copy the 16 chunks of rows 8q + 2pw / 8q + 2pw + 1, q = 0..15
-    const int pw = warp - kProdWarp0, ch = lane & 15;
-    const int r7 = 2 * pw + (lane >> 4);  // (row & 7) of every row this thread copies
-    const uint32_t dst_thread = (ch >> 3) * kColBlockBytes + r7 * 128 + (((ch & 7) ^ r7) << 4);
-    const int64_t col_bytes = static_cast<int64_t>(kvh) * (kD * 2) + ch * 16;
+    // A (token, kv-head) row is D*2 bytes = CPR 16-byte chunks, so a warp instruction covers RPI = 32/CPR rows
+    // (head_dim 128: 2 rows, head_dim 64: 4 rows) and a thread copies chunk `ch` of rows STEP*q + RPI*pw + lane/CPR,
+    // q = 0..NQ-1 (STEP = 4*RPI is a multiple of 8, so row & 7 is a per-thread constant).
+    constexpr int CPR = D / 8, RPI = 32 / CPR, STEP = 4 * RPI, NQ = kBN / STEP;
+    const int pw = warp - kProdWarp0, ch = lane % CPR;
+    const int rr = RPI * pw + lane / CPR, r7 = rr & 7;
+    const uint32_t dst_thread = (ch >> 3) * kColBlockBytes + rr * 128 + (((ch & 7) ^ r7) << 4);
+    const int64_t col_bytes = static_cast<int64_t>(kvh) * (D * 2) + ch * 16;
     const int total = 2 * nt;
     for (int n = 0; n < total; ++n) {
       const int j = n >> 1, is_v = n & 1, s = n % kSlots;
       const uint8_t* pool = (is_v ? a.vbuf : a.kbuf) + col_bytes;
       const int64_t pool_st = is_v ? a.v_st_bytes : a.k_st_bytes;
-      const int p0 = j * kBN + r7;
+      const int p0 = j * kBN + rr;
       mbar_wait(bar_empty(s), ((n / kSlots) & 1) ^ 1);
       if (tid == kProdWarp0 * 32) TC_TRACE(0, n);
       const uint32_t dst0 = sbase + kSmemRing + s * kTileBytes + dst_thread;
       if ((j + 1) * kBN <= pre) {
         // tile of cached-prefix keys only: page-table lookup (L1-resident after the first touch) + one copy
-        int slot[16];
+        int slot[NQ];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) slot[q] = __ldg(row + p0 + 8 * q);
+        for (int q = 0; q < NQ; ++q) slot[q] = __ldg(row + p0 + STEP * q);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) cp_async16(dst0 + q * 1024, kv_row_ptr(pool, slot[q], pool_st), 16);
+        for (int q = 0; q < NQ; ++q) cp_async16(dst0 + q * (STEP * 128), kv_row_ptr(pool, slot[q], pool_st), 16);
       } else {
         const uint8_t* fresh = reinterpret_cast<const uint8_t*>(is_v ? a.v_new : a.k_new) + col_bytes;
         const int64_t f_st = (is_v ? a.vn_st : a.kn_st) * 2;
 #pragma unroll 4
-        for (int q = 0; q < 16; ++q) {
-          const int p = p0 + 8 * q, pc = min(p, kv_len - 1);
+        for (int q = 0; q < NQ; ++q) {
+          const int p = p0 + STEP * q, pc = min(p, kv_len - 1);
           const uint8_t* src = pc < pre ? kv_row_ptr(pool, __ldg(row + pc), pool_st) : fresh + static_cast<int64_t>(start + pc - pre) * f_st;
-          cp_async16(dst0 + q * 1024, src, p < kv_len ? 16 : 0);
+          cp_async16(dst0 + q * (STEP * 128), src, p < kv_len ? 16 : 0);
         }
       }
       cp_async_commit();
@@ -525,14 +529,14 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     const bool leader = lane == 0;
     {
       constexpr uint32_t idesc_qk = instr_desc(kTileRows, kBN, false, F16);
-      constexpr uint32_t idesc_pv = instr_desc(kTileRows, kD, true, F16);
+      constexpr uint32_t idesc_pv = instr_desc(kTileRows, D, true, F16);
       const uint32_t q_base = sbase + kSmemQ;
       const uint32_t ring = sbase + kSmemRing;
       auto issue_qk = [&](int i, uint32_t k_base) {  // S_i = Q_i . K^T
         const uint32_t d = tmem + (i ? kColS1 : kColS0);
         const uint32_t qlo = desc_lo(q_base + i * kTileBytes, 16), klo = desc_lo(k_base, 16);
 #pragma unroll
-        for (int kc = 0; kc < kD / 16; ++kc) {
+        for (int kc = 0; kc < D / 16; ++kc) {
           const uint32_t off16 = ((kc >> 2) * kColBlockBytes + (kc & 3) * 32) >> 4;
           if (leader) tc_mma_ss(d, desc_from(qlo + off16, 1024), desc_from(klo + off16, 1024), idesc_qk, kc > 0);
         }
@@ -592,8 +596,8 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
     // Q tiles first (the 256 softmax threads are idle until the first S lands):
     // row R = i*128 + r -> (token t0 + R/G, head kvh*G + R%G)
-    for (int idx = tid; idx < kRows * 16; idx += kSoftmaxWarps * 32) {
-      const int R = idx >> 4, ch = idx & 15;
+    for (int idx = tid; idx < kRows * (D / 8); idx += kSoftmaxWarps * 32) {
+      const int R = idx / (D / 8), ch = idx % (D / 8);
       const bool live = R < live_rows;
       const int t = t0 + (live ? R / G : 0), h = kvh * G + (live ? R % G : 0);
       const __nv_bfloat16* src = a.q + static_cast<int64_t>(start + t) * a.q_st + static_cast<int64_t>(h) * a.q_sh + ch * 8;
@@ -675,7 +679,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
           m = mn;
           l *= alpha;
 #pragma unroll 1
-          for (int c4 = 0; c4 < 4; ++c4) {
+          for (int c4 = 0; c4 < D / 32; ++c4) {
             uint32_t w[32];
             tc_ld32(o_addr + c4 * 32, w);
             tc_wait_ld();
@@ -754,7 +758,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       __nv_bfloat16* op = a.o + static_cast<int64_t>(start + t0 + (live ? R / G : 0)) * a.o_st +
                           static_cast<int64_t>(kvh * G + (live ? R % G : 0)) * a.o_sh;
 #pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
+      for (int c4 = 0; c4 < D / 32; ++c4) {
         uint32_t w[32];
         tc_ld32(o_addr + c4 * 32, w);
         tc_wait_ld();
@@ -775,9 +779,9 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       const float inv = l > 0.f ? vs / l : 0.f;
       const int64_t pi = (static_cast<int64_t>(cas_split) * a.bs + t0 + (live ? R / G : 0)) * a.hq + kvh * G + (live ? R % G : 0);
       if (live) a.cas_lse[pi] = l > 0.f ? m + lg2(l) : -INFINITY;
-      float* op = a.cas_o + pi * kD;
+      float* op = a.cas_o + pi * D;
 #pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
+      for (int c4 = 0; c4 < D / 32; ++c4) {
         uint32_t w[32];
         tc_ld32(o_addr + c4 * 32, w);
         tc_wait_ld();
@@ -809,9 +813,9 @@ extern "C" int b200_debug_tc_trace_read(long long* host_dst) {
 }
 #endif
 
-template <int MODE, bool F16>
+template <int MODE, bool F16, int D>
 static int launch_tc(const tc::Args& a, dim3 grid, cudaStream_t st) {
-  auto kern = tc::extend_tc_kernel<MODE, F16>;
+  auto kern = tc::extend_tc_kernel<MODE, F16, D>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
@@ -820,7 +824,7 @@ static int launch_tc(const tc::Args& a, dim3 grid, cudaStream_t st) {
   return launch_pdl(kern, grid, dim3(tc::kThreads), tc::kSmemBytes, st, a);
 }
 
-// Called by b200_attn_extend (extend.cu) for head_dim 128.  Strides and pointers have been validated there.
+// Called by b200_attn_extend (extend.cu) for head_dim 128 (bf16 or fp8 pool) and 64 (bf16 pool).  Strides and pointers have been validated there.
 int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
   const bool fp8 = p->kv_dtype == B200_KV_FP8_E4M3;
   tc::Args a{};
@@ -857,7 +861,8 @@ int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
   a.logit_cap = p->logit_cap;
   const int nqb = (p->max_extend_len + a.bm_t - 1) / a.bm_t;
   const dim3 grid(nqb, p->hkv, p->bs);
-  return fp8 ? launch_tc<tc::kModeExtend, true>(a, grid, st) : launch_tc<tc::kModeExtend, false>(a, grid, st);
+  if (p->d == 64) return fp8 ? B200_ERR_UNSUPPORTED : launch_tc<tc::kModeExtend, false, 64>(a, grid, st);
+  return fp8 ? launch_tc<tc::kModeExtend, true, 128>(a, grid, st) : launch_tc<tc::kModeExtend, false, 128>(a, grid, st);
 }
 
 // Shared-prefix ("cascade") leg of b200_attn_decode (decode.cu): the decode queries of the whole batch against the
@@ -867,8 +872,8 @@ int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
 int launch_shared_prefix_tc(const b200_decode_params* p, const int* hdr, const int* req32, float* cas_o, float* cas_lse, int nsplit,
                             cudaStream_t st) {
   const int g = p->hq / p->hkv;
-  if (p->d != 128 || p->dv != 128 || tc::kRows % g != 0) return B200_ERR_UNSUPPORTED;
   const bool fp8 = p->kv_dtype == B200_KV_FP8_E4M3;
+  if (p->d != p->dv || tc::kRows % g != 0 || !(p->d == 128 || (p->d == 64 && !fp8))) return B200_ERR_UNSUPPORTED;
   tc::Args a{};
   a.q = static_cast<const __nv_bfloat16*>(p->q);
   a.q_st = p->q_stride_t;
@@ -893,7 +898,8 @@ int launch_shared_prefix_tc(const b200_decode_params* p, const int* hdr, const i
   a.v_scale = p->v_scale;
   a.bs = p->bs;
   const dim3 grid((p->bs + a.bm_t - 1) / a.bm_t, p->hkv, nsplit);
-  return fp8 ? launch_tc<tc::kModeShared, true>(a, grid, st) : launch_tc<tc::kModeShared, false>(a, grid, st);
+  if (p->d == 64) return launch_tc<tc::kModeShared, false, 64>(a, grid, st);
+  return fp8 ? launch_tc<tc::kModeShared, true, 128>(a, grid, st) : launch_tc<tc::kModeShared, false, 128>(a, grid, st);
 }
 
 }  // namespace b200

@@ -140,3 +140,22 @@ def test_extend_tcgen05_large_outliers_trigger_rescale():
     c["q"] = (c["q"].float() * 2.0).to(torch.bfloat16)
     got = G.run_extend_case(c, force_path=_lib.PATH_TC)[0]
     G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, "tc rescale")
+
+
+TC64_CASES = [
+    (32, 8, 64, [63, 64, 65], [64, 63, 200]),       # Llama-3.2-1B shapes, tile-boundary prefixes
+    (8, 2, 64, [7, 0, 300], [5, 190, 140]),
+    (4, 4, 64, [33], [300]),                        # MHA
+    (32, 8, 64, [700], [900]),                      # many tiles: ring wrap-around
+]
+
+
+@pytest.mark.parametrize("hq,hkv,d,pre,ext", TC64_CASES)
+def test_extend_tcgen05_head_dim_64(hq, hkv, d, pre, ext):
+    from scratchpad_b200 import _lib
+    c = G.random_extend_case(hq, hkv, d, pre, ext, seed=hq * 13 + hkv + len(pre))
+    got = G.run_extend_case(c, force_path=_lib.PATH_TC)[0]
+    G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, what=f"tc d64 {hq}/{hkv}/{pre}/{ext}")
+    with pytest.raises(_lib.B200AttnError):  # head_dim 64 over an fp8 pool has no tcgen05 variant
+        c8 = G.random_extend_case(hq, hkv, d, pre, ext, seed=1, kv_dtype=torch.float8_e4m3fn)
+        G.run_extend_case(c8, force_path=_lib.PATH_TC)

@@ -62,7 +62,7 @@ constexpr int kRegsSoftmax = 192, kRegsOther = 64;  // 256*192 + 256*64 = 64 Ki 
 constexpr int kSmemQ = 0;
 constexpr int kSmemRing = 2 * kTileBytes;
 constexpr int kSmemBar = kSmemRing + kSlots * kTileBytes;  // 229376
-constexpr int kNumBars = 2 * kSlots + 1 + 2 + 2 + 2;
+constexpr int kNumBars = 2 * kSlots + 1 + 2 + 4 + 2;
 constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
 constexpr int kSmemBytes = kSmemTmemPtr + 16 + 1024;       // + alignment slack
 
@@ -348,8 +348,8 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
   auto bar_empty = [&](int s) { return bar0 + 8u * (kSlots + s); };
   const uint32_t bar_q = bar0 + 8u * (2 * kSlots);
   auto bar_s = [&](int i) { return bar0 + 8u * (2 * kSlots + 1 + i); };
-  auto bar_p = [&](int i) { return bar0 + 8u * (2 * kSlots + 3 + i); };
-  auto bar_pv = [&](int i) { return bar0 + 8u * (2 * kSlots + 5 + i); };
+  auto bar_p = [&](int i, int half) { return bar0 + 8u * (2 * kSlots + 3 + 2 * i + half); };  // P_i keys [64 half, +64) written
+  auto bar_pv = [&](int i) { return bar0 + 8u * (2 * kSlots + 7 + i); };
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sgen + kSmemTmemPtr);
 
   if (warp == kMmaWarp) {
@@ -361,7 +361,8 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       mbar_init(bar_q, kSoftmaxWarps * 32);
       for (int i = 0; i < 2; ++i) {
         mbar_init(bar_s(i), 1);
-        mbar_init(bar_p(i), 128);
+        mbar_init(bar_p(i, 0), 128);
+        mbar_init(bar_p(i, 1), 128);
         mbar_init(bar_pv(i), 1);
       }
       fence_barrier_init();
@@ -542,14 +543,18 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
         }
         if (leader) tc_commit(bar_s(i));
       };
-      auto issue_pv = [&](int i, uint32_t v_base, bool first) {  // O_i (+)= P_i . V
+      // O_i (+)= P_i . V over keys [64 half, +64): P is released in two halves, so the first four k-steps run
+      // while the softmax threads are still exponentiating the second half of the row
+      auto issue_pv = [&](int i, uint32_t v_base, bool first, int half) {
         const uint32_t d = tmem + (i ? kColO1 : kColO0);
         const uint32_t p = tmem + (i ? kColS1 : kColS0);
         const uint32_t vlo = desc_lo(v_base, kColBlockBytes);
 #pragma unroll
-        for (int ks = 0; ks < kBN / 16; ++ks)
+        for (int k4 = 0; k4 < kBN / 32; ++k4) {
+          const int ks = half * (kBN / 32) + k4;
           if (leader) tc_mma_ts(d, p + ks * 8, desc_from(vlo + ((ks * 2048) >> 4), 1024), idesc_pv, !(first && ks == 0));
-        if (leader) tc_commit(bar_pv(i));
+        }
+        if (half && leader) tc_commit(bar_pv(i));
       };
       auto slot_of = [&](int n) { return n % kSlots; };
       auto wait_full = [&](int n) {
@@ -568,19 +573,25 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
         wait_full(nv);
         if (leader) TC_TRACE(2, j);
         const uint32_t v_base = ring + slot_of(nv) * kTileBytes;
-        mbar_wait(bar_p(0), j & 1);
+        mbar_wait(bar_p(0, 0), j & 1);
         tc_fence_after();
         if (leader) TC_TRACE(3, j);
-        issue_pv(0, v_base, j == 0);
+        issue_pv(0, v_base, j == 0, 0);
+        mbar_wait(bar_p(0, 1), j & 1);
+        tc_fence_after();
+        issue_pv(0, v_base, j == 0, 1);
         if (more) {
           wait_full(nk);
           if (leader) TC_TRACE(4, j);
           issue_qk(0, ring + slot_of(nk) * kTileBytes);
         }
-        mbar_wait(bar_p(1), j & 1);
+        mbar_wait(bar_p(1, 0), j & 1);
         tc_fence_after();
         if (leader) TC_TRACE(5, j);
-        issue_pv(1, v_base, j == 0);
+        issue_pv(1, v_base, j == 0, 0);
+        mbar_wait(bar_p(1, 1), j & 1);
+        tc_fence_after();
+        issue_pv(1, v_base, j == 0, 1);
         if (leader) tc_commit(bar_empty(slot_of(nv)));
         if (more) {
           issue_qk(1, ring + slot_of(nk) * kTileBytes);
@@ -715,6 +726,11 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
             pk[k >> 1] = pack2<F16>(p0, p1);
           }
           tc_st16(s_addr + c4 * 16, pk);
+          if (c4 == 1) {  // keys 0..63 of P are in TMEM: release them to the MMA warp
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_p(i, 0));
+          }
         }
         float la, lb;
         unpack_f32x2(l2, la, lb);
@@ -740,13 +756,18 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
             pk[k >> 1] = pack2<F16>(p0, p1);
           }
           tc_st16(s_addr + c4 * 16, pk);
+          if (c4 == 1) {
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_p(i, 0));
+          }
         }
       }
       if (R == 0) TC_TRACE(14, j);
       tc_wait_st();
       if (R == 0) TC_TRACE(15, j);
       tc_fence_before();
-      mbar_arrive(bar_p(i));
+      mbar_arrive(bar_p(i, 1));
       if (r == 0) TC_TRACE(8 + 3 * i, j);
     }
     // epilogue (thread = row): extend -> O_i / l as bf16; shared prefix -> fp32 partial (O_i v_scale / l, m + log2 l)

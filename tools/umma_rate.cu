@@ -23,7 +23,7 @@ __host__ __device__ constexpr uint32_t instr_desc(int m, int n, bool b_mn) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-template <int N, bool TS, int NACC>
+template <int N, bool TS, int NACC, int M = 128>
 __global__ void __launch_bounds__(128, 1) rate(int reps, long long* out) {
   extern __shared__ uint8_t raw[];
   const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(128, 1) rate(int reps, long long* out) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_slot;
   if (threadIdx.x == 0) {
-    constexpr uint32_t idesc = instr_desc(128, N, false);
+    constexpr uint32_t idesc = instr_desc(M, N, false);
     const uint64_t adesc = smem_desc(base, 16, 1024);            // A: 128 rows x 16 k (one 32-byte k-step of a 128B-swizzled block)
     const uint64_t bdesc = smem_desc(base + 65536, 16, 1024);    // B: N rows x 16 k
     const long long t0 = clock64();
@@ -76,13 +76,13 @@ __global__ void __launch_bounds__(128, 1) rate(int reps, long long* out) {
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
-template <int N, bool TS, int NACC>
+template <int N, bool TS, int NACC, int M = 128>
 void run(const char* name, int ctas) {
   const int reps = 4096, smem = 128 * 1024 + 1024 + 64;
   long long* d;
   cudaMalloc(&d, ctas * 16);
-  cudaFuncSetAttribute(rate<N, TS, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int it = 0; it < 3; ++it) rate<N, TS, NACC><<<ctas, 128, smem>>>(reps, d);
+  cudaFuncSetAttribute(rate<N, TS, NACC, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int it = 0; it < 3; ++it) rate<N, TS, NACC, M><<<ctas, 128, smem>>>(reps, d);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     printf("%s: %s\n", name, cudaGetErrorString(e));
@@ -97,14 +97,14 @@ void run(const char* name, int ctas) {
   }
   issue /= ctas * reps;
   total /= ctas * reps;
-  const double flops_per_clk = 2.0 * 128 * N * 16 / total;
+  const double flops_per_clk = 2.0 * M * N * 16 / total;
   printf("%-28s ctas=%3d  issue %.1f clk/instr  complete %.1f clk/instr  %.0f flop/clk/SM (%.0f%% of 8192)\n", name, ctas, issue, total,
          flops_per_clk, flops_per_clk / 81.92);
   cudaFree(d);
 }
 
 int main() {
-  for (int ctas : {1, 148}) {
+  for (int ctas : {148}) {
     run<64, false, 1>("SS M128 N64  1 acc", ctas);
     run<64, false, 4>("SS M128 N64  4 acc", ctas);
     run<128, false, 1>("SS M128 N128 1 acc", ctas);
@@ -113,6 +113,11 @@ int main() {
     run<128, true, 1>("TS M128 N128 1 acc", ctas);
     run<128, true, 2>("TS M128 N128 2 acc", ctas);
     run<256, true, 1>("TS M128 N256 1 acc", ctas);
+    run<128, false, 1, 64>("SS M64  N128 1 acc", ctas);
+    run<128, false, 2, 64>("SS M64  N128 2 acc", ctas);
+    run<256, false, 1, 64>("SS M64  N256 1 acc", ctas);
+    run<128, true, 1, 64>("TS M64  N128 1 acc", ctas);
+    run<128, true, 2, 64>("TS M64  N128 2 acc", ctas);
   }
   return 0;
 }

@@ -1,21 +1,26 @@
-// Extend / chunked-prefill attention on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+// Extend / chunked-prefill attention, and the shared-prefix leg of decode, on the 5th-generation tensor cores
+// (tcgen05 + TMEM), sm_100a.
 //
-// The Blackwell-native path of b200_attn_extend for head_dim 128, bf16 pools (the shape of
-// BASELINE.json config 4: Llama-3.1-8B, 8 x 2048 new tokens on an 8192-token cached prefix).
-// Same semantics as extend.cu / the reference's extend_attention_fwd
-// (scratchpad/nn/attention/triton_attn/extend_attention.py:53-226): query row t of request i sees
-// the gathered prefix slots req_to_token[r, :pre_i] (non-causal) and k_new/v_new[start_i : start_i+t+1].
+// extend_tc_kernel<MODE, F16, D>:
+//   MODE kModeExtend  the Blackwell-native path of b200_attn_extend (BASELINE.json config 4: Llama-3.1-8B, 8 x 2048
+//                     new tokens on an 8192-token cached prefix).  Same semantics as extend.cu / the reference's
+//                     extend_attention_fwd (scratchpad/nn/attention/triton_attn/extend_attention.py:53-226): query
+//                     row t of request i sees the gathered prefix slots req_to_token[r, :pre_i] (non-causal) and
+//                     k_new/v_new[start_i : start_i+t+1].
+//   MODE kModeShared  the decode queries of a whole batch against the prefix all its requests share.
+//   F16               the pool is fp8-e4m3: rows are widened to f16 on chip and the MMAs run f16 x f16.
+//   D                 head_dim 128, or 64 (bf16 pools).
 //
-// One CTA per SM, 10 warps, warp-specialised:
+// One CTA per SM, 16 warps in 4 warpgroups, warp-specialised:
 //   warps 0-3 / 4-7 : softmax warpgroups for Q tile 0 / 1 (thread = one query row = one TMEM lane);
 //                     a thread holds its whole 128-column S row in registers (one TMEM read per tile)
-//   warp  8         : MMA issuer (one elected thread issues every tcgen05.mma / tcgen05.commit)
+//   warp  8         : MMA issuer (the warp runs the loop uniformly, lane 0 issues tcgen05.mma / tcgen05.commit)
 //   warps 9-11      : idle (they only pad warpgroup 2 so that setmaxnreg can move its registers)
 //   warps 12-15     : producers -- gather K/V token rows through the page table with 16-byte cp.async
 //                     (LDGSTS) straight into the UMMA SWIZZLE_128B canonical layout.  Page size is 1, so
-//                     the gather unit is one 256-byte (token, kv-head) row; 16 lanes cover a row, a thread
-//                     always works on rows with the same (row & 7), so its swizzled destination is a
-//                     per-thread constant + 1 KiB per row and a copy costs ~3 instructions.
+//                     the gather unit is one (token, kv-head) row; a thread always works on rows with the
+//                     same (row & 7), so its swizzled destination is a per-thread constant + a fixed step
+//                     per row and a copy costs ~3 instructions.
 //                     (The TMA row gather, cp.async.bulk.tensor.2d.tile::gather4 + SWIZZLE_128B, was built
 //                     and measured first: correct -- tools/gather4_probe.cu -- but the TMA unit retires one
 //                     128-byte row segment per ~18 clk, 4500 clk per 32 KiB tile, 2x slower than the whole
@@ -24,13 +29,14 @@
 // MMA/producer warpgroups.
 // A CTA owns 256 query rows = 2 tiles x (128/g tokens x g q-heads of one kv head): GQA packing makes
 // every staged K/V tile serve the whole group and halves K/V shared-memory traffic per flop.
-// TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each; P (bf16) overwrites S in place and is
+// TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each; P (bf16/f16) overwrites S in place and is
 // the A operand of the P.V MMA straight from TMEM, so P never touches shared memory or registers of
 // another thread.  Ping-pong schedule on the tensor pipe:
 //   S0(j) S1(j) | PV0(j) S0(j+1) | PV1(j) S1(j+1) | ...
-// so the pipe works on tile 1 while warpgroup 0 does softmax and vice versa.  The O rescale is lazy
-// (only when a row maximum grows by more than 2^8), done by the softmax threads themselves.
-// K/V ring: 5 x 32 KiB slots (K_j, V_j alternate), mbarrier full (TMA complete_tx) / empty (tcgen05.commit).
+// so the pipe works on tile 1 while warpgroup 0 does softmax and vice versa; P is released in two 64-key
+// halves so the first P.V k-steps overlap the rest of the exponentials.  The O rescale is lazy (only when a
+// row maximum grows by more than 2^8), done by the softmax threads themselves.
+// K/V ring: 5 x 32 KiB slots (K_j, V_j alternate), mbarrier full (producers) / empty (tcgen05.commit).
 
 #include "common.cuh"
 

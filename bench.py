@@ -281,7 +281,13 @@ def run_reference(args, rank, world):
     w = synth.WORKLOADS[args.workload]
     gen = torch.Generator().manual_seed(args.seed)
     seq_lens = synth.workload_seq_lens(w, gen)
-    hq, hkv = w.hq_total // world, w.hkv_total // world
+    # the CPU arm has no GPUs to shard over: it always computes every head of the workload (the job the N GPUs share),
+    # with every host core (torchrun exports OMP_NUM_THREADS=1 to its workers, so the count is set explicitly)
+    hq, hkv = w.hq_total, w.hkv_total
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, RuntimeError):
+        torch.set_num_threads(os.cpu_count() or 1)
     sample = min(w.batch, 16)
     s = cpu_sample_state(w, seq_lens, hq, hkv, sample, args.seed)
     steps = min(args.steps, 64)

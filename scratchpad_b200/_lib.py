@@ -12,7 +12,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libb200attn.so")
+# B200_ATTN_LIB selects another build of the same library (kernel-tuning variants, the trace build); never a fallback
+LIB_PATH = os.environ.get("B200_ATTN_LIB") or os.path.join(_HERE, "csrc", "libb200attn.so")
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
 ABI_VERSION = 6

@@ -59,10 +59,17 @@ constexpr int kLag = 2;                    // cp.async groups a producer thread 
 #ifndef B200_TC_POLY
 #define B200_TC_POLY 0
 #endif
+#ifndef B200_TC_POLY1
+#define B200_TC_POLY1 B200_TC_POLY
+#endif
 // of every 4 score pairs, this many take the FMA-pipe exp2.  Measured on C4 (gpurun_out/r1s,r1t,r1u): 0 -> 1049,
 // 1 -> 1021, 2 -> 940 TFLOP/s: FFMA2/FADD2 retire 2 clk per warp instruction, so the polynomial costs the FMA
 // pipe what the MUFU saves; kept as a build option (B200_TC_POLY) for re-tuning.
-constexpr int kPolyPairsOf4 = B200_TC_POLY;
+constexpr int kPolyTile0 = B200_TC_POLY, kPolyTile1 = B200_TC_POLY1;  // per Q tile
+template <int V>
+struct IntTag {
+  static constexpr int value = V;
+};
 constexpr int kRegsSoftmax = 192, kRegsOther = 64;  // 256*192 + 256*64 = 64 Ki registers
 
 constexpr int kSmemQ = 0;
@@ -712,32 +719,38 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       if (fast) {
         const uint64_t sc2 = pack_f32x2(sc_log2, sc_log2), nm2 = pack_f32x2(-m, -m);
         uint64_t l2 = pack_f32x2(l, 0.f);
+        // NP of every 4 score pairs take the FMA-pipe exp2 (a compile-time constant per Q tile, see kPolyTile0/1)
+        auto exp_store = [&](auto np_tag) {
+          constexpr int NP = decltype(np_tag)::value;
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          uint32_t pk[16];
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint32_t pk[16];
 #pragma unroll
-          for (int k = 0; k < 32; k += 2) {
-            const uint64_t y =
-                fma_f32x2(pack_f32x2(__uint_as_float(v[c4 * 32 + k]), __uint_as_float(v[c4 * 32 + k + 1])), sc2, nm2);
-            float p0, p1;
-            if ((k >> 1) % 4 < kPolyPairsOf4) {
-              exp2_poly_x2(y, p0, p1);
-            } else {
-              float y0, y1;
-              unpack_f32x2(y, y0, y1);
-              p0 = ex2(y0);
-              p1 = ex2(y1);
+            for (int k = 0; k < 32; k += 2) {
+              const uint64_t y =
+                  fma_f32x2(pack_f32x2(__uint_as_float(v[c4 * 32 + k]), __uint_as_float(v[c4 * 32 + k + 1])), sc2, nm2);
+              float p0, p1;
+              if ((k >> 1) % 4 < NP) {
+                exp2_poly_x2(y, p0, p1);
+              } else {
+                float y0, y1;
+                unpack_f32x2(y, y0, y1);
+                p0 = ex2(y0);
+                p1 = ex2(y1);
+              }
+              l2 = add_f32x2(l2, pack_f32x2(p0, p1));
+              pk[k >> 1] = pack2<F16>(p0, p1);
             }
-            l2 = add_f32x2(l2, pack_f32x2(p0, p1));
-            pk[k >> 1] = pack2<F16>(p0, p1);
+            tc_st16(s_addr + c4 * 16, pk);
+            if (c4 == 1) {  // keys 0..63 of P are in TMEM: release them to the MMA warp
+              tc_wait_st();
+              tc_fence_before();
+              mbar_arrive(bar_p(i, 0));
+            }
           }
-          tc_st16(s_addr + c4 * 16, pk);
-          if (c4 == 1) {  // keys 0..63 of P are in TMEM: release them to the MMA warp
-            tc_wait_st();
-            tc_fence_before();
-            mbar_arrive(bar_p(i, 0));
-          }
-        }
+        };
+        if (kPolyTile0 == kPolyTile1 || i == 0) exp_store(IntTag<kPolyTile0>{});
+        else exp_store(IntTag<kPolyTile1>{});
         float la, lb;
         unpack_f32x2(l2, la, lb);
         l = la + lb;

@@ -161,6 +161,25 @@ __device__ __forceinline__ float e4m3_to_float(uint8_t b) {
   return __half2float(*reinterpret_cast<__half*>(&h));
 }
 
+// bf16 activation -> pool byte: e4m3_rn(bf16_rn(x / scale)), the double rounding of the reference's bf16 div_
+// followed by .to(fp8) (memory/pool.py:404-412); overflow becomes NaN exactly as torch's cast does (no saturation)
+__device__ __forceinline__ uint8_t quant_e4m3(uint16_t bf16_bits, float scale) {
+  const float x = bf16_bits_to_float(bf16_bits);
+  const float y = __bfloat162float(__float2bfloat16_rn(__fdiv_rn(x, scale)));
+  return static_cast<uint8_t>(__nv_cvt_float_to_fp8(y, __NV_NOSAT, __NV_E4M3));
+}
+// 8 bf16 (one uint4) -> 8 e4m3 bytes
+__device__ __forceinline__ uint2 quant_e4m3x8(uint4 x, float scale) {
+  const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+  uint32_t out[2] = {0u, 0u};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint16_t bits = static_cast<uint16_t>(j & 1 ? w[j >> 1] >> 16 : w[j >> 1] & 0xffffu);
+    out[j >> 2] |= static_cast<uint32_t>(quant_e4m3(bits, scale)) << (8 * (j & 3));
+  }
+  return make_uint2(out[0], out[1]);
+}
+
 // XOR swizzle of 16-byte chunks inside one (token, head) segment so that the 8
 // rows an ldmatrix phase touches land in 8 different bank groups.
 // CPS = 16-byte chunks per segment (4, 8 or 16).

@@ -10,12 +10,6 @@
 
 namespace b200 {
 
-__device__ __forceinline__ uint8_t quant_e4m3(uint16_t bf16_bits, float scale) {
-  const float x = bf16_bits_to_float(bf16_bits);
-  const float y = __bfloat162float(__float2bfloat16_rn(__fdiv_rn(x, scale)));
-  return static_cast<uint8_t>(__nv_cvt_float_to_fp8(y, __NV_NOSAT, __NV_E4M3));
-}
-
 template <bool FP8>
 __global__ void __launch_bounds__(256) kv_store_kernel(uint8_t* __restrict__ kbuf, uint8_t* __restrict__ vbuf,
                                                        int64_t k_st_bytes, int64_t v_st_bytes,
@@ -48,14 +42,7 @@ __global__ void __launch_bounds__(256) kv_store_kernel(uint8_t* __restrict__ kbu
     } else {
       const float* sp = is_v ? v_scale : k_scale;
       const float s = sp ? __ldg(sp + h) : 1.0f;
-      const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-      uint32_t out[2] = {0u, 0u};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint16_t bits = static_cast<uint16_t>(j & 1 ? w[j >> 1] >> 16 : w[j >> 1] & 0xffffu);
-        out[j >> 2] |= static_cast<uint32_t>(quant_e4m3(bits, s)) << (8 * (j & 3));
-      }
-      *reinterpret_cast<uint2*>(row + static_cast<int64_t>(h) * dd + c * 8) = make_uint2(out[0], out[1]);
+      *reinterpret_cast<uint2*>(row + static_cast<int64_t>(h) * dd + c * 8) = quant_e4m3x8(x, s);
     }
   }
 }

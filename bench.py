@@ -181,7 +181,6 @@ def pick_layers(per_layer_bytes: int, want: int, total_layers: int) -> int:
 
 
 def build_state(args, rank, world):
-    from oracle import attn_oracle as O  # byte accounting only (decode_algorithmic_bytes)
     from scratchpad_b200 import CudaB200AttnBackend, synth
 
     w = synth.WORKLOADS[args.workload]
@@ -208,7 +207,7 @@ def build_state(args, rank, world):
     fb = synth.make_decode_batch(runner, seq_lens, gen, mode=args.index_mode, shared_prefix=shared,
                                  idx_dtype=torch.int64, backend=backend)
     lay = [synth.make_layer(runner, i) for i in range(layers)]
-    algo_bytes = O.decode_algorithmic_bytes(seq_lens, hq_l, hkv_l, w.head_dim, w.head_dim, kv_elt)
+    algo_bytes = synth.decode_algorithmic_bytes(seq_lens, hq_l, hkv_l, w.head_dim, w.head_dim, kv_elt)
     uniq_tokens = need
     return dict(w=w, seq_lens=seq_lens, runner=runner, backend=backend, fb=fb, layers=lay, L=layers,
                 hq=hq_l, hkv=hkv_l, d=w.head_dim, algo_bytes=algo_bytes, kv_elt=kv_elt, fused_kv=fused,
@@ -336,7 +335,6 @@ def workload_config(w, world, args, st):
 # extend / chunked-prefill workloads (C4): tensor-bound, metric TFLOP/s
 # ----------------------------------------------------------------------------
 def run_extend_bench(args, rank, world, local_rank, dist):
-    from oracle import attn_oracle as O  # flop accounting only
     from scratchpad_b200 import CudaB200AttnBackend, synth
 
     w = synth.WORKLOADS[args.workload]
@@ -358,7 +356,7 @@ def run_extend_bench(args, rank, world, local_rank, dist):
     gq = torch.Generator(device=dev).manual_seed(77 + rank)
     qkv = torch.randn((T, (hq + 2 * hkv) * d), generator=gq, device=dev, dtype=torch.float32).to(torch.bfloat16)
     q, k, v = qkv[:, : hq * d], qkv[:, hq * d: (hq + hkv) * d], qkv[:, (hq + hkv) * d:]
-    flops = O.extend_algorithmic_flops(pre, ext, hq, d)
+    flops = synth.extend_algorithmic_flops(pre, ext, hq, d)
     K, W = min(args.steps, 64), min(max(args.warmup, 3), 8)
 
     def step(i):

@@ -203,3 +203,19 @@ def make_extend_batch(runner, prefix_lens: Sequence[int], extend_lens: Sequence[
         extend_prefix_lens_cpu=list(prefix_lens), extend_seq_lens_cpu=list(extend_lens),
         req_to_token_pool=r2t_pool, token_to_kv_pool=runner.token_to_kv_pool, attn_backend=backend,
     )
+
+
+# ---- roofline accounting: algorithmic bytes / flops of one launch ---------------------------------
+def decode_algorithmic_bytes(seq_lens: Sequence[int], hq: int, hkv: int, d: int, dv: int,
+                             kv_elt: int, q_elt: int = 2, idx_elt: int = 8, len_elt: int = 8) -> int:
+    """K/V rows of every context token + Q read + O write + one int32 slot id per token + the batch index tensors.
+    Split-KV partials and LSE are implementation traffic and excluded."""
+    tot = int(sum(int(s) for s in seq_lens))
+    b = len(seq_lens)
+    return (tot * hkv * (d + dv) * kv_elt + b * hq * d * q_elt + b * hq * dv * q_elt
+            + tot * 4 + b * (idx_elt + len_elt))
+
+
+def extend_algorithmic_flops(prefix_lens: Sequence[int], extend_lens: Sequence[int], hq: int, d: int) -> int:
+    """2 (Q.K^T) + 2 (P.V) flops per (query, visible key, head, dim); the causal half is counted exactly."""
+    return 4 * d * hq * sum(int(e) * int(p) + int(e) * (int(e) + 1) // 2 for p, e in zip(prefix_lens, extend_lens))

@@ -499,7 +499,7 @@ def main():
     # the cascade leg is launched (and exits at once when nothing is shared) wherever it is supported
     cascade_launched = bool(backend.cascade) and d == 128 and B * (hq // hkv) >= 64
     KERNELS_PER_LAYER_CALL = 3 + int(cascade_launched)  # kv_store, [extend_tc<shared>], decode_mma, merge
-    KERNELS_PER_PLAN = 1 + int(cascade_launched)        # [lcp_kernel], plan_kernel
+    KERNELS_PER_PLAN = 1 + 2 * int(cascade_launched)    # [group_kernel, lcp_kernel], plan_kernel
 
     def plan():
         backend.init_forward_metadata(fb)
@@ -696,7 +696,8 @@ def main():
         shared_len = int(backend.workspace[:64].view(torch.int32)[7].item())
         cfg_out = workload_config(w, world * args.shard, args, st)
         cfg_out["cascade"] = {"enabled": bool(backend.cascade), "launched": cascade_launched,
-                              "shared_prefix_tokens_detected": shared_len}
+                              "shared_prefix_tokens_detected": shared_len,
+                              "row_tiles": int(backend.workspace[:64].view(torch.int32)[8].item())}
         roof_kernel = "decode_mma_kernel"
         roof_note = None
         if shared_len > 0:

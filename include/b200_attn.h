@@ -148,12 +148,13 @@ int b200_attn_get_config(int32_t max_bs, int32_t hq, int32_t hkv, int32_t d, int
  * attn_logits allocation, triton_backend.py:48-68, and FlashInfer's kv_indices
  * flatten + host-side plan, flashinfer_backend.py:623-670): normalises the index
  * dtypes and balances KV tiles over the persistent grid, entirely on device. */
-/* cascade != 0 additionally looks for a prefix the WHOLE batch shares: the common prefix of the
- * req_to_token rows (RadixAttention gives requests with a common prompt the same slot ids,
- * memory/radix_cache.py:105-135), rounded down to 128 tokens and used when >= 1024.  b200_attn_decode then
- * computes that prefix once per kv head as a dense tcgen05 contraction over all queries of the batch and
- * only the per-request suffixes through the split-KV kernel; the LSE merge combines both.  Detection is
- * on device (no host sync, CUDA-graph safe); head_dim 128, or 64 with a bf16 pool; otherwise the flag is ignored.
+/* cascade != 0 additionally looks for shared prompt prefixes: requests whose req_to_token rows start with the same
+ * slot id form a prefix group (RadixAttention gives requests with a common prompt the same slot ids,
+ * memory/radix_cache.py:105-135); a group's common prefix, rounded down to 128 tokens, is used when it is >= 1024
+ * tokens and the group has >= 64 query rows per kv head.  b200_attn_decode then computes that prefix once per kv
+ * head as a dense tcgen05 contraction over all queries of the group and only the per-request suffixes through the
+ * split-KV kernel; the LSE merge combines both.  Detection is on device (no host sync, CUDA-graph safe); head_dim
+ * 128, or 64 with a bf16 pool, and bs <= 1024; otherwise the flag is ignored.
  * req_to_token may be NULL when cascade == 0. */
 int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs,
                    const void* req_pool_indices, const void* seq_lens, int32_t idx_dtype,

@@ -19,6 +19,22 @@ namespace b200 {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+// plan header words shared by decode.cu and extend_tc.cu: 7 = longest prefix any prefix group hands to the dense
+// shared-prefix leg (0 = nothing to do), 8 = number of row tiles of that leg
+constexpr int kHdrShared = 7, kHdrCasTiles = 8;
+
+// device tables the plan writes for the shared-prefix leg (decode.cu) and extend_tc.cu reads
+struct CasTables {
+  const int* hdr;
+  const int* req32;      // request -> req_to_token row
+  const int* perm;       // sorted position -> request (requests of a prefix group are adjacent)
+  const int* ct_first;   // per row tile: first sorted position, number of requests, a request whose row holds the
+  const int* ct_cnt;     //   group's shared slots, and the shared length (multiple of 128)
+  const int* ct_leader;
+  const int* ct_shared;
+  int max_tiles;
+};
+
 // ---- index helpers ---------------------------------------------------------
 __device__ __forceinline__ int64_t load_idx(const void* p, int idx64, int i) {
   return idx64 ? static_cast<const int64_t*>(p)[i] : static_cast<int64_t>(static_cast<const int32_t*>(p)[i]);

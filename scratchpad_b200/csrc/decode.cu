@@ -42,8 +42,9 @@ constexpr int kStages = 3;
 constexpr int kPlanMagic = 0x62323030;  // "b200"
 constexpr int kHdrInts = 16;
 // header words: 0 total tiles, 1 tiles per CTA, 2 CTAs used, 3 bs, 4 tile tokens, 5 grid, 6 magic,
-// 7 shared-prefix length in use (multiple of 128, 0 = none), 8 raw common-prefix length (lcp_kernel)
-constexpr int kHdrShared = 7, kHdrLcp = 8;
+// 7 / 8: kHdrShared / kHdrCasTiles (common.cuh)
+constexpr int kExtraCasTiles = 4;    // row tiles beyond ceil(bs / requests-per-tile): room for that many more prefix groups
+constexpr int kMaxGroupBs = 1024;    // prefix groups are found by one CTA; larger batches run without the cascade
 constexpr int kMaxCasSplits = 8;     // KV splits of the shared-prefix leg (workspace is sized for this many)
 constexpr int kCasTile = 128;        // its key-tile size (extend_tc.cu)
 constexpr int kMinShared = 1024;     // shorter common prefixes stay on the split-KV kernel
@@ -51,6 +52,8 @@ constexpr int kMinCasRows = 64;      // bs * g below this: the dense leg would b
 
 struct WsLayout {
   size_t tile_off, seq_len, req_idx, cta_b0, part_lse, part_o, cas_lse, cas_o, total;
+  // prefix groups (cascade): per request / per sorted position / per row tile of the shared-prefix leg
+  size_t shared32, perm, grp_of, grp_min, grp_size, grp_fin, ct_first, ct_cnt, ct_leader, ct_shared;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -77,31 +80,88 @@ static WsLayout ws_layout(int max_bs, int grid, int nsub, int hq, int dv) {
   off = align_up(off + ncas * sizeof(float), 256);
   L.cas_o = off;
   off = align_up(off + ncas * dv * sizeof(float), 256);
-  L.total = off;
+  size_t* ints[] = {&L.shared32, &L.perm, &L.grp_of, &L.grp_min, &L.grp_size, &L.grp_fin, &L.ct_first, &L.ct_cnt, &L.ct_leader, &L.ct_shared};
+  for (size_t* f : ints) {
+    *f = off;
+    off = align_up(off + (size_t)max_bs * sizeof(int), 16);
+  }
+  L.total = align_up(off, 256);
   return L;
 }
 
 // ---------------------------------------------------------------------------
-// shared-prefix detection: hdr[kHdrLcp] = min over the batch of the length of the common prefix of
-// req_to_token[req_b, :seq_b] and req_to_token[req_0, :seq_0] (RadixAttention makes requests that share
-// a prompt prefix share its slot ids -- memory/radix_cache.py:105-135 -- so equal slot ids ARE the sharing
-// information, and reading it here needs nothing from the scheduler).  One CTA per request; hdr[kHdrLcp]
-// is preset to a large value by a memset node.
+// shared-prefix detection.  RadixAttention makes requests that share a prompt prefix share its slot ids
+// (memory/radix_cache.py:105-135), so equal slot ids in req_to_token ARE the sharing information and reading it
+// here needs nothing from the scheduler.
+//   group_kernel (1 CTA): requests whose FIRST slot id is equal form a prefix group (a slot belongs to one radix
+//     node, so two requests share a prefix iff they share position 0).  Stable rank of the keys -> perm (sorted
+//     position -> request), group id = sorted position of the group's first member, group sizes.  Rows the CUDA
+//     graph runner pads the batch with (seq_len <= 1, cuda_graph_runner.py:457-465) get unique keys.
+//   lcp_kernel (1 CTA per request): length of the common prefix of the request's row and its group leader's row,
+//     at most seq - 1 (the newest token always stays in the split-KV leg); atomicMin into the group's slot.
+//   plan_kernel then rounds a group's length down to 128 tokens, drops it below kMinShared or when the group has
+//     fewer than kMinCasRows query rows per kv head, and cuts the group into row tiles for the dense leg.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lcp_kernel(int* __restrict__ hdr, const int32_t* __restrict__ r2t, int64_t r2t_stride,
-                                                  const void* __restrict__ req, const void* __restrict__ seq, int idx64) {
+__global__ void __launch_bounds__(1024) group_kernel(int* __restrict__ perm, int* __restrict__ grp_of, int* __restrict__ grp_min,
+                                                     int* __restrict__ grp_size, const int32_t* __restrict__ r2t,
+                                                     int64_t r2t_stride, const void* __restrict__ req,
+                                                     const void* __restrict__ seq, int idx64, int bs) {
+  __shared__ int key[kMaxGroupBs];
+  __shared__ int sorted_key[kMaxGroupBs];
+  __shared__ int sorted_req[kMaxGroupBs];
+  __shared__ int gstart[kMaxGroupBs];
+  __shared__ int gsize[kMaxGroupBs];
+  const int tid = threadIdx.x;  // bs <= kMaxGroupBs == blockDim.x: one request / sorted position per thread
+  if (tid < bs) {
+    const int64_t s = load_idx(seq, idx64, tid);
+    // real slot ids are > 0; padded / empty rows get distinct negative keys
+    key[tid] = s >= 2 ? __ldg(r2t + load_idx(req, idx64, tid) * r2t_stride) : -1 - tid;
+    gsize[tid] = 0;
+  }
+  __syncthreads();
+  if (tid < bs) {
+    const int k = key[tid];
+    int rank = 0;
+    for (int j = 0; j < bs; ++j) rank += (key[j] < k) || (key[j] == k && j < tid);
+    sorted_key[rank] = k;
+    sorted_req[rank] = tid;
+  }
+  __syncthreads();
+  if (tid < bs) {
+    // first sorted position of my group: binary search for the first equal key (keys are sorted)
+    const int k = sorted_key[tid];
+    int lo = 0, hi = tid;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (sorted_key[mid] < k) lo = mid + 1;
+      else hi = mid;
+    }
+    gstart[tid] = lo;
+    atomicAdd(&gsize[lo], 1);  // shared-memory atomic
+  }
+  __syncthreads();
+  if (tid < bs) {
+    perm[tid] = sorted_req[tid];
+    grp_of[sorted_req[tid]] = gstart[tid];
+    grp_size[tid] = gsize[tid];
+    grp_min[tid] = 0x7fffffff;
+  }
+}
+
+__global__ void __launch_bounds__(256) lcp_kernel(const int* __restrict__ perm, const int* __restrict__ grp_of,
+                                                  int* __restrict__ grp_min, const int32_t* __restrict__ r2t,
+                                                  int64_t r2t_stride, const void* __restrict__ req,
+                                                  const void* __restrict__ seq, int idx64) {
   __shared__ int s_first;
   const int b = blockIdx.x, tid = threadIdx.x;
-  // rows the CUDA-graph runner pads the batch with (seq_len = fill value 1, cuda_graph_runner.py:457-465) do not
-  // take part: they get no suffix tiles and the merge leaves the shared leg out for them
-  if (b != 0 && load_idx(seq, idx64, b) <= 1) return;
-  int64_t n = min(load_idx(seq, idx64, b), load_idx(seq, idx64, 0));
+  const int g = grp_of[b], leader = perm[g];
+  int64_t n = min(load_idx(seq, idx64, b), load_idx(seq, idx64, leader)) - 1;
   if (n < 0) n = 0;
   const int32_t* mine = r2t + load_idx(req, idx64, b) * r2t_stride;
-  const int32_t* ref = r2t + load_idx(req, idx64, 0) * r2t_stride;
+  const int32_t* ref = r2t + load_idx(req, idx64, leader) * r2t_stride;
   if (tid == 0) s_first = static_cast<int>(n);
   __syncthreads();
-  if (b != 0) {
+  if (b != leader) {
     for (int base = 0; base < n; base += 256 * 8) {
       int first = 0x7fffffff;
 #pragma unroll
@@ -115,29 +175,69 @@ __global__ void __launch_bounds__(256) lcp_kernel(int* __restrict__ hdr, const i
     }
   }
   __syncthreads();
-  if (tid == 0) atomicMin(hdr + kHdrLcp, s_first);
+  if (tid == 0) atomicMin(grp_min + g, s_first);
 }
 
 // ---------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------
+struct CasPlan {  // prefix-group tables of the cascade (null perm = cascade off for this batch)
+  const int* perm;
+  const int* grp_of;
+  const int* grp_min;
+  const int* grp_size;
+  int* grp_fin;
+  int max_tiles;       // capacity of the row-tile table = grid.z of the dense leg
+  int* shared32;
+  int* ct_first;
+  int* ct_cnt;
+  int* ct_leader;
+  int* ct_shared;
+  int rows_per_tile;  // requests per 256-row tile of the dense leg = 256 / g
+  int g;
+};
+
 __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* __restrict__ tile_off,
                                                     int* __restrict__ seq32, int* __restrict__ req32,
                                                     int* __restrict__ cta_b0,
                                                     const void* __restrict__ req, const void* __restrict__ seq,
-                                                    int idx64, int bs, int tile_tokens, int grid, int cascade) {
+                                                    int idx64, int bs, int tile_tokens, int grid, const CasPlan cp) {
   __shared__ int warp_sums[32];
   __shared__ int s_running;
   pdl_wait();
   pdl_launch_dependents();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_running = 0;
-  // prefix shared by the whole batch (lcp_kernel ran before us): handled by the dense tcgen05 leg, so the
-  // split-KV tiles of every request start behind it
-  int shared = 0;
-  if (cascade) {
-    shared = hdr[kHdrLcp] / kCasTile * kCasTile;
-    if (shared < kMinShared) shared = 0;
+  __shared__ int s_cas_tiles, s_max_shared;
+  if (tid == 0) s_running = s_cas_tiles = s_max_shared = 0;
+  __syncthreads();
+  // Prefix groups (group_kernel / lcp_kernel ran before us): the part of a group's common prefix that the dense
+  // tcgen05 leg takes over; the split-KV tiles of its requests start behind it.
+  // cp.grp_fin[group] = what the dense leg takes over for the group: its common prefix rounded down to 128 tokens,
+  // 0 when that is short, the group has too few query rows, or the fixed-size tile table is full
+  if (cp.perm != nullptr) {
+    for (int p0 = tid; p0 < bs; p0 += 1024) {  // sorted positions that start a group: cut it into row tiles
+      const int b = cp.perm[p0];
+      if (cp.grp_of[b] != p0) continue;
+      int sh = cp.grp_min[p0] / kCasTile * kCasTile;
+      const int size = cp.grp_size[p0], nt = (size + cp.rows_per_tile - 1) / cp.rows_per_tile;
+      if (sh < kMinShared || size * cp.g < kMinCasRows) sh = 0;
+      if (sh > 0) {
+        const int base = atomicAdd(&s_cas_tiles, nt);
+        if (base + nt > cp.max_tiles) {
+          atomicSub(&s_cas_tiles, nt);  // no room: this group stays on the split-KV kernel
+          sh = 0;
+        } else {
+          for (int k = 0; k < nt; ++k) {
+            cp.ct_first[base + k] = p0 + k * cp.rows_per_tile;
+            cp.ct_cnt[base + k] = min(cp.rows_per_tile, size - k * cp.rows_per_tile);
+            cp.ct_leader[base + k] = b;
+            cp.ct_shared[base + k] = sh;
+          }
+          atomicMax(&s_max_shared, sh);
+        }
+      }
+      cp.grp_fin[p0] = sh;
+    }
   }
   __syncthreads();
   for (int base = 0; base < bs; base += 1024) {
@@ -148,7 +248,12 @@ __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* 
       if (s < 0) s = 0;
       seq32[i] = static_cast<int>(s);
       req32[i] = static_cast<int>(load_idx(req, idx64, i));
-      n = s > shared ? static_cast<int>((s - shared + tile_tokens - 1) / tile_tokens) : 0;  // padded rows: s = 1
+      int shared = 0;
+      if (cp.perm != nullptr) {
+        shared = cp.grp_fin[cp.grp_of[i]];  // <= s - 1 by construction (lcp_kernel)
+        cp.shared32[i] = shared;
+      }
+      n = static_cast<int>((s - shared + tile_tokens - 1) / tile_tokens);
     }
     int x = n;
 #pragma unroll
@@ -204,7 +309,8 @@ __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* 
     hdr[4] = tile_tokens;
     hdr[5] = grid;
     hdr[6] = kPlanMagic;
-    hdr[kHdrShared] = shared;
+    hdr[kHdrShared] = s_max_shared;
+    hdr[kHdrCasTiles] = s_cas_tiles;
   }
 }
 
@@ -224,6 +330,7 @@ struct DecodeArgs {
   const int* seq_len;
   const int* req_idx;
   const int* cta_b0;
+  const int* shared32;  // per request: tokens the shared-prefix leg handles (null = cascade off)
   float* part_o;
   float* part_lse;
   int hq, hkv, g;
@@ -238,15 +345,15 @@ struct Cursor {
   int b_begin, b_end;  // tile range of request b
   int seq_len;
   const int32_t* row;  // req_to_token row of request b
-  int shared;          // length of the batch-shared prefix the cascade leg handles (0 = none)
 };
 
 __device__ __forceinline__ void cursor_load_req(Cursor& c, const DecodeArgs& a) {
   c.b_begin = __ldg(a.tile_off + c.b);
   c.b_end = __ldg(a.tile_off + c.b + 1);
-  // positions are relative to the end of the batch-shared prefix (0 unless the cascade leg handles it)
-  c.seq_len = __ldg(a.seq_len + c.b) - c.shared;
-  c.row = a.r2t + static_cast<int64_t>(__ldg(a.req_idx + c.b)) * a.r2t_stride + c.shared;
+  // positions are relative to the end of the prefix the cascade leg handles for this request's group (if any)
+  const int shared = a.shared32 ? __ldg(a.shared32 + c.b) : 0;
+  c.seq_len = __ldg(a.seq_len + c.b) - shared;
+  c.row = a.r2t + static_cast<int64_t>(__ldg(a.req_idx + c.b)) * a.r2t_stride + shared;
 }
 __device__ __forceinline__ bool cursor_valid(const Cursor& c) { return c.gt < c.gt_end; }
 __device__ __forceinline__ void cursor_advance(Cursor& c, const DecodeArgs& a) {
@@ -306,7 +413,6 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
   pc.gt = gt_begin;
   pc.gt_end = gt_end;
   pc.b = lo;
-  pc.shared = __ldg(a.hdr + kHdrShared);
   cursor_load_req(pc, a);
   Cursor cc = pc;  // consumer cursor
 
@@ -585,7 +691,7 @@ __global__ void __launch_bounds__(256, 4) merge_kernel(const int* __restrict__ h
                                                     const float* __restrict__ part_lse, __nv_bfloat16* __restrict__ o,
                                                     int64_t o_st, int64_t o_sh, int bs, int hq, int nsub,
                                                     const float* __restrict__ cas_o, const float* __restrict__ cas_lse,
-                                                    int cas_splits, const int* __restrict__ seq_len) {
+                                                    int cas_splits, const int* __restrict__ shared32) {
   pdl_wait();
   pdl_launch_dependents();
   constexpr int VPL = DV / 32;  // floats per lane
@@ -596,8 +702,7 @@ __global__ void __launch_bounds__(256, 4) merge_kernel(const int* __restrict__ h
   const int tpc = __ldg(hdr + 1);
   const int t0 = __ldg(tile_off + b), t1 = __ldg(tile_off + b + 1);
   // partials of the shared-prefix leg (one per KV split), present when the plan found a shared prefix
-  const int shared = cas_splits > 0 ? __ldg(hdr + kHdrShared) : 0;
-  const int ncas = (shared > 0 && __ldg(seq_len + b) >= shared) ? cas_splits : 0;  // graph-padding rows stay out
+  const int ncas = (cas_splits > 0 && __ldg(shared32 + b) > 0) ? cas_splits : 0;
   __nv_bfloat16* op = o + static_cast<int64_t>(b) * o_st + static_cast<int64_t>(h) * o_sh + lane * VPL;
   float acc[VPL];
 #pragma unroll
@@ -841,7 +946,7 @@ static int get_config(int max_bs, int hq, int hkv, int d, int dv, int kv_dtype, 
   return B200_OK;
 }
 
-int launch_shared_prefix_tc(const b200_decode_params* p, const int* hdr, const int* req32, float* cas_o, float* cas_lse, int nsplit,
+int launch_shared_prefix_tc(const b200_decode_params* p, const CasTables& t, float* cas_o, float* cas_lse, int nsplit,
                             cudaStream_t st);  // extend_tc.cu
 
 }  // namespace b200
@@ -879,6 +984,14 @@ int b200_attn_get_config(int32_t max_bs, int32_t hq, int32_t hkv, int32_t d, int
   return get_config(max_bs, hq, hkv, d, dv, kv_dtype, force_path, out);
 }
 
+// Row-tile capacity of the dense leg (its grid is fixed at launch, the plan fills the table on device): one group
+// covering the batch needs ceil(bs / requests-per-tile); every further prefix group can add one partial tile.
+static int cas_max_tiles(int bs, int g) {
+  const int rows_per_tile = 256 / g;
+  int n = (bs + rows_per_tile - 1) / rows_per_tile + kExtraCasTiles;
+  return n > bs ? bs : n;
+}
+
 // cascade is honoured only where the dense leg exists and is worth launching
 static bool cascade_supported(int bs, int hq, int hkv, int d, int dv, int kv_dtype) {
   const bool shape_ok = d == dv && (d == 128 || (d == 64 && kv_dtype == B200_KV_BF16));
@@ -898,17 +1011,34 @@ int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs, co
   const WsLayout L = ws_layout(max_bs, cfg.grid_ctas, cfg.sub_splits, hq, dv);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int use_cascade = cascade && cascade_supported(bs, hq, hkv, d, dv, kv_dtype);
+  const int use_cascade = cascade && bs <= kMaxGroupBs && cascade_supported(bs, hq, hkv, d, dv, kv_dtype);
+  auto wi = [&](size_t off) { return reinterpret_cast<int*>(ws + off); };
+  CasPlan cp{};
   if (use_cascade) {
-    B200_CUDA_TRY(cudaMemsetAsync(reinterpret_cast<int*>(ws) + kHdrLcp, 0x7f, sizeof(int), st));
-    lcp_kernel<<<bs, 256, 0, st>>>(reinterpret_cast<int*>(ws), req_to_token, req_to_token_stride, req_pool_indices, seq_lens,
-                                   idx_dtype == B200_IDX_I64);
+    const bool i64 = idx_dtype == B200_IDX_I64;
+    group_kernel<<<1, 1024, 0, st>>>(wi(L.perm), wi(L.grp_of), wi(L.grp_min), wi(L.grp_size), req_to_token, req_to_token_stride,
+                                     req_pool_indices, seq_lens, i64, bs);
+    lcp_kernel<<<bs, 256, 0, st>>>(wi(L.perm), wi(L.grp_of), wi(L.grp_min), req_to_token, req_to_token_stride, req_pool_indices,
+                                   seq_lens, i64);
     B200_CUDA_TRY(cudaGetLastError());
+    cp.perm = wi(L.perm);
+    cp.grp_of = wi(L.grp_of);
+    cp.grp_min = wi(L.grp_min);
+    cp.grp_size = wi(L.grp_size);
+    cp.grp_fin = wi(L.grp_fin);
+    cp.max_tiles = cas_max_tiles(bs, hq / hkv);
+    cp.shared32 = wi(L.shared32);
+    cp.ct_first = wi(L.ct_first);
+    cp.ct_cnt = wi(L.ct_cnt);
+    cp.ct_leader = wi(L.ct_leader);
+    cp.ct_shared = wi(L.ct_shared);
+    cp.g = hq / hkv;
+    cp.rows_per_tile = 256 / cp.g;
   }
   plan_kernel<<<1, 1024, 0, st>>>(
       reinterpret_cast<int*>(ws), reinterpret_cast<int*>(ws + L.tile_off), reinterpret_cast<int*>(ws + L.seq_len),
       reinterpret_cast<int*>(ws + L.req_idx), reinterpret_cast<int*>(ws + L.cta_b0), req_pool_indices, seq_lens, idx_dtype == B200_IDX_I64, bs,
-      cfg.tile_tokens, cfg.grid_ctas, use_cascade);
+      cfg.tile_tokens, cfg.grid_ctas, cp);
   B200_CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }
@@ -963,11 +1093,23 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
   int cas_splits = 0;
   float* cas_o = reinterpret_cast<float*>(ws + L.cas_o);
   float* cas_lse = reinterpret_cast<float*>(ws + L.cas_lse);
-  if (p->cascade && cascade_supported(p->bs, p->hq, p->hkv, p->d, p->dv, p->kv_dtype)) {
-    const int g = p->hq / p->hkv, row_blocks = (p->bs * g + 255) / 256;
+  a.shared32 = nullptr;
+  if (p->cascade && p->bs <= kMaxGroupBs && cascade_supported(p->bs, p->hq, p->hkv, p->d, p->dv, p->kv_dtype)) {
+    const int g = p->hq / p->hkv, rows_per_tile = 256 / g, row_blocks = (p->bs + rows_per_tile - 1) / rows_per_tile;
     cas_splits = cfg.num_sms / (row_blocks * p->hkv);
     cas_splits = cas_splits < 1 ? 1 : (cas_splits > kMaxCasSplits ? kMaxCasSplits : cas_splits);
-    rc = launch_shared_prefix_tc(p, a.hdr, a.req_idx, cas_o, cas_lse, cas_splits, st);
+    auto wi = [&](size_t off) { return reinterpret_cast<const int*>(ws + off); };
+    CasTables t;
+    t.hdr = a.hdr;
+    t.req32 = a.req_idx;
+    t.perm = wi(L.perm);
+    t.ct_first = wi(L.ct_first);
+    t.ct_cnt = wi(L.ct_cnt);
+    t.ct_leader = wi(L.ct_leader);
+    t.ct_shared = wi(L.ct_shared);
+    t.max_tiles = cas_max_tiles(p->bs, g);
+    a.shared32 = wi(L.shared32);
+    rc = launch_shared_prefix_tc(p, t, cas_o, cas_lse, cas_splits, st);
     if (rc) return rc;
   }
   rc = dispatch(kc, a, cfg.grid_ctas, p->hkv / kc.hpc, st, false, nullptr);
@@ -979,11 +1121,11 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
     return launch_pdl(merge_kernel<64>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
                       static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
                       static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
-                      static_cast<int>(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, a.seq_len);
+                      static_cast<int>(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
   return launch_pdl(merge_kernel<128>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
                     static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
                     static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
-                    static_cast<int>(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, a.seq_len);
+                    static_cast<int>(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
 }
 
 int b200_debug_gather(const void* buf, int64_t stride_t_bytes, int32_t row_bytes, const int32_t* req_to_token,

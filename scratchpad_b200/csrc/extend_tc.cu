@@ -284,8 +284,7 @@ struct Args {
   int hq, hkv, g, bm_t;  // bm_t = tokens (extend) or requests (shared-prefix decode) per CTA = 256 / g
   float sm_scale, logit_cap;
   // shared-prefix decode (kModeShared) only
-  const int* hdr;          // plan header: hdr[kHdrShared] = length of the prefix every request of the batch shares
-  const int* req32;        // normalised request rows (plan)
+  CasTables cas;           // prefix-group row tiles (plan)
   float* cas_o;            // [nsplit, bs, hq, 128] fp32 partial outputs, normalised
   float* cas_lse;          // [nsplit, bs, hq] log2-domain log-sum-exp
   const float* k_scale;    // per kv head (fp8 pools), or null
@@ -295,7 +294,6 @@ struct Args {
 
 constexpr int kModeExtend = 0;  // causal extend over [gathered prefix | new tokens], bf16 out
 constexpr int kModeShared = 1;  // decode queries of the whole batch against the prefix they all share, fp32 partials out
-constexpr int kHdrShared = 7;   // index into the plan header (decode.cu)
 
 // byte offset of 16-byte chunk (row r, element block cb of 64, chunk c of 8) inside a [128 x 128] bf16 tile
 __device__ __forceinline__ uint32_t tile_off(int r, int cb, int c) {
@@ -314,7 +312,10 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
   pdl_wait();
   pdl_launch_dependents();
 
-  const int kvh = blockIdx.y;
+  // extend: grid (query block, kv head, request); shared-prefix decode: grid (kv head, KV split, row tile) -- the row
+  // tile is the slowest index so that the tiles the plan actually produced are dispatched first and the unused
+  // tail of the fixed-size grid (it exits at once) drains through whatever SMs are free
+  const int kvh = MODE == kModeExtend ? blockIdx.y : blockIdx.x;
   const int G = a.g, bm_t = a.bm_t;
   // extend: token range [t0, t_end) of request b; shared: request range [t0, t_end) of the batch
   int pre, start, t0, t_end, kv_len, nt, cas_split = 0;
@@ -334,21 +335,24 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     kv_len = pre + t_end;
     nt = (kv_len + kBN - 1) / kBN;
   } else {
-    const int shared = __ldg(a.hdr + kHdrShared);  // multiple of kBN, 0 = this batch shares nothing
-    if (shared <= 0) return;
-    t0 = static_cast<int>(blockIdx.x) * bm_t;
-    t_end = min(a.bs, t0 + bm_t);
-    if (t0 >= t_end) return;
-    cas_split = blockIdx.z;
-    const int ntot = shared / kBN, ns = gridDim.z;
+    // one row tile of one prefix group: requests perm[t0 .. t_end) share `shared` leading slots (a multiple of kBN)
+    const int tile = blockIdx.z;
+    if (tile >= __ldg(a.cas.hdr + kHdrCasTiles)) return;
+    const int shared = __ldg(a.cas.ct_shared + tile);
+    t0 = __ldg(a.cas.ct_first + tile);
+    t_end = t0 + __ldg(a.cas.ct_cnt + tile);
+    cas_split = blockIdx.y;
+    const int ntot = shared / kBN, ns = gridDim.y;
     const int j0 = static_cast<int>(static_cast<int64_t>(cas_split) * ntot / ns);
     nt = static_cast<int>(static_cast<int64_t>(cas_split + 1) * ntot / ns) - j0;
-    row = a.r2t + static_cast<int64_t>(__ldg(a.req32)) * a.r2t_stride + j0 * kBN;  // request 0 holds the shared slots too
+    const int leader = __ldg(a.cas.ct_leader + tile);
+    row = a.r2t + static_cast<int64_t>(__ldg(a.cas.req32 + leader)) * a.r2t_stride + j0 * kBN;
     start = 0;
     pre = kv_len = nt * kBN;
     if (nt <= 0) {  // more splits than tiles (the plan never produces this): an empty partial
       const int R = tid;
-      if (R < (t_end - t0) * G) a.cas_lse[(static_cast<int64_t>(cas_split) * a.bs + t0 + R / G) * a.hq + kvh * G + R % G] = -INFINITY;
+      if (R < (t_end - t0) * G)
+        a.cas_lse[(static_cast<int64_t>(cas_split) * a.bs + __ldg(a.cas.perm + t0 + R / G)) * a.hq + kvh * G + R % G] = -INFINITY;
       return;
     }
   }
@@ -624,7 +628,9 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       const int R = idx / (D / 8), ch = idx % (D / 8);
       const bool live = R < live_rows;
       const int t = t0 + (live ? R / G : 0), h = kvh * G + (live ? R % G : 0);
-      const __nv_bfloat16* src = a.q + static_cast<int64_t>(start + t) * a.q_st + static_cast<int64_t>(h) * a.q_sh + ch * 8;
+      // extend: token start + t of the flattened batch; shared-prefix decode: request perm[t]
+      const int qrow = MODE == kModeExtend ? start + t : __ldg(a.cas.perm + t);
+      const __nv_bfloat16* src = a.q + static_cast<int64_t>(qrow) * a.q_st + static_cast<int64_t>(h) * a.q_sh + ch * 8;
       const uint32_t dst = sbase + kSmemQ + (R >> 7) * kTileBytes + tile_off(R & 127, ch >> 3, ch & 7);
       if constexpr (F16) {
         uint4 x = live ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0u, 0u, 0u, 0u);
@@ -817,7 +823,8 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     } else {
       const float vs = (F16 && a.v_scale) ? __ldg(a.v_scale + kvh) : 1.f;
       const float inv = l > 0.f ? vs / l : 0.f;
-      const int64_t pi = (static_cast<int64_t>(cas_split) * a.bs + t0 + (live ? R / G : 0)) * a.hq + kvh * G + (live ? R % G : 0);
+      const int req = __ldg(a.cas.perm + t0 + (live ? R / G : 0));
+      const int64_t pi = (static_cast<int64_t>(cas_split) * a.bs + req) * a.hq + kvh * G + (live ? R % G : 0);
       if (live) a.cas_lse[pi] = l > 0.f ? m + lg2(l) : -INFINITY;
       float* op = a.cas_o + pi * D;
 #pragma unroll 1
@@ -909,7 +916,7 @@ int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
 // hdr[kHdrShared] leading tokens that every request shares (same slot ids), as one dense tcgen05 contraction per kv
 // head split `nsplit` ways along the keys; writes fp32 partials that merge_kernel folds in with the per-request
 // suffix partials.  head_dim 128 only; returns B200_ERR_UNSUPPORTED otherwise (the caller then leaves cascade off).
-int launch_shared_prefix_tc(const b200_decode_params* p, const int* hdr, const int* req32, float* cas_o, float* cas_lse, int nsplit,
+int launch_shared_prefix_tc(const b200_decode_params* p, const CasTables& t, float* cas_o, float* cas_lse, int nsplit,
                             cudaStream_t st) {
   const int g = p->hq / p->hkv;
   const bool fp8 = p->kv_dtype == B200_KV_FP8_E4M3;
@@ -930,14 +937,13 @@ int launch_shared_prefix_tc(const b200_decode_params* p, const int* hdr, const i
   a.bm_t = tc::kRows / g;
   a.sm_scale = p->sm_scale;
   a.logit_cap = p->logit_cap;
-  a.hdr = hdr;
-  a.req32 = req32;
+  a.cas = t;
   a.cas_o = cas_o;
   a.cas_lse = cas_lse;
   a.k_scale = p->k_scale;
   a.v_scale = p->v_scale;
   a.bs = p->bs;
-  const dim3 grid((p->bs + a.bm_t - 1) / a.bm_t, p->hkv, nsplit);
+  const dim3 grid(p->hkv, nsplit, t.max_tiles);  // row tiles beyond hdr[kHdrCasTiles] exit at once
   if (p->d == 64) return launch_tc<tc::kModeShared, false, 64>(a, grid, st);
   return fp8 ? launch_tc<tc::kModeShared, true, 128>(a, grid, st) : launch_tc<tc::kModeShared, false, 128>(a, grid, st);
 }

@@ -381,3 +381,63 @@ def test_decode_cascade_head_dim_64():
     got, backend = _run_full(c, cascade=True)[:2]
     assert _shared_len(backend) == 0
     G.assert_close(got, _oracle(c), G.FP8_ABS, G.FP8_REL, what="d64 fp8 stays on split-KV")
+
+
+def _multi_group_case(hq, hkv, d, groups, seed, kv_dtype=torch.bfloat16):
+    """Decode case with several prefix groups: groups = [(n_requests, shared_len, max_suffix), ...]; requests of a
+    group share their first shared_len slot ids (what RadixAttention does for a common prompt), rows are shuffled."""
+    gen = torch.Generator().manual_seed(seed)
+    lens, specs = [], []
+    for gi, (n, sh, suf) in enumerate(groups):
+        for _ in range(n):
+            s = sh + int(torch.randint(1, suf + 1, (1,), generator=gen))
+            lens.append(s)
+            specs.append((gi, sh))
+    order = torch.randperm(len(lens), generator=gen).tolist()
+    lens = [lens[i] for i in order]
+    specs = [specs[i] for i in order]
+    need = sum(sh for _, sh, _ in groups) + sum(s - sh for s, (_, sh) in zip(lens, specs))
+    c = G.random_decode_case(hq, hkv, d, lens, seed=seed + 1, kv_dtype=kv_dtype)   # pools big enough? rebuild below
+    pool = need + 33
+    ids = (torch.randperm(pool, generator=gen) + 1).to(torch.int32)
+    r2t = torch.zeros((len(lens) + 3, max(lens) + 4), dtype=torch.int32)
+    r2t[:] = ids[torch.randint(0, pool, r2t.shape, generator=gen)]                # stale garbage everywhere
+    cur = 0
+    shared_ids = []
+    for _, sh, _ in groups:
+        shared_ids.append(ids[cur:cur + sh])
+        cur += sh
+    rows = torch.randperm(len(lens) + 3, generator=gen)[: len(lens)]
+    for i, (s, (gi, sh)) in enumerate(zip(lens, specs)):
+        r2t[rows[i], :sh] = shared_ids[gi]
+        r2t[rows[i], sh:s] = ids[cur:cur + s - sh]
+        cur += s - sh
+    kf = torch.randn((pool + 1, hkv, d), generator=gen).to(torch.bfloat16)
+    vf = torch.randn((pool + 1, hkv, d), generator=gen).to(torch.bfloat16)
+    ks = vs = None
+    if kv_dtype != torch.bfloat16:
+        ks = kf.float().abs().amax(dim=(0, 2)) / 448.0
+        vs = vf.float().abs().amax(dim=(0, 2)) / 448.0
+        kf, vf = O.quantize_kv_ref(kf, kv_dtype, ks), O.quantize_kv_ref(vf, kv_dtype, vs)
+    c.update(k_buf=kf, v_buf=vf, req_to_token=r2t, req_pool_indices=rows.to(torch.int64),
+             seq_lens=torch.tensor(lens, dtype=torch.int64), k_scale=ks, v_scale=vs)
+    return c, specs
+
+
+@pytest.mark.parametrize("kv", ["bf16", "fp8"])
+def test_decode_cascade_prefix_groups(kv):
+    """Several radix subtrees in one batch: each sufficiently large group gets its own dense shared-prefix leg, small
+    groups and singletons stay on the split-KV kernel; everything merges to the oracle's result."""
+    kv_dtype = torch.bfloat16 if kv == "bf16" else torch.float8_e4m3fn
+    tol = (G.BF16_ABS, G.BF16_REL) if kv == "bf16" else (G.FP8_ABS, G.FP8_REL)
+    groups = [(70, 1300, 200),   # 280 query rows per kv head: two row tiles (64 + 6 requests), shared 1280
+              (18, 2100, 60),    # one partial row tile, shared 2048
+              (5, 1500, 40),     # 20 rows: below the 64-row threshold -> split-KV only
+              (1, 0, 900), (1, 0, 33), (1, 0, 1400), (1, 0, 2)]
+    c, specs = _multi_group_case(32, 8, 128, groups, seed=71, kv_dtype=kv_dtype)
+    got, backend = _run_full(c, cascade=True)[:2]
+    ws = backend.workspace[:64].view(torch.int32)
+    assert int(ws[7]) == 2048 and int(ws[8]) == 3, (int(ws[7]), int(ws[8]))   # longest shared length, row tiles
+    G.assert_close(got, _oracle(c), *tol, what=f"prefix groups {kv}")
+    off = _run_full(c, cascade=False)[0]
+    G.assert_close(got, off, *tol, what="prefix groups vs split-KV only")

@@ -441,3 +441,18 @@ def test_decode_cascade_prefix_groups(kv):
     G.assert_close(got, _oracle(c), *tol, what=f"prefix groups {kv}")
     off = _run_full(c, cascade=False)[0]
     G.assert_close(got, off, *tol, what="prefix groups vs split-KV only")
+
+
+def test_decode_cascade_duplicate_rows_and_large_batch():
+    # the same request row twice in a batch (and hence a "shared prefix" of seq - 1 tokens): still the oracle's answer
+    c = G.random_decode_case(32, 8, 128, [1400] * 24, seed=51, shared_prefix=1300)
+    c["req_pool_indices"][1::2] = c["req_pool_indices"][0::2]          # 12 distinct rows, each listed twice
+    got, backend = _run_full(c, cascade=True)[:2]
+    assert _shared_len(backend) == 1280                                 # every pair still shares the 1300-token prompt
+    G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, what="duplicate rows")
+    # more requests than the single-CTA grouping handles (1024): the cascade switches itself off, results unchanged
+    lens = [3 + (i % 29) for i in range(1100)]
+    c = G.random_decode_case(4, 1, 128, lens, seed=52)
+    got, backend = _run_full(c, cascade=True)[:2]
+    assert _shared_len(backend) == 0
+    G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, what="bs > 1024")

@@ -45,8 +45,11 @@ def parse_args():
     ap.add_argument("--layers", type=int, default=0, help="distinct per-layer KV pools rotated (0 = auto)")
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="device-resident leg: replay one CUDA graph per layer-call (engine default) or eager calls")
-    ap.add_argument("--cascade", default="on", choices=["on", "off"],
-                    help="shared-prefix cascade decode (dense tcgen05 leg over the prefix the whole batch shares)")
+    ap.add_argument("--cascade", default="auto", choices=["auto", "on", "off"],
+                    help="shared-prefix cascade decode (server flag b200_shared_prefix_cascade; the backend's own default "
+                         "is on).  auto = what an operator would set for the deployment the workload stands for: on when "
+                         "its requests share a prompt prefix (C3), off otherwise -- an idle cascade costs one early-exit "
+                         "launch (~2 us) per layer-call")
     ap.add_argument("--force-path", default="auto", choices=["auto", "mma", "tc"],
                     help="extend workloads: kernel family (mma = legacy mma.sync kernel, tc = tcgen05/TMEM kernel)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -203,7 +206,8 @@ def build_state(args, rank, world):
                                      pool_tokens=pool_tokens, max_reqs=w.batch, context_len=max(seq_lens) + 1,
                                      kv_dtype=w.kv_dtype, device=dev, fused_kv=fused)
     fill_pool(runner.token_to_kv_pool, 1000 + rank % max(world, 1))
-    backend = CudaB200AttnBackend(runner, cascade=(args.cascade == "on"))
+    cascade = args.cascade == "on" or (args.cascade == "auto" and w.shared_prefix > 0)
+    backend = CudaB200AttnBackend(runner, cascade=cascade)
     fb = synth.make_decode_batch(runner, seq_lens, gen, mode=args.index_mode, shared_prefix=shared,
                                  idx_dtype=torch.int64, backend=backend)
     lay = [synth.make_layer(runner, i) for i in range(layers)]
@@ -497,7 +501,8 @@ def main():
 
     launches = {"n": 0}
     # the cascade leg is launched (and exits at once when nothing is shared) wherever it is supported
-    cascade_launched = bool(backend.cascade) and d == 128 and B * (hq // hkv) >= 64
+    cascade_launched = (bool(backend.cascade) and (d == 128 or (d == 64 and w.kv_dtype == torch.bfloat16))
+                        and B * (hq // hkv) >= 64 and B <= 1024 and 256 % (hq // hkv) == 0)
     KERNELS_PER_LAYER_CALL = 3 + int(cascade_launched)  # kv_store, [extend_tc<shared>], decode_mma, merge
     KERNELS_PER_PLAN = 1 + 2 * int(cascade_launched)    # [group_kernel, lcp_kernel], plan_kernel
 

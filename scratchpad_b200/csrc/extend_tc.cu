@@ -75,7 +75,7 @@ constexpr int kRegsSoftmax = 192, kRegsOther = 64;  // 256*192 + 256*64 = 64 Ki 
 constexpr int kSmemQ = 0;
 constexpr int kSmemRing = 2 * kTileBytes;
 constexpr int kSmemBar = kSmemRing + kSlots * kTileBytes;  // 229376
-constexpr int kNumBars = 2 * kSlots + 1 + 2 + 4 + 2;
+constexpr int kNumBars = 2 * kSlots + 1 + 2 + 4 + 2 + 1;
 constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
 constexpr int kSmemBytes = kSmemTmemPtr + 16 + 1024;       // + alignment slack
 
@@ -312,52 +312,6 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
   pdl_wait();
   pdl_launch_dependents();
 
-  // extend: grid (query block, kv head, request); shared-prefix decode: grid (kv head, KV split, row tile) -- the row
-  // tile is the slowest index so that the tiles the plan actually produced are dispatched first and the unused
-  // tail of the fixed-size grid (it exits at once) drains through whatever SMs are free
-  const int kvh = MODE == kModeExtend ? blockIdx.y : blockIdx.x;
-  const int G = a.g, bm_t = a.bm_t;
-  // extend: token range [t0, t_end) of request b; shared: request range [t0, t_end) of the batch
-  int pre, start, t0, t_end, kv_len, nt, cas_split = 0;
-  const int32_t* row;
-  if constexpr (MODE == kModeExtend) {
-    const int b = blockIdx.z;
-    const int ext = __ldg(a.ext_lens + b);
-    const int nqb = (ext + bm_t - 1) / bm_t;
-    const int qb = nqb - 1 - static_cast<int>(blockIdx.x);  // heavy (late) blocks first
-    if (qb < 0) return;
-    const int seq = static_cast<int>(load_idx(a.seq_lens, a.idx64, b));
-    pre = seq - ext;
-    start = __ldg(a.ext_start + b);
-    row = a.r2t + load_idx(a.req_idx, a.idx64, b) * a.r2t_stride;
-    t0 = qb * bm_t;
-    t_end = min(ext, t0 + bm_t);
-    kv_len = pre + t_end;
-    nt = (kv_len + kBN - 1) / kBN;
-  } else {
-    // one row tile of one prefix group: requests perm[t0 .. t_end) share `shared` leading slots (a multiple of kBN)
-    const int tile = blockIdx.z;
-    if (tile >= __ldg(a.cas.hdr + kHdrCasTiles)) return;
-    const int shared = __ldg(a.cas.ct_shared + tile);
-    t0 = __ldg(a.cas.ct_first + tile);
-    t_end = t0 + __ldg(a.cas.ct_cnt + tile);
-    cas_split = blockIdx.y;
-    const int ntot = shared / kBN, ns = gridDim.y;
-    const int j0 = static_cast<int>(static_cast<int64_t>(cas_split) * ntot / ns);
-    nt = static_cast<int>(static_cast<int64_t>(cas_split + 1) * ntot / ns) - j0;
-    const int leader = __ldg(a.cas.ct_leader + tile);
-    row = a.r2t + static_cast<int64_t>(__ldg(a.cas.req32 + leader)) * a.r2t_stride + j0 * kBN;
-    start = 0;
-    pre = kv_len = nt * kBN;
-    if (nt <= 0) {  // more splits than tiles (the plan never produces this): an empty partial
-      const int R = tid;
-      if (R < (t_end - t0) * G)
-        a.cas_lse[(static_cast<int64_t>(cas_split) * a.bs + __ldg(a.cas.perm + t0 + R / G)) * a.hq + kvh * G + R % G] = -INFINITY;
-      return;
-    }
-  }
-  const int live_rows = (t_end - t0) * G;
-
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-byte alignment
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t bar0 = sbase + kSmemBar;
@@ -367,35 +321,92 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
   auto bar_s = [&](int i) { return bar0 + 8u * (2 * kSlots + 1 + i); };
   auto bar_p = [&](int i, int half) { return bar0 + 8u * (2 * kSlots + 3 + 2 * i + half); };  // P_i keys [64 half, +64) written
   auto bar_pv = [&](int i) { return bar0 + 8u * (2 * kSlots + 7 + i); };
+  const uint32_t bar_fin = bar0 + 8u * (2 * kSlots + 9);  // every MMA and every commit of the tile has landed
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sgen + kSmemTmemPtr);
 
-  if (warp == kMmaWarp) {
-    if (lane == 0) {
-      for (int s = 0; s < kSlots; ++s) {
-        mbar_init(bar_full(s), kProdThreads);
-        mbar_init(bar_empty(s), 1);
+  // extend: grid (query block, kv head, request), one tile per CTA.  Shared-prefix decode: grid (kv head, KV split,
+  // row-tile lane): the grid has ceil(bs / requests-per-tile) lanes -- exactly the tiles of one group that covers the
+  // batch -- and a CTA loops `tile += gridDim.z` over whatever further tiles the plan produced for more groups.
+  // Every role runs the same tile loop inside its own branch (so that ptxas sees one register budget per role):
+  //   get_tile -> [MMA warp: barrier init, TMEM alloc] -> tile_begin (CTA barrier) -> role body -> tile_end (CTA barrier)
+  const int kvh = MODE == kModeExtend ? blockIdx.y : blockIdx.x;
+  const int G = a.g, bm_t = a.bm_t;
+  struct Tile {
+    int pre, start, t0, t_end, kv_len, nt, cas_split, live_rows;
+    const int32_t* row;
+  };
+  // 0: no more tiles for this CTA, 1: run the tile, 2: nothing to compute (skip)
+  auto get_tile = [&](int it, Tile& t) -> int {
+    t.cas_split = 0;
+    if constexpr (MODE == kModeExtend) {
+      if (it > 0) return 0;
+      const int b = blockIdx.z;
+      const int ext = __ldg(a.ext_lens + b);
+      const int nqb = (ext + bm_t - 1) / bm_t;
+      const int qb = nqb - 1 - static_cast<int>(blockIdx.x);  // heavy (late) blocks first
+      if (qb < 0) return 0;
+      const int seq = static_cast<int>(load_idx(a.seq_lens, a.idx64, b));
+      t.pre = seq - ext;
+      t.start = __ldg(a.ext_start + b);
+      t.row = a.r2t + load_idx(a.req_idx, a.idx64, b) * a.r2t_stride;
+      t.t0 = qb * bm_t;
+      t.t_end = min(ext, t.t0 + bm_t);
+      t.kv_len = t.pre + t.t_end;
+      t.nt = (t.kv_len + kBN - 1) / kBN;
+    } else {
+      // one row tile of one prefix group: requests perm[t0 .. t_end) share `shared` leading slots (a multiple of kBN)
+      const int tile = blockIdx.z + it * gridDim.z;
+      if (tile >= __ldg(a.cas.hdr + kHdrCasTiles)) return 0;
+      const int shared = __ldg(a.cas.ct_shared + tile);
+      t.t0 = __ldg(a.cas.ct_first + tile);
+      t.t_end = t.t0 + __ldg(a.cas.ct_cnt + tile);
+      t.cas_split = blockIdx.y;
+      const int ntot = shared / kBN, ns = gridDim.y;
+      const int j0 = static_cast<int>(static_cast<int64_t>(t.cas_split) * ntot / ns);
+      t.nt = static_cast<int>(static_cast<int64_t>(t.cas_split + 1) * ntot / ns) - j0;
+      const int leader = __ldg(a.cas.ct_leader + tile);
+      t.row = a.r2t + static_cast<int64_t>(__ldg(a.cas.req32 + leader)) * a.r2t_stride + j0 * kBN;
+      t.start = 0;
+      t.pre = t.kv_len = t.nt * kBN;
+      if (t.nt <= 0) {  // more splits than tiles (the plan never produces this): an empty partial
+        const int R = tid;
+        if (R < (t.t_end - t.t0) * G)
+          a.cas_lse[(static_cast<int64_t>(t.cas_split) * a.bs + __ldg(a.cas.perm + t.t0 + R / G)) * a.hq + kvh * G + R % G] = -INFINITY;
+        return 2;
       }
-      mbar_init(bar_q, kSoftmaxWarps * 32);
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(bar_s(i), 1);
-        mbar_init(bar_p(i, 0), 128);
-        mbar_init(bar_p(i, 1), 128);
-        mbar_init(bar_pv(i), 1);
-      }
-      fence_barrier_init();
     }
-    __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmemTmemPtr), "r"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    t.live_rows = (t.t_end - t.t0) * G;
+    return 1;
+  };
+  auto tile_begin = [&]() -> uint32_t {  // barriers initialised, TMEM allocated: visible to the whole CTA
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return *tmem_ptr;
+  };
+  auto tile_end = [&]() {  // every role is done with shared memory, TMEM and the barriers of this tile
+    tc_fence_before();
+    __syncthreads();
+  };
+#define TC_TILE_LOOP_BEGIN                                                                                   \
+  for (int it = 0;; ++it) {                                                                                  \
+    Tile tl;                                                                                                 \
+    const int tile_state = get_tile(it, tl);                                                                 \
+    if (tile_state == 0) break;                                                                              \
+    if (tile_state == 2) continue;                                                                           \
+    const int pre = tl.pre, start = tl.start, t0 = tl.t0, t_end = tl.t_end, kv_len = tl.kv_len, nt = tl.nt,   \
+              cas_split = tl.cas_split, live_rows = tl.live_rows;                                            \
+    const int32_t* row = tl.row;                                                                             \
+    (void)pre; (void)start; (void)t0; (void)t_end; (void)kv_len; (void)nt; (void)cas_split; (void)live_rows; (void)row;
+#define TC_TILE_LOOP_END \
+    tile_end();          \
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
 
   if (warp >= kProdWarp0) {
     // =========================== producers ===========================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
+    TC_TILE_LOOP_BEGIN
+    tile_begin();
     if constexpr (F16) {
       // fp8-e4m3 pool.  A 128-key tile is 16 KiB of e4m3 and 32 KiB of f16:
       //  phase A  the raw pool rows are gathered with LDGSTS into the UPPER half of the tile's ring slot (row r
@@ -539,9 +550,35 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     fence_proxy_async();
     for (int n = max(total - kLag, 0); n < total; ++n) mbar_arrive(bar_full(n % kSlots));
     }  // !F16
+    TC_TILE_LOOP_END
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ============================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
+    bool have_tmem = false;
+    uint32_t tmem = 0;
+    TC_TILE_LOOP_BEGIN
+    if (lane == 0) {  // (re-)initialise: every barrier starts each tile at phase 0
+      for (int s = 0; s < kSlots; ++s) {
+        mbar_init(bar_full(s), kProdThreads);
+        mbar_init(bar_empty(s), 1);
+      }
+      mbar_init(bar_q, kSoftmaxWarps * 32);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_s(i), 1);
+        mbar_init(bar_p(i, 0), 128);
+        mbar_init(bar_p(i, 1), 128);
+        mbar_init(bar_pv(i), 1);
+      }
+      mbar_init(bar_fin, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    if (!have_tmem) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmemTmemPtr), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+      have_tmem = true;
+    }
+    tmem = tile_begin();
     // The whole warp runs this loop so that every address / descriptor is warp-uniform (uniform registers,
     // no R2UR in front of each UTCHMMA); only the tcgen05.mma / tcgen05.commit themselves are issued by lane 0.
     const bool leader = lane == 0;
@@ -615,13 +652,28 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
           if (leader) tc_commit(bar_empty(slot_of(nk)));
         }
       }
+      // all asynchronous arrivals of this tile (the commits above) are in before the barriers are re-initialised
+      if (leader) tc_commit(bar_fin);
+      mbar_wait(bar_fin, 0);
+      tc_fence_after();
     }
     __syncwarp();
+    TC_TILE_LOOP_END
+    if (have_tmem) {
+      tc_fence_after();
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    }
   } else if (warp > kMmaWarp) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));  // idle padding warps of warpgroup 2
+    // idle padding warps of warpgroup 2: they only take part in the CTA barriers
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
+    TC_TILE_LOOP_BEGIN
+    tile_begin();
+    TC_TILE_LOOP_END
   } else {
     // =========================== softmax warpgroups =======================================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
+    TC_TILE_LOOP_BEGIN
+    const uint32_t tmem = tile_begin();
     // Q tiles first (the 256 softmax threads are idle until the first S lands):
     // row R = i*128 + r -> (token t0 + R/G, head kvh*G + R%G)
     for (int idx = tid; idx < kRows * (D / 8); idx += kSoftmaxWarps * 32) {
@@ -841,15 +893,11 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
         }
       }
     }
+    TC_TILE_LOOP_END
   }
 
-  // ---- teardown ------------------------------------------------------------------------------------------
-  tc_fence_before();
-  __syncthreads();
-  if (warp == kMmaWarp) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
-  }
+#undef TC_TILE_LOOP_BEGIN
+#undef TC_TILE_LOOP_END
 }
 
 }  // namespace tc
@@ -943,7 +991,7 @@ int launch_shared_prefix_tc(const b200_decode_params* p, const CasTables& t, flo
   a.k_scale = p->k_scale;
   a.v_scale = p->v_scale;
   a.bs = p->bs;
-  const dim3 grid(p->hkv, nsplit, t.max_tiles);  // row tiles beyond hdr[kHdrCasTiles] exit at once
+  const dim3 grid(p->hkv, nsplit, (p->bs + a.bm_t - 1) / a.bm_t);  // z = row-tile lanes; CTAs loop over further tiles
   if (p->d == 64) return launch_tc<tc::kModeShared, false, 64>(a, grid, st);
   return fp8 ? launch_tc<tc::kModeShared, true, 128>(a, grid, st) : launch_tc<tc::kModeShared, false, 128>(a, grid, st);
 }

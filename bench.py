@@ -499,6 +499,12 @@ def main():
 
     from scratchpad_b200 import ForwardMode
 
+    # The batch metadata the forward pass reads (seq_lens, req_pool_indices, out_cache_loc) lives in ONE device buffer
+    # (three views), like the static buffers of a graph runner: the e2e leg then uploads it with one copy, not three.
+    meta_dev = torch.stack([fb.seq_lens.to(torch.int64), fb.req_pool_indices.to(torch.int64),
+                            fb.out_cache_loc.to(torch.int64)]).contiguous()
+    fb.seq_lens, fb.req_pool_indices, fb.out_cache_loc = meta_dev[0], meta_dev[1], meta_dev[2]
+
     launches = {"n": 0}
     # the cascade leg is launched (and exits at once when nothing is shared) wherever it is supported
     cascade_launched = (bool(backend.cascade) and (d == 128 or (d == 64 and w.kv_dtype == torch.bfloat16))
@@ -599,13 +605,11 @@ def main():
     e2e = None
     if not args.no_e2e:
         h_qkv = qkv.cpu().pin_memory()
-        h_sl = fb.seq_lens.cpu().pin_memory()
-        h_rpi = fb.req_pool_indices.cpu().pin_memory()
-        h_loc = fb.out_cache_loc.cpu().pin_memory()
+        h_meta = meta_dev.cpu().pin_memory()
         h_o = torch.empty((B, hq * d), dtype=torch.bfloat16).pin_memory()
         d_qkv = torch.empty_like(qkv)
         dq, dk, dv_ = d_qkv[:, : hq * d], d_qkv[:, hq * d: (hq + hkv) * d], d_qkv[:, (hq + hkv) * d:]
-        h2d = h_qkv.numel() * 2 + h_sl.numel() * 8 + h_rpi.numel() * 8 + h_loc.numel() * 8
+        h2d = h_qkv.numel() * 2 + h_meta.numel() * 8
         d2h = h_o.numel() * 2
 
         if graphs is not None:
@@ -613,9 +617,7 @@ def main():
             # into the static buffers the graph was captured on, refresh the metadata in place, replay, read o back
             def e2e_step(i):
                 qkv.copy_(h_qkv, non_blocking=True)
-                fb.seq_lens.copy_(h_sl, non_blocking=True)
-                fb.req_pool_indices.copy_(h_rpi, non_blocking=True)
-                fb.out_cache_loc.copy_(h_loc, non_blocking=True)
+                meta_dev.copy_(h_meta, non_blocking=True)
                 backend.init_forward_metadata_replay_cuda_graph(B, fb.req_pool_indices, fb.seq_lens, fb.seq_lens_sum,
                                                                 None, ForwardMode.DECODE, None, seq_lens_cpu=None)
                 graphs[i % L].replay()
@@ -624,9 +626,7 @@ def main():
         else:
             def e2e_step(i):
                 d_qkv.copy_(h_qkv, non_blocking=True)
-                fb.seq_lens.copy_(h_sl, non_blocking=True)
-                fb.req_pool_indices.copy_(h_rpi, non_blocking=True)
-                fb.out_cache_loc.copy_(h_loc, non_blocking=True)
+                meta_dev.copy_(h_meta, non_blocking=True)
                 backend.init_forward_metadata(fb)  # metadata depends on the step's seq_lens: once per call here
                 o = layers[i % L](dq, dk, dv_, fb, save_kv_cache=True)
                 h_o.copy_(o, non_blocking=True)

@@ -5,7 +5,7 @@
 tag="${1:-dev}"
 out=gpurun_out
 mkdir -p $out
-K='lcp_kernel|plan_kernel|decode_mma|merge_kernel|kv_store|extend_tc|extend_mma'
+K='group_kernel|lcp_kernel|plan_kernel|decode_mma|merge_kernel|kv_store|extend_tc|extend_mma'
 CMD="python bench.py --steps 32 --warmup 8 --no-e2e --no-cpu-baseline --mode eager --layers 4"
 timeout -s KILL 120 $CMD > $out/${tag}_plain.log 2>&1 && timeout -s KILL 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$K" -c 400 --csv --log-file $out/${tag}_launches_c2.csv $CMD > $out/${tag}_ncu_launches.log 2>&1
 timeout -s KILL 200 ncu --set full --clock-control none --import-source on -k regex:decode_mma -s 12 -c 2 -o $out/${tag}_prof_c2 $CMD > $out/${tag}_ncu_c2.log 2>&1

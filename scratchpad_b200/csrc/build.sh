@@ -7,7 +7,7 @@ out="$here/libb200attn.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a
        -Xcompiler -fPIC --expt-relaxed-constexpr
-       -I"$root/include" -I"$here" ${B200_PTXAS_V:+-Xptxas -v} ${B200_TC_TRACE:+-DB200_TC_TRACE} ${B200_TC_POLY:+-DB200_TC_POLY=$B200_TC_POLY} ${B200_TC_POLY1:+-DB200_TC_POLY1=$B200_TC_POLY1})
+       -I"$root/include" -I"$here" ${B200_PTXAS_V:+-Xptxas -v} ${B200_TC_TRACE:+-DB200_TC_TRACE} ${B200_DEC_TRACE:+-DB200_DEC_TRACE} ${B200_TC_POLY:+-DB200_TC_POLY=$B200_TC_POLY} ${B200_TC_POLY1:+-DB200_TC_POLY1=$B200_TC_POLY1})
 objs=()
 pids=()
 for f in decode store extend extend_tc; do

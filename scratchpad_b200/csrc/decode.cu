@@ -339,6 +339,23 @@ struct DecodeArgs {
   const float* v_scale;
 };
 
+// ---- optional per-CTA timeline (build with -DB200_DEC_TRACE; tools/dec_trace.py): %globaltimer at six points
+#ifdef B200_DEC_TRACE
+__device__ unsigned long long g_dec_trace[1024][6];
+#define DEC_TRACE(i)                                                                                   \
+  do {                                                                                                 \
+    if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 1024) {                                    \
+      unsigned long long t_;                                                                           \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                           \
+      g_dec_trace[blockIdx.x][i] = t_;                                                                 \
+    }                                                                                                  \
+  } while (0)
+#else
+#define DEC_TRACE(i) \
+  do {               \
+  } while (0)
+#endif
+
 struct Cursor {
   int gt, gt_end;  // global tile index / end of this CTA's range
   int b;           // request (batch row) the tile belongs to
@@ -401,8 +418,10 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x;
   const int h0 = blockIdx.y * HPC;  // first kv head of this CTA
+  DEC_TRACE(0);
   pdl_wait();               // everything below reads what earlier launches (plan, kv store, qkv GEMM) wrote
   pdl_launch_dependents();  // let the merge grid get scheduled behind us; it waits for our completion
+  DEC_TRACE(1);
 
   const int total = __ldg(a.hdr + 0), tpc = __ldg(a.hdr + 1), bs = __ldg(a.hdr + 3);
   const int gt_begin = cta * tpc;
@@ -646,11 +665,21 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
   }
   reset_state();
   load_q(cc.b);
+  DEC_TRACE(2);
 
   int stage = 0;
+#ifdef B200_DEC_TRACE
+  bool first_tile = true;
+#endif
   while (cursor_valid(cc)) {
     cp_async_wait<kStages - 2>();
     __syncthreads();
+#ifdef B200_DEC_TRACE
+    if (first_tile) {
+      DEC_TRACE(3);
+      first_tile = false;
+    }
+#endif
     {
       int pstage = stage + kStages - 1;
       if (pstage >= kStages) pstage -= kStages;
@@ -677,7 +706,9 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
     }
     stage = stage + 1 == kStages ? 0 : stage + 1;
   }
+  DEC_TRACE(4);
   cp_async_wait<0>();
+  DEC_TRACE(5);
 }
 
 // ---------------------------------------------------------------------------
@@ -1127,6 +1158,12 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
                     static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
                     static_cast<int>(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
 }
+
+#ifdef B200_DEC_TRACE
+int b200_debug_dec_trace_read(unsigned long long* host_dst) {
+  return cudaMemcpyFromSymbol(host_dst, g_dec_trace, sizeof(g_dec_trace)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 int b200_debug_gather(const void* buf, int64_t stride_t_bytes, int32_t row_bytes, const int32_t* req_to_token,
                       int64_t req_to_token_stride, const void* req_pool_indices, const void* seq_lens,

@@ -251,7 +251,7 @@ __host__ __device__ constexpr uint32_t instr_desc(int m, int n, bool b_mn_major,
 
 // ---- optional timeline trace of CTA (0,0,0) (build with -DB200_TC_TRACE; tools/tc_trace.py) ----------------
 #ifdef B200_TC_TRACE
-constexpr int kTraceEvents = 16, kTraceLen = 128;
+constexpr int kTraceEvents = 20, kTraceLen = 128;
 __device__ long long g_trace[kTraceEvents][kTraceLen];
 #define TC_TRACE(ev, idx)                                                                                  \
   do {                                                                                                     \
@@ -309,8 +309,10 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
   static_assert(D == 128 || (D == 64 && !F16), "head_dim 64 over an fp8 pool stays on the mma.sync kernels");
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) TC_TRACE(16, 0);
   pdl_wait();
   pdl_launch_dependents();
+  if (tid == 0) TC_TRACE(16, 1);
 
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-byte alignment
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -674,24 +676,47 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
     TC_TILE_LOOP_BEGIN
     const uint32_t tmem = tile_begin();
+    if (tid == 0) TC_TRACE(17, it);
     // Q tiles first (the 256 softmax threads are idle until the first S lands):
     // row R = i*128 + r -> (token t0 + R/G, head kvh*G + R%G)
-    for (int idx = tid; idx < kRows * (D / 8); idx += kSoftmaxWarps * 32) {
+    constexpr int kQIters = kRows * (D / 8) / (kSoftmaxWarps * 32);  // 16-byte chunks per thread
+    auto q_chunk = [&](int it_q, const __nv_bfloat16*& src, uint32_t& dst, bool& live) {
+      const int idx = tid + it_q * (kSoftmaxWarps * 32);
       const int R = idx / (D / 8), ch = idx % (D / 8);
-      const bool live = R < live_rows;
+      live = R < live_rows;
       const int t = t0 + (live ? R / G : 0), h = kvh * G + (live ? R % G : 0);
       // extend: token start + t of the flattened batch; shared-prefix decode: request perm[t]
       const int qrow = MODE == kModeExtend ? start + t : __ldg(a.cas.perm + t);
-      const __nv_bfloat16* src = a.q + static_cast<int64_t>(qrow) * a.q_st + static_cast<int64_t>(h) * a.q_sh + ch * 8;
-      const uint32_t dst = sbase + kSmemQ + (R >> 7) * kTileBytes + tile_off(R & 127, ch >> 3, ch & 7);
-      if constexpr (F16) {
-        uint4 x = live ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0u, 0u, 0u, 0u);
-        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+      src = a.q + static_cast<int64_t>(qrow) * a.q_st + static_cast<int64_t>(h) * a.q_sh + ch * 8;
+      dst = sbase + kSmemQ + (R >> 7) * kTileBytes + tile_off(R & 127, ch >> 3, ch & 7);
+    };
+    if constexpr (F16) {
+      // bf16 -> f16 on the way in: all of the thread's loads are issued before the first one is converted
+      // (one memory round trip; one load per iteration was 10 us of the shared-prefix leg's 40)
+      uint4 x[kQIters];
+      uint32_t dsts[kQIters];
+#pragma unroll
+      for (int it_q = 0; it_q < kQIters; ++it_q) {
+        const __nv_bfloat16* src;
+        bool live;
+        q_chunk(it_q, src, dsts[it_q], live);
+        x[it_q] = live ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int it_q = 0; it_q < kQIters; ++it_q) {
+        const uint32_t w[4] = {x[it_q].x, x[it_q].y, x[it_q].z, x[it_q].w};
         uint32_t h2[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) h2[e] = pack_f16x2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
-        st_shared_v4(dst, h2[0], h2[1], h2[2], h2[3]);
-      } else {
+        st_shared_v4(dsts[it_q], h2[0], h2[1], h2[2], h2[3]);
+      }
+    } else {
+#pragma unroll 4
+      for (int it_q = 0; it_q < kQIters; ++it_q) {
+        const __nv_bfloat16* src;
+        uint32_t dst;
+        bool live;
+        q_chunk(it_q, src, dst, live);
         cp_async16(dst, src, live ? 16 : 0);
       }
     }
@@ -699,6 +724,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     cp_async_wait<0>();
     fence_proxy_async();
     mbar_arrive(bar_q);
+    if (tid == 0) TC_TRACE(18, it);
 
     const int i = warp >> 2;                       // Q tile
     const int r = (warp & 3) * 32 + lane;          // row inside the tile == TMEM lane
@@ -893,6 +919,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
         }
       }
     }
+    if (tid == 0) TC_TRACE(19, it);
     TC_TILE_LOOP_END
   }
 

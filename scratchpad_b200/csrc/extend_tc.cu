@@ -680,14 +680,20 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     // Q tiles first (the 256 softmax threads are idle until the first S lands):
     // row R = i*128 + r -> (token t0 + R/G, head kvh*G + R%G)
     constexpr int kQIters = kRows * (D / 8) / (kSoftmaxWarps * 32);  // 16-byte chunks per thread
+    // chunk it_q of this thread: row R of the CTA tile, 16-byte chunk ch of its head row
+    int q_rowidx[kQIters];  // extend: token start + t of the flattened batch; shared-prefix decode: request perm[t]
+#pragma unroll
+    for (int it_q = 0; it_q < kQIters; ++it_q) {  // (all perm loads first: they are a dependent hop of their own)
+      const int R = (tid + it_q * (kSoftmaxWarps * 32)) / (D / 8);
+      const int t = t0 + (R < live_rows ? R / G : 0);
+      q_rowidx[it_q] = MODE == kModeExtend ? start + t : __ldg(a.cas.perm + t);
+    }
     auto q_chunk = [&](int it_q, const __nv_bfloat16*& src, uint32_t& dst, bool& live) {
       const int idx = tid + it_q * (kSoftmaxWarps * 32);
       const int R = idx / (D / 8), ch = idx % (D / 8);
       live = R < live_rows;
-      const int t = t0 + (live ? R / G : 0), h = kvh * G + (live ? R % G : 0);
-      // extend: token start + t of the flattened batch; shared-prefix decode: request perm[t]
-      const int qrow = MODE == kModeExtend ? start + t : __ldg(a.cas.perm + t);
-      src = a.q + static_cast<int64_t>(qrow) * a.q_st + static_cast<int64_t>(h) * a.q_sh + ch * 8;
+      const int h = kvh * G + (live ? R % G : 0);
+      src = a.q + static_cast<int64_t>(q_rowidx[it_q]) * a.q_st + static_cast<int64_t>(h) * a.q_sh + ch * 8;
       dst = sbase + kSmemQ + (R >> 7) * kTileBytes + tile_off(R & 127, ch >> 3, ch & 7);
     };
     if constexpr (F16) {
@@ -702,8 +708,10 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
         q_chunk(it_q, src, dsts[it_q], live);
         x[it_q] = live ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0u, 0u, 0u, 0u);
       }
+      if (tid == 0) TC_TRACE(17, 1);
 #pragma unroll
       for (int it_q = 0; it_q < kQIters; ++it_q) {
+        if (tid == 0 && it_q == 1) TC_TRACE(17, 2);
         const uint32_t w[4] = {x[it_q].x, x[it_q].y, x[it_q].z, x[it_q].w};
         uint32_t h2[4];
 #pragma unroll
@@ -711,7 +719,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
         st_shared_v4(dsts[it_q], h2[0], h2[1], h2[2], h2[3]);
       }
     } else {
-#pragma unroll 4
+#pragma unroll
       for (int it_q = 0; it_q < kQIters; ++it_q) {
         const __nv_bfloat16* src;
         uint32_t dst;
@@ -720,6 +728,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
         cp_async16(dst, src, live ? 16 : 0);
       }
     }
+    if (tid == 0) TC_TRACE(17, 3);
     cp_async_commit();
     cp_async_wait<0>();
     fence_proxy_async();

@@ -27,6 +27,7 @@ names = ["prod:empty", "prod:issued", "mma:fullV", "mma:P0", "mma:fullK", "mma:P
 t0 = buf[buf > 0].min()
 np.set_printoptions(linewidth=250)
 print("kernel entry", buf[16, 0] - t0, "after griddepcontrol.wait", buf[16, 1] - t0, "tile begin (TMEM/barriers ready)", buf[17, 0] - t0,
+      "Q loads issued", buf[17, 1] - t0, "first Q chunk converted", buf[17, 2] - t0, "Q stored", buf[17, 3] - t0,
       "Q loaded", buf[18, 0] - t0, "epilogue done", buf[19, 0] - t0)
 print("clock offsets from the first event; rows = KV tile j (producer rows: n = 2j / 2j+1 shown as K,V)")
 print("j   " + " ".join(f"{n:>11s}" for n in ["prodK:empty", "prodK:iss", "prodV:empty", "prodV:iss"] + names[2:]))

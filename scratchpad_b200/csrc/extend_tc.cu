@@ -679,22 +679,39 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     if (tid == 0) TC_TRACE(17, it);
     // Q tiles first (the 256 softmax threads are idle until the first S lands):
     // row R = i*128 + r -> (token t0 + R/G, head kvh*G + R%G)
-    constexpr int kQIters = kRows * (D / 8) / (kSoftmaxWarps * 32);  // 16-byte chunks per thread
-    // chunk it_q of this thread: row R of the CTA tile, 16-byte chunk ch of its head row
+    // Q tiles: chunk `ch` (constant per thread) of rows R = r_base + RSTEP * it_q.  (token, head) of a row advance
+    // incrementally -- one division per thread instead of two per chunk: with 1300 dependent integer instructions
+    // in front of the first MMA this loop was 10 K clocks of every CTA's prologue.
+    constexpr int CPRQ = D / 8;                                  // 16-byte chunks per Q row
+    constexpr int RSTEP = kSoftmaxWarps * 32 / CPRQ;              // rows between two chunks of a thread
+    constexpr int kQIters = kRows / RSTEP;
+    const int ch = tid % CPRQ, r_base = tid / CPRQ;
+    const uint32_t q_dst0 = sbase + kSmemQ + (ch >> 3) * kColBlockBytes + (((ch & 7) ^ (r_base & 7)) << 4);
+    static_assert(RSTEP % 8 == 0, "row & 7 must be a per-thread constant");
     int q_rowidx[kQIters];  // extend: token start + t of the flattened batch; shared-prefix decode: request perm[t]
+    int q_head[kQIters];
+    {
+      int t = r_base / G, h = r_base % G;
+      const int dt = RSTEP / G, dh = RSTEP % G;
 #pragma unroll
-    for (int it_q = 0; it_q < kQIters; ++it_q) {  // (all perm loads first: they are a dependent hop of their own)
-      const int R = (tid + it_q * (kSoftmaxWarps * 32)) / (D / 8);
-      const int t = t0 + (R < live_rows ? R / G : 0);
-      q_rowidx[it_q] = MODE == kModeExtend ? start + t : __ldg(a.cas.perm + t);
+      for (int it_q = 0; it_q < kQIters; ++it_q) {  // (all perm loads first: they are a dependent hop of their own)
+        const bool live = r_base + RSTEP * it_q < live_rows;
+        q_head[it_q] = live ? h : 0;
+        const int tt = t0 + (live ? t : 0);
+        q_rowidx[it_q] = MODE == kModeExtend ? start + tt : __ldg(a.cas.perm + tt);
+        t += dt;
+        h += dh;
+        if (h >= G) {
+          h -= G;
+          ++t;
+        }
+      }
     }
     auto q_chunk = [&](int it_q, const __nv_bfloat16*& src, uint32_t& dst, bool& live) {
-      const int idx = tid + it_q * (kSoftmaxWarps * 32);
-      const int R = idx / (D / 8), ch = idx % (D / 8);
+      const int R = r_base + RSTEP * it_q;
       live = R < live_rows;
-      const int h = kvh * G + (live ? R % G : 0);
-      src = a.q + static_cast<int64_t>(q_rowidx[it_q]) * a.q_st + static_cast<int64_t>(h) * a.q_sh + ch * 8;
-      dst = sbase + kSmemQ + (R >> 7) * kTileBytes + tile_off(R & 127, ch >> 3, ch & 7);
+      src = a.q + static_cast<int64_t>(q_rowidx[it_q]) * a.q_st + static_cast<int64_t>(kvh * G + q_head[it_q]) * a.q_sh + ch * 8;
+      dst = q_dst0 + ((RSTEP * it_q) >> 7) * kTileBytes + (r_base + ((RSTEP * it_q) & 127)) * 128;
     };
     if constexpr (F16) {
       // bf16 -> f16 on the way in: all of the thread's loads are issued before the first one is converted

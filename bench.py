@@ -422,7 +422,10 @@ def run_extend_bench(args, rank, world, local_rank, dist):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak = float(peaks.get("bf16_tflops", 1590.0))
+        # K back-to-back launches of a multi-millisecond tensor kernel are the sustained regime of MEASURED_PEAKS.json
+        # (cuBLAS bf16 back to back for 4 s); the burst figure (best single GEMM) is reported beside it
+        burst = float(peaks.get("bf16_tflops", 1590.0))
+        peak = float(peaks.get("bf16_tflops_sustained", burst))
         ach = flops / (t_max / K) / 1e12
         traffic = None
         try:
@@ -444,7 +447,9 @@ def run_extend_bench(args, rank, world, local_rank, dist):
             "roofline": {"bound": "tensor", "kernel": "extend_tc_kernel", "achieved": ach, "peak": peak,
                          "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                          "algorithmic_flops_per_launch": flops,
-                         "peak_kind": "measured burst (MEASURED_PEAKS.json bf16_tflops)",
+                         "peak_kind": "measured sustained cuBLAS bf16 (MEASURED_PEAKS.json bf16_tflops_sustained): the timed "
+                                      "region is K back-to-back launches of this kernel",
+                         "peak_burst": burst, "frac_of_burst": ach / burst, "frac_of_nominal_2250": ach / 2250.0,
                          "note": "step time used (KV store + extend kernel); the store is <1% of the step"},
             "cpu_baseline": None,
             "e2e": {"value": flops * ke / float(te.item()) / 1e12 * world, "unit": "TFLOP/s",

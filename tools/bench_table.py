@@ -11,7 +11,8 @@ for f in sys.argv[1:]:
         continue
     r = j["roofline"]
     if r["bound"] != "hbm":
-        print(f"{f.split('/')[-1]:30s} step {j['ms_per_step'] * 1e3:9.1f}us  {r['achieved']:7.1f} TFLOP/s ({r['frac'] * 100:5.1f}% of measured)")
+        print(f"{f.split('/')[-1]:30s} step {j['ms_per_step'] * 1e3:9.1f}us  {r['achieved']:7.1f} TFLOP/s ({r['frac'] * 100:5.1f}% of measured "
+              f"sustained, {r.get('frac_of_burst', r['frac']) * 100:5.1f}% of burst)")
         continue
     e2e = j["e2e"]["value"] / 1e6 if j.get("e2e") else 0
     print(f"{f.split('/')[-1]:30s} step {j['ms_per_step'] * 1e3:8.1f}us {j['value'] / 1e6:7.3f} Mtok/s step-GB/s {j['hbm_gbs_step']:6.0f} | "

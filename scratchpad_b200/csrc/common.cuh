@@ -6,6 +6,7 @@
 #include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "b200_attn.h"
 
@@ -66,7 +67,8 @@ static inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  static const bool no_pdl = getenv("B200_NO_PDL") != nullptr;  // measurement switch: plain stream-ordered launches
+  cfg.numAttrs = no_pdl ? 0 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
   if (e != cudaSuccess) return 1000 + static_cast<int>(e);
   return B200_OK;

@@ -499,15 +499,20 @@ def main():
 
     gq = torch.Generator(device=dev).manual_seed(77 + rank)
     # q/k/v as column slices of the fused qkv GEMM output (llama.py:149-152)
-    qkv = torch.randn((B, (hq + 2 * hkv) * d), generator=gq, device=dev, dtype=torch.float32).to(torch.bfloat16)
-    q, k, v = qkv[:, : hq * d], qkv[:, hq * d: (hq + hkv) * d], qkv[:, (hq + hkv) * d:]
-
     from scratchpad_b200 import ForwardMode
 
-    # The batch metadata the forward pass reads (seq_lens, req_pool_indices, out_cache_loc) lives in ONE device buffer
-    # (three views), like the static buffers of a graph runner: the e2e leg then uploads it with one copy, not three.
-    meta_dev = torch.stack([fb.seq_lens.to(torch.int64), fb.req_pool_indices.to(torch.int64),
-                            fb.out_cache_loc.to(torch.int64)]).contiguous()
+    # Static step inputs, like the buffers of a graph runner: the activations (q/k/v as column slices of the fused qkv
+    # GEMM output, llama.py:149-152) and the batch metadata the forward pass reads (seq_lens, req_pool_indices,
+    # out_cache_loc) are views of ONE device buffer, so the e2e leg uploads a step's inputs with a single copy.
+    qkv_bytes = B * (hq + 2 * hkv) * d * 2
+    meta_off = (qkv_bytes + 255) // 256 * 256
+    step_in = torch.zeros(meta_off + 3 * B * 8, dtype=torch.uint8, device=dev)
+    qkv = step_in[:qkv_bytes].view(torch.bfloat16).view(B, (hq + 2 * hkv) * d)
+    qkv.copy_(torch.randn((B, (hq + 2 * hkv) * d), generator=gq, device=dev, dtype=torch.float32))
+    q, k, v = qkv[:, : hq * d], qkv[:, hq * d: (hq + hkv) * d], qkv[:, (hq + hkv) * d:]
+    meta_dev = step_in[meta_off:].view(torch.int64).view(3, B)
+    meta_dev.copy_(torch.stack([fb.seq_lens.to(torch.int64), fb.req_pool_indices.to(torch.int64),
+                                fb.out_cache_loc.to(torch.int64)]))
     fb.seq_lens, fb.req_pool_indices, fb.out_cache_loc = meta_dev[0], meta_dev[1], meta_dev[2]
 
     launches = {"n": 0}
@@ -609,20 +614,16 @@ def main():
     # --- e2e leg: host buffers, H2D + forward + D2H every step ------------------------------------
     e2e = None
     if not args.no_e2e:
-        h_qkv = qkv.cpu().pin_memory()
-        h_meta = meta_dev.cpu().pin_memory()
+        h_in = step_in.cpu().pin_memory()
         h_o = torch.empty((B, hq * d), dtype=torch.bfloat16).pin_memory()
-        d_qkv = torch.empty_like(qkv)
-        dq, dk, dv_ = d_qkv[:, : hq * d], d_qkv[:, hq * d: (hq + hkv) * d], d_qkv[:, (hq + hkv) * d:]
-        h2d = h_qkv.numel() * 2 + h_meta.numel() * 8
+        h2d = h_in.numel()
         d2h = h_o.numel() * 2
 
         if graphs is not None:
             # the engine's decode path (CudaGraphRunner.replay, cuda_graph_runner.py:443-510): copy the step's inputs
             # into the static buffers the graph was captured on, refresh the metadata in place, replay, read o back
             def e2e_step(i):
-                qkv.copy_(h_qkv, non_blocking=True)
-                meta_dev.copy_(h_meta, non_blocking=True)
+                step_in.copy_(h_in, non_blocking=True)
                 backend.init_forward_metadata_replay_cuda_graph(B, fb.req_pool_indices, fb.seq_lens, fb.seq_lens_sum,
                                                                 None, ForwardMode.DECODE, None, seq_lens_cpu=None)
                 graphs[i % L].replay()
@@ -630,10 +631,9 @@ def main():
                 torch.cuda.current_stream().synchronize()  # the caller consumes the result
         else:
             def e2e_step(i):
-                d_qkv.copy_(h_qkv, non_blocking=True)
-                meta_dev.copy_(h_meta, non_blocking=True)
+                step_in.copy_(h_in, non_blocking=True)
                 backend.init_forward_metadata(fb)  # metadata depends on the step's seq_lens: once per call here
-                o = layers[i % L](dq, dk, dv_, fb, save_kv_cache=True)
+                o = layers[i % L](q, k, v, fb, save_kv_cache=True)
                 h_o.copy_(o, non_blocking=True)
                 torch.cuda.current_stream().synchronize()  # the caller consumes the result
 

@@ -59,3 +59,31 @@ def test_fuzz_extend_both_kernel_families(seed):
     for path in ([_lib.PATH_MMA, _lib.PATH_TC] if tc_ok else [_lib.PATH_MMA]):
         got = G.run_extend_case(c, force_path=path, save_kv_cache=rng.random() < 0.5)[0]
         G.assert_close(got, want, *tol, what=f"fuzz extend seed {seed} path {path}: {hq}/{hkv}/{d} fp8={fp8} pre={pre} ext={ext}")
+
+
+@pytest.mark.parametrize("kv", ["bf16", "fp8"])
+def test_large_logits_decode_extend_cascade(kv):
+    """Scores of magnitude ~1e2 (sharp softmax, huge dynamic range): running maxima, lazy rescale, LSE merge of
+    split-KV / shared-prefix partials must stay finite and match the oracle."""
+    kv_dtype = torch.float8_e4m3fn if kv == "fp8" else torch.bfloat16
+    tol = (G.FP8_ABS, G.FP8_REL) if kv == "fp8" else (G.BF16_ABS, G.BF16_REL)
+    # decode + cascade
+    lens = [1300 + 17 * i for i in range(20)]
+    c = G.random_decode_case(32, 8, 128, lens, seed=5, kv_dtype=kv_dtype, shared_prefix=1290)
+    c["q"] = (c["q"].float() * 6.0).to(torch.bfloat16)
+    got = G.run_decode_case(c["q"], c["k_buf"], c["v_buf"], c["req_to_token"], c["req_pool_indices"], c["seq_lens"],
+                            c["sm_scale"], 0.0, kv_dtype, c.get("k_scale"), c.get("v_scale"), cascade=True)[0]
+    want = O.decode_ref(c["q"], c["k_buf"], c["v_buf"], c["req_to_token"], c["req_pool_indices"], c["seq_lens"],
+                        c["sm_scale"], 0.0, c.get("kv_dtype"), c.get("k_scale"), c.get("v_scale"))
+    G.assert_close(got, want, *tol, what=f"large logits decode {kv}")
+    # extend on both kernel families, scores growing along the sequence
+    e = G.random_extend_case(16, 4, 128, [300, 0], [200, 333], seed=6, kv_dtype=kv_dtype)
+    e["q"] = (e["q"].float() * 5.0).to(torch.bfloat16)
+    ramp = torch.linspace(0.5, 2.5, e["k_new"].shape[0]).view(-1, 1, 1)
+    e["k_new"] = (e["k_new"].float() * ramp).to(torch.bfloat16)
+    want = O.extend_ref(e["q"], e["k_new"], e["v_new"], e["k_buf"], e["v_buf"], e["req_to_token"], e["req_pool_indices"],
+                        e["seq_lens"], e["extend_seq_lens"], e["extend_start_loc"], e["sm_scale"], 0.0, e.get("kv_dtype"),
+                        e.get("k_scale"), e.get("v_scale"))
+    for path in (_lib.PATH_MMA, _lib.PATH_TC):
+        got = G.run_extend_case(e, force_path=path)[0]
+        G.assert_close(got, want, *tol, what=f"large logits extend {kv} path {path}")

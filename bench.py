@@ -52,6 +52,10 @@ def parse_args():
                          "launch (~2 us) per layer-call")
     ap.add_argument("--force-path", default="auto", choices=["auto", "mma", "tc"],
                     help="extend workloads: kernel family (mma = legacy mma.sync kernel, tc = tcgen05/TMEM kernel)")
+    ap.add_argument("--rope", default="off", choices=["off", "separate", "fused"],
+                    help="decode only: include the model's rotary embedding in the layer-call -- 'separate' = the "
+                         "reference's sequence rotary_emb(positions, q, k) then attention (llama.py:149-152), 'fused' = "
+                         "one b200_rope_kv_store launch doing the rotation and the KV write (SURVEY 8f #1)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -519,16 +523,33 @@ def main():
     # the cascade leg is launched (and exits at once when nothing is shared) wherever it is supported
     cascade_launched = (bool(backend.cascade) and (d == 128 or (d == 64 and w.kv_dtype == torch.bfloat16))
                         and B * (hq // hkv) >= 64 and B <= 1024 and 256 % (hq // hkv) == 0)
-    KERNELS_PER_LAYER_CALL = 3 + int(cascade_launched)  # kv_store, [extend_tc<shared>], decode_mma, merge
+    # kv_store (or rope_kv_store), [extend_tc<shared>], decode_mma, merge; + the separate rotary kernel
+    KERNELS_PER_LAYER_CALL = 3 + int(cascade_launched) + int(args.rope == "separate")
     KERNELS_PER_PLAN = 1 + 2 * int(cascade_launched)    # [group_kernel, lcp_kernel], plan_kernel
 
     def plan():
         backend.init_forward_metadata(fb)
         launches["n"] += KERNELS_PER_PLAN
 
+    rotary_emb = positions = None
+    if args.rope != "off":
+        from scratchpad_b200.rotary_embedding import get_rope
+        rotary_emb = get_rope(d, d, max(int(fb.seq_lens.max().item()) + 1, 8192), 500000.0, True,
+                              {"rope_type": "llama3", "factor": 32.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+                               "original_max_position_embeddings": 8192}, dtype=torch.bfloat16).to(dev)
+        positions = (fb.seq_lens - 1).clone()
+
+    def run_layer(i):
+        """One layer-call as the model's attention block issues it (llama.py:149-152)."""
+        if args.rope == "fused":
+            return layers[i](q, k, v, fb, save_kv_cache=True, rope=(rotary_emb, positions))
+        if args.rope == "separate":
+            rotary_emb(positions, q, k)
+        return layers[i](q, k, v, fb, save_kv_cache=True)
+
     def layer_call(i):
         launches["n"] += KERNELS_PER_LAYER_CALL
-        return layers[i % L](q, k, v, fb, save_kv_cache=True)
+        return run_layer(i % L)
 
     # --- device-resident leg -------------------------------------------------------------------
     graphs = None
@@ -540,13 +561,13 @@ def main():
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for i in range(min(L, 2)):
-                layers[i](q, k, v, fb, save_kv_cache=True)
+                run_layer(i)
         torch.cuda.current_stream().wait_stream(side)
         graphs, outs = [], []
         for i in range(L):  # one graph per layer-call so that any K can be timed exactly
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                outs.append(layers[i](q, k, v, fb, save_kv_cache=True))
+                outs.append(run_layer(i))
             graphs.append(g)
 
         def replan():
@@ -604,7 +625,7 @@ def main():
     torch.cuda.synchronize()
     for i, (a, b) in enumerate(evs):
         backend.profile_events = (a.cuda_event, b.cuda_event)
-        layers[i % L](q, k, v, fb, save_kv_cache=True)
+        run_layer(i % L)
     backend.profile_events = None
     torch.cuda.synchronize()
     kt = sorted(a.elapsed_time(b) * 1e-3 for a, b in evs[8:])
@@ -633,7 +654,7 @@ def main():
             def e2e_step(i):
                 step_in.copy_(h_in, non_blocking=True)
                 backend.init_forward_metadata(fb)  # metadata depends on the step's seq_lens: once per call here
-                o = layers[i % L](q, k, v, fb, save_kv_cache=True)
+                o = run_layer(i % L)
                 h_o.copy_(o, non_blocking=True)
                 torch.cuda.current_stream().synchronize()  # the caller consumes the result
 
@@ -705,6 +726,7 @@ def main():
         achieved = st["algo_bytes"] / k_avg / 1e9
         shared_len = int(backend.workspace[:64].view(torch.int32)[7].item())
         cfg_out = workload_config(w, world * args.shard, args, st)
+        cfg_out["rope"] = args.rope
         cfg_out["cascade"] = {"enabled": bool(backend.cascade), "launched": cascade_launched,
                               "shared_prefix_tokens_detected": shared_len,
                               "row_tiles": int(backend.workspace[:64].view(torch.int32)[8].item())}

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define B200_ATTN_ABI_VERSION 6
+#define B200_ATTN_ABI_VERSION 7
 
 /* kv_dtype */
 #define B200_KV_BF16 0
@@ -135,8 +135,8 @@ typedef struct b200_extend_params {
 } b200_extend_params;
 
 int b200_attn_abi_version(void);
-/* sizeof() of the structs above as compiled (which: 0 config, 1 decode, 2 extend),
- * so a binding can verify its own layout before the first call. */
+/* sizeof() of the structs above as compiled (which: 0 config, 1 decode, 2 extend,
+ * 3 rope-store), so a binding can verify its own layout before the first call. */
 uint64_t b200_attn_struct_size(int which);
 const char* b200_attn_error_string(int code);
 
@@ -174,6 +174,50 @@ int b200_kv_store(void* k_buf, void* v_buf, int64_t k_stride_t, int64_t v_stride
                   int64_t k_src_stride_t, int64_t k_src_stride_h, int64_t v_src_stride_t,
                   int64_t v_src_stride_h, int32_t num_tokens, int32_t hkv, int32_t d, int32_t dv,
                   int32_t kv_dtype, const float* k_scale, const float* v_scale, b200_stream_t stream);
+
+/* Rotary position embedding fused with the KV write: one launch replaces the model's
+ * `q, k = self.rotary_emb(positions, q, k)` (scratchpad/nn/models/llama/llama.py:149-152 ->
+ * RotaryEmbedding.forward_cuda, scratchpad/nn/layers/rotary_embedding.py:131-164, an in-place kernel on q and k)
+ * and MHATokenToKVPool.set_kv_buffer (memory/pool.py:392-424, two index_put_ + div_/cast).
+ * Arithmetic is RotaryEmbedding.forward_native's (rotary_embedding.py:24-49,101-129) in the model dtype: every
+ * product and every sum is rounded to bf16, so results are bit-identical to the reference's:
+ *   o1 = bf16(bf16(x1*cos) - bf16(x2*sin)),  o2 = bf16(bf16(x2*cos) + bf16(x1*sin)),
+ * (x1, x2) = (x[i], x[i + rotary_dim/2]) for neox style, (x[2i], x[2i+1]) for GPT-J style; elements
+ * >= rotary_dim pass through.  cos/sin come from the module's cos_sin_cache[positions[t]] = [cos | sin]
+ * (rotary_embedding.py:90-99), whatever scaling variant built it (llama3, linear, dynamic NTK, ...).
+ * q is rotated in place.  k is rotated and stored as k_buf[loc[t]] = quant(rot(k[t])); it is written back
+ * in place only when write_back_k != 0 (the extend kernels read the new tokens' K from the k argument;
+ * decode reads it from the pool).  v is stored as b200_kv_store does. */
+typedef struct b200_rope_store_params {
+  void* q;                  /* bf16 [T, hq, d], rotated in place; NULL = no q */
+  int64_t q_stride_t, q_stride_h;
+  void* k;                  /* bf16 [T, hkv, d] */
+  int64_t k_src_stride_t, k_src_stride_h;
+  const void* v;            /* bf16 [T, hkv, dv] */
+  int64_t v_src_stride_t, v_src_stride_h;
+  const void* positions;    /* [T] int32 / int64 (pos_dtype = B200_IDX_*) */
+  const void* cos_sin_cache; /* [max_position, rotary_dim] = [cos(rotary_dim/2) | sin(rotary_dim/2)] */
+  int64_t cache_stride;     /* row stride in elements */
+  int32_t cache_dtype;      /* B200_CACHE_BF16 / B200_CACHE_F32 (f32 is rounded to bf16 first: cos.to(x.dtype)) */
+  int32_t pos_dtype;
+  int32_t rotary_dim;       /* multiple of 16, <= d */
+  int32_t is_neox;
+  void* k_buf;              /* NULL (with v_buf) = rotate only, nothing stored (save_kv_cache = False) */
+  void* v_buf;
+  int64_t k_stride_t, v_stride_t; /* pool token strides in elements */
+  const void* loc;          /* [T] slot ids (out_cache_loc) */
+  int32_t loc_dtype;
+  int32_t num_tokens, hq, hkv, d, dv;
+  int32_t kv_dtype;
+  const float* k_scale;
+  const float* v_scale;
+  int32_t write_back_k;
+  int32_t reserved;
+} b200_rope_store_params;
+#define B200_CACHE_BF16 0
+#define B200_CACHE_F32 1
+
+int b200_rope_kv_store(const b200_rope_store_params* p, b200_stream_t stream);
 
 /* Test hook for the bit-exact gather contract: copies, with the kernels' own
  * slot -> row address arithmetic, rows buf[req_to_token[req_pool_indices[i], t]]

@@ -16,11 +16,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200_ATTN_LIB") or os.path.join(_HERE, "csrc", "libb200attn.so")
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 KV_BF16, KV_FP8_E4M3 = 0, 1
 IDX_I32, IDX_I64 = 0, 1
 PATH_AUTO, PATH_MMA, PATH_TC = -1, 0, 1
+CACHE_BF16, CACHE_F32 = 0, 1
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_NOT_PLANNED = 0, 1, 2, 3, 4
 
@@ -33,6 +34,7 @@ EXPORTS = (
     "b200_attn_decode",
     "b200_attn_extend",
     "b200_kv_store",
+    "b200_rope_kv_store",
     "b200_debug_gather",
     "b200_debug_decode_naive",
 )
@@ -91,6 +93,22 @@ class ExtendParams(C.Structure):
     ]
 
 
+class RopeStoreParams(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("q_stride_t", C.c_int64), ("q_stride_h", C.c_int64),
+        ("k", C.c_void_p), ("k_src_stride_t", C.c_int64), ("k_src_stride_h", C.c_int64),
+        ("v", C.c_void_p), ("v_src_stride_t", C.c_int64), ("v_src_stride_h", C.c_int64),
+        ("positions", C.c_void_p), ("cos_sin_cache", C.c_void_p), ("cache_stride", C.c_int64),
+        ("cache_dtype", C.c_int32), ("pos_dtype", C.c_int32), ("rotary_dim", C.c_int32), ("is_neox", C.c_int32),
+        ("k_buf", C.c_void_p), ("v_buf", C.c_void_p), ("k_stride_t", C.c_int64), ("v_stride_t", C.c_int64),
+        ("loc", C.c_void_p), ("loc_dtype", C.c_int32),
+        ("num_tokens", C.c_int32), ("hq", C.c_int32), ("hkv", C.c_int32), ("d", C.c_int32), ("dv", C.c_int32),
+        ("kv_dtype", C.c_int32),
+        ("k_scale", C.c_void_p), ("v_scale", C.c_void_p),
+        ("write_back_k", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 class B200AttnError(RuntimeError):
     def __init__(self, code: int, what: str, where: str):
         super().__init__(f"{where} failed: [{code}] {what}")
@@ -133,7 +151,7 @@ def load() -> C.CDLL:
         )
     lib.b200_attn_struct_size.restype = C.c_uint64
     lib.b200_attn_struct_size.argtypes = [C.c_int]
-    for which, cls in enumerate((AttnConfig, DecodeParams, ExtendParams)):
+    for which, cls in enumerate((AttnConfig, DecodeParams, ExtendParams, RopeStoreParams)):
         if lib.b200_attn_struct_size(which) != C.sizeof(cls):
             raise ImportError(f"{cls.__name__}: ctypes layout ({C.sizeof(cls)} B) != compiled layout "
                               f"({lib.b200_attn_struct_size(which)} B)")
@@ -143,6 +161,7 @@ def load() -> C.CDLL:
     lib.b200_attn_decode.argtypes = [C.POINTER(DecodeParams), vp]
     lib.b200_attn_extend.argtypes = [C.POINTER(ExtendParams), vp]
     lib.b200_kv_store.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp, i64, i64, i64, i64, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.b200_rope_kv_store.argtypes = [C.POINTER(RopeStoreParams), vp]
     lib.b200_debug_gather.argtypes = [vp, i64, i32, vp, i64, vp, vp, i32, vp, i32, vp, vp]
     lib.b200_debug_decode_naive.argtypes = [C.POINTER(DecodeParams), vp, vp, i32, vp]
     for name in EXPORTS[3:]:

@@ -49,11 +49,15 @@ class AttentionBackend(ABC):
     def get_cuda_graph_seq_len_fill_value(self):
         raise NotImplementedError()
 
-    def forward(self, q, k, v, layer, forward_batch, save_kv_cache: bool = True):
+    def forward(self, q, k, v, layer, forward_batch, save_kv_cache: bool = True, rope=None):
+        # rope is this backend's one extension of the reference signature: (rotary_emb, positions) asks the backend
+        # to apply the rotary embedding itself, fused with the KV write (rotary_embedding.py); None = the reference's
+        # contract, q and k arrive rotated
+        kw = {} if rope is None else {"rope": rope}
         if forward_batch.forward_mode.is_decode():
-            return self.forward_decode(q, k, v, layer, forward_batch, save_kv_cache=save_kv_cache)
+            return self.forward_decode(q, k, v, layer, forward_batch, save_kv_cache=save_kv_cache, **kw)
         else:
-            return self.forward_extend(q, k, v, layer, forward_batch, save_kv_cache=save_kv_cache)
+            return self.forward_extend(q, k, v, layer, forward_batch, save_kv_cache=save_kv_cache, **kw)
 
     def forward_decode(self, q, k, v, layer, forward_batch, save_kv_cache: bool = True):
         raise NotImplementedError()
@@ -188,7 +192,17 @@ class CudaB200AttnBackend(AttentionBackend):
         if getattr(layer, "sliding_window_size", -1) not in (None, -1):
             raise NotImplementedError("cuda_b200 backend: sliding-window attention is not supported")
 
-    def forward_decode(self, q, k, v, layer, forward_batch, save_kv_cache: bool = True):
+    def _rope_and_store(self, rope, q, k, v, layer, forward_batch, save_kv_cache: bool, write_back_k: bool) -> None:
+        """q (in place) and k rotated, (k, v) written to the pool: one launch instead of the model's rotary kernel
+        (llama.py:149-152) plus set_kv_buffer's two index_put_ (pool.py:392-424)."""
+        rotary_emb, positions = rope
+        if save_kv_cache:
+            rotary_emb.rope_kv_store(positions, q, k, v, forward_batch.token_to_kv_pool, layer.layer_id,
+                                     forward_batch.out_cache_loc, write_back_k)
+        else:
+            rotary_emb(positions, q, k)
+
+    def forward_decode(self, q, k, v, layer, forward_batch, save_kv_cache: bool = True, rope=None):
         self._check_layer(layer)
         hq, d, dv = layer.tp_q_head_num, layer.qk_head_dim, layer.v_head_dim
         q = q.reshape(-1, hq * d)
@@ -196,7 +210,10 @@ class CudaB200AttnBackend(AttentionBackend):
             q = q.contiguous()
         o = q.new_empty((q.shape[0], hq * dv))
         pool = forward_batch.token_to_kv_pool
-        if save_kv_cache:
+        if rope is not None:
+            # decode reads the new token's K from the pool, so the rotated k is not written back
+            self._rope_and_store(rope, q, k, v, layer, forward_batch, save_kv_cache, write_back_k=not save_kv_cache)
+        elif save_kv_cache:
             pool.set_kv_buffer(layer, forward_batch.out_cache_loc, k, v)
         kind, bs = self.forward_metadata
         assert kind == "decode" and bs == q.shape[0], "init_forward_metadata was not called for this batch"
@@ -220,7 +237,7 @@ class CudaB200AttnBackend(AttentionBackend):
         _lib.check(rc, "b200_attn_decode")
         return o
 
-    def forward_extend(self, q, k, v, layer, forward_batch, save_kv_cache: bool = True):
+    def forward_extend(self, q, k, v, layer, forward_batch, save_kv_cache: bool = True, rope=None):
         self._check_layer(layer)
         hq, hkv, d, dv = layer.tp_q_head_num, layer.tp_k_head_num, layer.qk_head_dim, layer.v_head_dim
         q3 = q.view(-1, hq, d) if q.dim() == 2 else q
@@ -228,7 +245,10 @@ class CudaB200AttnBackend(AttentionBackend):
             q3 = q3.contiguous()
         o = q.new_empty((q3.shape[0], hq * dv))
         pool = forward_batch.token_to_kv_pool
-        if save_kv_cache:
+        if rope is not None:
+            # the extend kernels read the new tokens' K from the k argument: rotated k is written back in place
+            self._rope_and_store(rope, q3, k, v, layer, forward_batch, save_kv_cache, write_back_k=True)
+        elif save_kv_cache:
             pool.set_kv_buffer(layer, forward_batch.out_cache_loc, k, v)
         kind, max_extend_len = self.forward_metadata
         assert kind == "extend", "init_forward_metadata was not called for this batch"

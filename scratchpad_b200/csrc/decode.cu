@@ -993,6 +993,7 @@ uint64_t b200_attn_struct_size(int which) {
     case 0: return sizeof(b200_attn_config);
     case 1: return sizeof(b200_decode_params);
     case 2: return sizeof(b200_extend_params);
+    case 3: return sizeof(b200_rope_store_params);
     default: return 0;
   }
 }

@@ -41,9 +41,14 @@ class RadixAttention(nn.Module):
         self.v_scale = None
         self.use_irope = use_irope
 
-    def forward(self, q, k, v, forward_batch, save_kv_cache: bool = True):
+    def forward(self, q, k, v, forward_batch, save_kv_cache: bool = True, rope=None):
+        """``rope=(rotary_emb, positions)``: q and k arrive UNrotated and the backend applies the rotary
+        embedding fused with its KV write (cuda_b200 only; see rotary_embedding.py).  Default: the reference's
+        contract (radix_attention.py:41-57)."""
         if k is not None:
             assert v is not None
             k = k.view(-1, self.tp_k_head_num, self.qk_head_dim)
             v = v.view(-1, self.tp_v_head_num, self.v_head_dim)
-        return forward_batch.attn_backend.forward(q, k, v, self, forward_batch, save_kv_cache)
+        if rope is None:
+            return forward_batch.attn_backend.forward(q, k, v, self, forward_batch, save_kv_cache)
+        return forward_batch.attn_backend.forward(q, k, v, self, forward_batch, save_kv_cache, rope=rope)

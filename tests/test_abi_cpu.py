@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_the_header_layout():
     lib = _lib.load()
-    for which, cls in enumerate((_lib.AttnConfig, _lib.DecodeParams, _lib.ExtendParams)):
+    for which, cls in enumerate((_lib.AttnConfig, _lib.DecodeParams, _lib.ExtendParams, _lib.RopeStoreParams)):
         assert lib.b200_attn_struct_size(which) == ctypes.sizeof(cls), cls
 
 
@@ -60,9 +60,55 @@ def test_backend_surface_matches_reference_abc():
         "forward_decode": ["self", "q", "k", "v", "layer", "forward_batch", "save_kv_cache"],
         "forward_extend": ["self", "q", "k", "v", "layer", "forward_batch", "save_kv_cache"],
     }
+    ext = ("forward", "forward_decode", "forward_extend")  # CudaB200AttnBackend appends one optional keyword: rope
     for cls in (sb.AttentionBackend, sb.CudaB200AttnBackend):
         for name, args in want.items():
-            assert list(inspect.signature(getattr(cls, name)).parameters) == args, (cls, name)
+            got = list(inspect.signature(getattr(cls, name)).parameters)
+            if name in ext and got[-1] == "rope":
+                assert inspect.signature(getattr(cls, name)).parameters["rope"].default is None
+                got = got[:-1]
+            assert got == args, (cls, name)
+
+
+def test_rope_store_argument_checks_run_before_any_launch():
+    """b200_rope_kv_store validates on the host first: these return without touching a device."""
+    lib = _lib.load()
+    buf = (ctypes.c_uint8 * 4096)()
+    base = (ctypes.addressof(buf) + 15) & ~15
+
+    def params(**kw):
+        p = _lib.RopeStoreParams(k=base, k_src_stride_t=128, k_src_stride_h=64, positions=base, cos_sin_cache=base,
+                                 cache_stride=64, cache_dtype=_lib.CACHE_BF16, pos_dtype=_lib.IDX_I64, rotary_dim=64,
+                                 is_neox=1, num_tokens=1, hq=0, hkv=2, d=64, dv=64, kv_dtype=_lib.KV_BF16)
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    assert lib.b200_rope_kv_store(None, None) == _lib.ERR_INVALID
+    assert lib.b200_rope_kv_store(params(num_tokens=0), None) == _lib.OK          # nothing to do
+    assert lib.b200_rope_kv_store(params(rotary_dim=24), None) == _lib.ERR_UNSUPPORTED
+    assert lib.b200_rope_kv_store(params(rotary_dim=128), None) == _lib.ERR_UNSUPPORTED  # > head size
+    assert lib.b200_rope_kv_store(params(k=base + 2), None) == _lib.ERR_INVALID   # misaligned
+    assert lib.b200_rope_kv_store(params(k_buf=base), None) == _lib.ERR_INVALID   # k_buf without v_buf
+    assert lib.b200_rope_kv_store(params(cache_dtype=5), None) == _lib.ERR_UNSUPPORTED
+
+
+def test_rotary_module_builds_the_reference_cache():
+    """get_rope -> cos_sin_cache identical to the reference module's (tests/golden/rope_*.npz hold the caches the
+    reference built in the build container)."""
+    from scratchpad_b200.rotary_embedding import get_rope
+    from golden_util import golden_names, load_golden
+    scaling = {"rope_type": "llama3", "factor": 32.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+               "original_max_position_embeddings": 8192}
+    for name in golden_names("rope"):
+        g = load_golden(name)
+        emb = get_rope(g["head_size"], g["rotary_dim"], g["max_position"], g["base"], bool(g["is_neox"]),
+                       scaling if g["llama3"] else None, dtype=torch.bfloat16)
+        want = g["cos_sin_cache"].view(torch.int16)
+        assert torch.equal(emb.cos_sin_cache.cpu().view(torch.int16), want), name
+    with pytest.raises(RuntimeError):  # no CPU fallback
+        emb(torch.zeros(1, dtype=torch.int64), torch.zeros(1, 64, dtype=torch.bfloat16),
+            torch.zeros(1, 64, dtype=torch.bfloat16))
 
 
 def test_forward_mode_values_and_dispatch():

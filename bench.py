@@ -56,6 +56,9 @@ def parse_args():
                     help="decode only: include the model's rotary embedding in the layer-call -- 'separate' = the "
                          "reference's sequence rotary_emb(positions, q, k) then attention (llama.py:149-152), 'fused' = "
                          "one b200_rope_kv_store launch doing the rotation and the KV write (SURVEY 8f #1)")
+    ap.add_argument("--page-size", type=int, default=1, choices=[1, 16, 32, 64, 128],
+                    help="decode only: KV pool page size.  1 = the reference's token-granular pool (default, the headline "
+                         "configuration); > 1 = paged pool, random pages, whole tiles fetched by TMA (SURVEY 8f #4)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -200,6 +203,9 @@ def build_state(args, rank, world):
     shared = w.shared_prefix
     need = shared + sum(n - shared if shared and n >= shared else n for n in seq_lens)
     pool_tokens = need + 64
+    ps = args.page_size
+    if ps > 1:
+        pool_tokens = (shared // ps + sum((n + ps - 1) // ps for n in seq_lens) + 4) * ps
     kv_elt = 2 if w.kv_dtype == torch.bfloat16 else 1
     per_layer = 2 * (pool_tokens + 1) * hkv_l * w.head_dim * kv_elt
     layers = pick_layers(per_layer, args.layers, w.layers_total)
@@ -208,7 +214,7 @@ def build_state(args, rank, world):
     fused = args.kv_layout == "fused" or (args.kv_layout == "auto" and row_bytes < 256)
     runner = synth.make_model_runner(w.hq_total, w.hkv_total, w.head_dim, tp_size=world, layer_num=layers,
                                      pool_tokens=pool_tokens, max_reqs=w.batch, context_len=max(seq_lens) + 1,
-                                     kv_dtype=w.kv_dtype, device=dev, fused_kv=fused)
+                                     kv_dtype=w.kv_dtype, device=dev, fused_kv=fused, page_size=ps)
     fill_pool(runner.token_to_kv_pool, 1000 + rank % max(world, 1))
     cascade = args.cascade == "on" or (args.cascade == "auto" and w.shared_prefix > 0)
     backend = CudaB200AttnBackend(runner, cascade=cascade)
@@ -320,7 +326,7 @@ def run_reference(args, rank, world):
 def workload_config(w, world, args, st):
     cfg = {
         "workload": f"{w.name}: {w.description}", "batch": w.batch, "hq_per_gpu": w.hq_total // world,
-        "hkv_per_gpu": w.hkv_total // world, "head_dim": w.head_dim, "page_size": 1,
+        "hkv_per_gpu": w.hkv_total // world, "head_dim": w.head_dim, "page_size": args.page_size,
         "kv_dtype": "bf16" if w.kv_dtype == torch.bfloat16 else "fp8_e4m3", "index": args.index_mode,
         "parallelism": f"kv-head sharded x{world} (tensor-parallel head layout), no collective on the path",
         "step": "one forward_decode layer-call: fused KV store + split-KV paged decode + LSE merge; "

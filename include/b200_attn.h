@@ -23,7 +23,9 @@
  *   req_pool_indices, seq_lens  int32 or int64 (eager batches are int64,
  *                 schedule_batch.py:916-924; graph buffers int32,
  *                 cuda_graph_runner.py:194-197) -- see idx_dtype fields
- *   page size is 1 (model_runner.py:431-432): the gather unit is one token row.
+ *   page size is 1 in the reference (model_runner.py:431-432): the gather unit is one token row.  Decode also
+ *                 accepts page sizes 16..128 (b200_decode_params.page_size): req_to_token keeps one slot id per
+ *                 token, slots of a page are consecutive, and the gather unit becomes a page.
  */
 #ifndef B200_ATTN_H_
 #define B200_ATTN_H_
@@ -35,7 +37,7 @@
 extern "C" {
 #endif
 
-#define B200_ATTN_ABI_VERSION 7
+#define B200_ATTN_ABI_VERSION 8
 
 /* kv_dtype */
 #define B200_KV_BF16 0
@@ -97,7 +99,13 @@ typedef struct b200_decode_params {
   void* ev_kernel_begin;    /* optional cudaEvent_t pair recorded on `stream` around the */
   void* ev_kernel_end;      /* split-KV kernel alone (bench.py roofline timing); NULL = off */
   int32_t cascade;          /* must equal the `cascade` b200_attn_plan was called with for this batch */
-  int32_t reserved;
+  int32_t page_size;        /* 0 / 1: token-granular pool (the reference today, model_runner.py:431-432).
+                             * 16, 32, 64 or 128: paged pool -- the caller guarantees, for every request row r and
+                             * position t < seq_len, req_to_token[r, t] = req_to_token[r, t - t % page_size] +
+                             * t % page_size with that page start a multiple of page_size (what a paged allocator
+                             * yields: schedule_batch.py:754-828, radix_cache.py:57-66 page-aligned matching).
+                             * Whole KV tiles are then fetched by TMA box copies, one per page run. */
+  int64_t kv_pool_rows;     /* paged only: token rows of k_buf / v_buf (bounds of the tensor maps) */
 } b200_decode_params;
 
 /* One layer's extend / chunked-prefill attention over prefix-cached chunks

@@ -6,7 +6,7 @@ library behind it.  See DESIGN.md / INTEGRATION.md.
 
 from .backend import AttentionBackend, CudaB200AttnBackend
 from .forward_info import ForwardBatch, ForwardMode, compute_extend_start_loc
-from .pool import MHATokenToKVPool, ReqToTokenPool, TokenToKVPoolAllocator
+from .pool import MHATokenToKVPool, PagedTokenToKVPoolAllocator, ReqToTokenPool, TokenToKVPoolAllocator
 from .radix_attention import RadixAttention
 
 __all__ = [
@@ -16,6 +16,7 @@ __all__ = [
     "ForwardMode",
     "compute_extend_start_loc",
     "MHATokenToKVPool",
+    "PagedTokenToKVPoolAllocator",
     "ReqToTokenPool",
     "TokenToKVPoolAllocator",
     "RadixAttention",

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200_ATTN_LIB") or os.path.join(_HERE, "csrc", "libb200attn.so")
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 KV_BF16, KV_FP8_E4M3 = 0, 1
 IDX_I32, IDX_I64 = 0, 1
@@ -68,7 +68,7 @@ class DecodeParams(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
         ("max_bs", C.c_int32), ("force_path", C.c_int32),
         ("ev_kernel_begin", C.c_void_p), ("ev_kernel_end", C.c_void_p),
-        ("cascade", C.c_int32), ("reserved", C.c_int32),
+        ("cascade", C.c_int32), ("page_size", C.c_int32), ("kv_pool_rows", C.c_int64),
     ]
 
 

@@ -230,6 +230,7 @@ class CudaB200AttnBackend(AttentionBackend):
             k_scale=_ptr(ks), v_scale=_ptr(vs),
             workspace=self.workspace.data_ptr(), workspace_bytes=self.workspace.numel(),
             max_bs=self.max_bs, force_path=self.force_path, cascade=self.cascade,
+            page_size=int(getattr(pool, "page_size", 1)), kv_pool_rows=kb.shape[0],
         )
         if self.profile_events is not None:
             p.ev_kernel_begin, p.ev_kernel_end = self.profile_events

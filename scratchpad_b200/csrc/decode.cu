@@ -34,6 +34,8 @@
 // in f16; per-head scales are folded into the softmax scale (K) and the
 // epilogue (V).
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace b200 {
@@ -337,6 +339,7 @@ struct DecodeArgs {
   float sm_scale, logit_cap;
   const float* k_scale;
   const float* v_scale;
+  int box_tok;  // paged pools: token rows per TMA box = min(tile tokens, page size)
 };
 
 // ---- optional per-CTA timeline (build with -DB200_DEC_TRACE; tools/dec_trace.py): %globaltimer at six points
@@ -383,10 +386,11 @@ __device__ __forceinline__ void cursor_advance(Cursor& c, const DecodeArgs& a) {
   }
 }
 
-template <int D_, bool FP8_, int HPC_, int NW_>
+template <int D_, bool FP8_, int HPC_, int NW_, bool PAGED_ = false>
 struct DecodeCfg {
   static constexpr int D = D_;
   static constexpr bool FP8 = FP8_;
+  static constexpr bool PAGED = PAGED_;  // page_size >= 16: whole tiles arrive by TMA box copies (one per page)
   static constexpr int HPC = HPC_;     // kv heads per CTA
   static constexpr int NW = NW_;       // warps per CTA
   static constexpr int NT = NW * 32;
@@ -400,7 +404,10 @@ struct DecodeCfg {
   static constexpr int TOK_PER_PASS = NT / CPT;
   static constexpr int TILE_BYTES = HPC * TN * SEG;  // K (or V) bytes per stage
   static constexpr int STAGE_BYTES = 2 * TILE_BYTES;
-  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES;
+  static constexpr int ROWB = SEG >= 128 ? 128 : SEG;  // bytes of one shared-memory row = inner extent of a TMA box
+  static constexpr int HALVES = SEG / ROWB;            // 256-byte segments are kept as two 128-byte column halves
+  // paged: + slack to align the ring to the 1024-byte swizzle atom, + kStages mbarriers behind it
+  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + (PAGED ? 1024 + 64 : 0);
   static constexpr int NSLOT = (TN + 31) / 32;  // slot-id registers per lane
   static constexpr int KC = D / 16;             // MMA k-chunks (bf16) == 16-elt chunks (fp8)
   static constexpr int MT = D / 16;             // PV m-tiles
@@ -409,16 +416,67 @@ struct DecodeCfg {
   static_assert(CPS == 4 || CPS == 8 || CPS == 16, "segment size");
 };
 
+// Byte offset of 16-byte chunk `chunk` of row (head, tok) inside a K (or V) tile.  Rows are 128 bytes (64 for
+// 64-byte segments), XOR-swizzled by 16-byte chunk exactly the way TMA's SWIZZLE_128B (SWIZZLE_64B) mode lays down
+// a [tokens x 128 B] box at a 1024-byte-aligned address, so the LDGSTS row gather and the TMA page copy fill ONE
+// layout and ldmatrix reads it conflict-free.  A 256-byte segment (bf16, head_dim 128) is two 128-byte column halves.
+template <int CPS, int TN>
+__device__ __forceinline__ int tile_chunk_off(int head, int tok, int chunk) {
+  if constexpr (CPS == 16) return (((head * 2 + (chunk >> 3)) * TN + tok) * 8 + ((chunk & 7) ^ (tok & 7))) * 16;
+  else return ((head * TN + tok) * CPS + swz_chunk<CPS>(chunk, tok)) * 16;
+}
+
+// ---- mbarrier / TMA wrappers (paged pools) -------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  int spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1 << 22)) __trap();  // a copy that never lands must not hang the GPU
+  }
+}
+// one [box_tok x ROWB-byte] box of the pool viewed as (head_dim, kv heads, token rows) -> shared memory
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 template <class C>
-__global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a) {
+__device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorMap* tmk, const CUtensorMap* tmv) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int D = C::D, HPC = C::HPC, TN = C::TN, SEG = C::SEG, CPS = C::CPS, CPT = C::CPT;
-  constexpr bool FP8 = C::FP8;
+  constexpr bool FP8 = C::FP8, PAGED = C::PAGED;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x;
   const int h0 = blockIdx.y * HPC;  // first kv head of this CTA
   DEC_TRACE(0);
+  uint32_t smem_base = smem_u32(smem);
+  uint32_t bar_base = 0, phases = 0;  // paged: one "tile has landed" mbarrier per stage; parity bit per stage
+  if constexpr (PAGED) {
+    smem_base = (smem_base + 1023u) & ~1023u;  // TMA's swizzle pattern is a function of the address
+    bar_base = smem_base + kStages * C::STAGE_BYTES;
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < kStages; ++s) mbar_init(bar_base + 8 * s, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
   pdl_wait();               // everything below reads what earlier launches (plan, kv store, qkv GEMM) wrote
   pdl_launch_dependents();  // let the merge grid get scheduled behind us; it waits for our completion
   DEC_TRACE(1);
@@ -439,7 +497,6 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
   const int p_tok = tid / CPT;  // token of pass 0; pass i adds i * TOK_PER_PASS
   const int p_wc = tid % CPT;   // 16-byte chunk inside the token's HPC*SEG span
   const int p_head = p_wc / CPS, p_col = p_wc % CPS;
-  const uint32_t smem_base = smem_u32(smem);
   const int64_t k_head_off = static_cast<int64_t>(h0) * SEG + p_wc * 16;  // byte offset inside a pool row
 
   int slot_reg[C::NSLOT];
@@ -455,6 +512,44 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
     const int tok0 = (c.gt - c.b_begin) * TN;
     const uint32_t sk = smem_base + stage * C::STAGE_BYTES;
     const uint32_t sv = sk + C::TILE_BYTES;
+    if constexpr (PAGED) {
+      // A tile that lies wholly inside the sequence is page-aligned runs of consecutive slots (slot = page * page_size
+      // + offset, request position t sits at offset t % page_size): one TMA box per (K|V, head, column half, page
+      // run), issued by the lanes of warp 0, all signalling the stage's mbarrier.  The ragged last tile of a request
+      // takes the row gather below (it zero-fills rows past the end, which the softmax masking relies on for V).
+      if (tok0 + TN <= c.seq_len) {
+        if (warp == 0) {
+          const uint32_t bar = bar_base + 8 * stage;
+          if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy traffic on this stage
+            mbar_arrive_expect_tx(bar, C::STAGE_BYTES);
+          }
+          __syncwarp();
+          const int bt = a.box_tok, nb = TN / bt;
+          const int nops = 2 * HPC * C::HALVES * nb;
+          for (int op0 = 0; op0 < nops; op0 += 32) {
+            const int op = op0 + lane;
+            const bool live = op < nops;
+            const int j = live ? op % nb : 0;
+            int rest = op / nb;
+            const int half = rest % C::HALVES;
+            rest /= C::HALVES;
+            const int head = rest % HPC, is_v = rest / HPC;
+            const int tokb = j * bt;
+            int sreg = slot_reg[0];
+#pragma unroll
+            for (int jj = 1; jj < C::NSLOT; ++jj)
+              if ((tokb >> 5) == jj) sreg = slot_reg[jj];
+            const int slot = __shfl_sync(0xffffffffu, sreg, tokb & 31);
+            if (live) {
+              const uint32_t dst = (is_v ? sv : sk) + tile_chunk_off<CPS, TN>(head, tokb, half * 8);
+              tma_load_3d(dst, is_v ? tmv : tmk, bar, half * (C::ROWB / C::ELT), h0 + head, slot);
+            }
+          }
+        }
+        return;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < C::PASSES; ++i) {
       const int tok = p_tok + i * C::TOK_PER_PASS;
@@ -464,7 +559,7 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
         if ((tok >> 5) == j) sreg = slot_reg[j];  // predicated select keeps slot_reg in registers
       const int slot = __shfl_sync(0xffffffffu, sreg, tok & 31);
       const int nbytes = (tok0 + tok < c.seq_len) ? 16 : 0;
-      const uint32_t doff = ((p_head * TN + tok) * CPS + swz_chunk<CPS>(p_col, tok)) * 16;
+      const uint32_t doff = tile_chunk_off<CPS, TN>(p_head, tok, p_col);
       cp_async16(sk + doff, kv_row_ptr(a.kbuf, slot, a.k_st_bytes) + k_head_off, nbytes);
       cp_async16(sv + doff, kv_row_ptr(a.vbuf, slot, a.v_st_bytes) + k_head_off, nbytes);
     }
@@ -524,23 +619,24 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
 
   auto compute_tile = [&](int stage, int nvalid) {
     // nvalid: valid tokens in this warp's 16-token slice (>= 1)
-    const uint32_t sk = smem_base + stage * C::STAGE_BYTES + (w_head * TN + w_sub * 16) * SEG;
+    const uint32_t sk = smem_base + stage * C::STAGE_BYTES;
     const uint32_t sv = sk + C::TILE_BYTES;
-    const int lrow = lane & 15;  // ldmatrix row (token) this lane addresses
+    const int wtok = w_sub * 16;  // this warp's 16-token slice of the tile
+    const int lrow = lane & 15;   // ldmatrix row (token) this lane addresses
     const int lhi = lane >> 4;
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     if constexpr (!FP8) {
 #pragma unroll
       for (int kc = 0; kc < C::KC; ++kc) {
         uint32_t af[4];
-        ldmatrix_x4(af, sk + lrow * SEG + swz_chunk<CPS>(2 * kc + lhi, lrow) * 16);
+        ldmatrix_x4(af, sk + tile_chunk_off<CPS, TN>(w_head, wtok + lrow, 2 * kc + lhi));
         mma_16816<false>(s, af, qf[kc][0], qf[kc][1]);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < C::KC / 2; ++j) {
         uint32_t r[4];  // r0:(tok 0-7, chunk 2j) r1:(tok 8-15, 2j) r2:(tok 0-7, 2j+1) r3:(tok 8-15, 2j+1)
-        ldmatrix_x4(r, sk + lrow * SEG + swz_chunk<CPS>(2 * j + lhi, lrow) * 16);
+        ldmatrix_x4(r, sk + tile_chunk_off<CPS, TN>(w_head, wtok + lrow, 2 * j + lhi));
         uint32_t af[4];
         af[0] = e4m3x2_to_f16x2(static_cast<uint16_t>(r[0] & 0xffffu));
         af[1] = e4m3x2_to_f16x2(static_cast<uint16_t>(r[1] & 0xffffu));
@@ -593,14 +689,14 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
 #pragma unroll
       for (int mt = 0; mt < C::MT; ++mt) {
         uint32_t af[4];  // V^T tile: rows d = 16mt + {gid, gid+8}, cols tokens
-        ldmatrix_x4_trans(af, sv + vtok * SEG + swz_chunk<CPS>(2 * mt + vhalf, vtok) * 16);
+        ldmatrix_x4_trans(af, sv + tile_chunk_off<CPS, TN>(w_head, wtok + vtok, 2 * mt + vhalf));
         mma_16816<false>(o[mt], af, pb0, pb1);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < C::MT / 2; ++j) {
         uint32_t r[4];  // transposed: lane holds bytes {V[2c][d0],V[2c][d0+1],V[2c+1][d0],V[2c+1][d0+1]}, d0 = 16ch+2gid
-        ldmatrix_x4_trans(r, sv + lrow * SEG + swz_chunk<CPS>(2 * j + lhi, lrow) * 16);
+        ldmatrix_x4_trans(r, sv + tile_chunk_off<CPS, TN>(w_head, wtok + lrow, 2 * j + lhi));
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const uint32_t t0 = prmt(r[2 * h], 0u, 0x3120u);      // tokens 0-7 : {d0:(2c,2c+1) | d0+1:(2c,2c+1)}
@@ -673,6 +769,12 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
 #endif
   while (cursor_valid(cc)) {
     cp_async_wait<kStages - 2>();
+    if constexpr (PAGED) {
+      if ((cc.gt - cc.b_begin) * TN + TN <= cc.seq_len) {  // same predicate the producer used: this tile came by TMA
+        mbar_wait(bar_base + 8 * stage, (phases >> stage) & 1u);
+        phases ^= 1u << stage;
+      }
+    }
     __syncthreads();
 #ifdef B200_DEC_TRACE
     if (first_tile) {
@@ -709,6 +811,18 @@ __global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a
   DEC_TRACE(4);
   cp_async_wait<0>();
   DEC_TRACE(5);
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a) {
+  decode_body<C>(a, nullptr, nullptr);
+}
+// paged pools: the two tensor maps (K and V pool of this layer) ride in the kernel parameters
+template <class C>
+__global__ void __launch_bounds__(C::NT, 2) decode_paged_kernel(const __grid_constant__ DecodeArgs a,
+                                                                const __grid_constant__ CUtensorMap tmk,
+                                                                const __grid_constant__ CUtensorMap tmv) {
+  decode_body<C>(a, &tmk, &tmv);
 }
 
 // ---------------------------------------------------------------------------
@@ -911,38 +1025,93 @@ static int device_info(DeviceInfo* di) {
   return B200_OK;
 }
 
-template <class C>
-static int launch_decode_t(const DecodeArgs& a, int grid_x, int grid_y, cudaStream_t st, bool query_only,
-                           int* occ_out) {
-  auto kern = decode_mma_kernel<C>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+// ---- tensor maps of a paged pool ---------------------------------------------------------------------------------
+// The pool buffer [rows, Hkv, D] (token stride given, so the fused K|V layout works too) as a 3-d tensor
+// (D, Hkv, rows); box = (one 128-byte row segment, 1 head, box_tok token rows), shared-memory side swizzled by
+// 128 bytes (64 for 64-byte segments) -- the layout tile_chunk_off() describes.
+struct PagedMaps {
+  CUtensorMap k, v;
+};
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int encode_pool_map(CUtensorMap* out, const void* buf, int64_t stride_t_bytes, int64_t rows, int hkv, int d, bool fp8,
+                           int box_tok) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    B200_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+    if (!sym || qres != cudaDriverEntryPointSuccess) return B200_ERR_UNSUPPORTED;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
   }
-  if (query_only) {
-    B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, C::NT, C::SMEM_BYTES));
-    return B200_OK;
-  }
-  return launch_pdl(kern, dim3(grid_x, grid_y), dim3(C::NT), C::SMEM_BYTES, st, a);
+  const int elt = fp8 ? 1 : 2, seg = d * elt, rowb = seg >= 128 ? 128 : seg;
+  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(hkv), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(seg), static_cast<cuuint64_t>(stride_t_bytes)};
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(rowb / elt), 1u, static_cast<cuuint32_t>(box_tok)};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = fn(out, fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(buf), gdim,
+                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? B200_OK : B200_ERR_INVALID;
 }
 
-template <int D, bool FP8>
-static int dispatch_hpc(const KernelChoice& kc, const DecodeArgs& a, int gx, int gy, cudaStream_t st, bool q, int* occ) {
+template <class C>
+static int launch_decode_t(const DecodeArgs& a, const PagedMaps* maps, int grid_x, int grid_y, cudaStream_t st, bool query_only,
+                           int* occ_out) {
+  static bool attr_set = false;  // per instantiation
+  if constexpr (C::PAGED) {
+    auto kern = decode_paged_kernel<C>;
+    if (!attr_set) {
+      B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+      attr_set = true;
+    }
+    if (query_only) {
+      B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, C::NT, C::SMEM_BYTES));
+      return B200_OK;
+    }
+    return launch_pdl(kern, dim3(grid_x, grid_y), dim3(C::NT), C::SMEM_BYTES, st, a, maps->k, maps->v);
+  } else {
+    auto kern = decode_mma_kernel<C>;
+    if (!attr_set) {
+      B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+      attr_set = true;
+    }
+    if (query_only) {
+      B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, C::NT, C::SMEM_BYTES));
+      return B200_OK;
+    }
+    return launch_pdl(kern, dim3(grid_x, grid_y), dim3(C::NT), C::SMEM_BYTES, st, a);
+  }
+}
+
+template <int D, bool FP8, bool PAGED>
+static int dispatch_hpc(const KernelChoice& kc, const DecodeArgs& a, const PagedMaps* m, int gx, int gy, cudaStream_t st, bool q,
+                        int* occ) {
   constexpr int NW = (D == 128 && !FP8) ? 4 : 8;
   switch (kc.hpc) {
-    case 1: return launch_decode_t<DecodeCfg<D, FP8, 1, NW>>(a, gx, gy, st, q, occ);
-    case 2: return launch_decode_t<DecodeCfg<D, FP8, 2, NW>>(a, gx, gy, st, q, occ);
-    case 4: return launch_decode_t<DecodeCfg<D, FP8, 4, NW>>(a, gx, gy, st, q, occ);
+    case 1: return launch_decode_t<DecodeCfg<D, FP8, 1, NW, PAGED>>(a, m, gx, gy, st, q, occ);
+    case 2: return launch_decode_t<DecodeCfg<D, FP8, 2, NW, PAGED>>(a, m, gx, gy, st, q, occ);
+    case 4: return launch_decode_t<DecodeCfg<D, FP8, 4, NW, PAGED>>(a, m, gx, gy, st, q, occ);
     case 8:
-      if constexpr (NW >= 8) return launch_decode_t<DecodeCfg<D, FP8, 8, NW>>(a, gx, gy, st, q, occ);
+      if constexpr (NW >= 8) return launch_decode_t<DecodeCfg<D, FP8, 8, NW, PAGED>>(a, m, gx, gy, st, q, occ);
   }
   return B200_ERR_UNSUPPORTED;
 }
 
-static int dispatch(const KernelChoice& kc, const DecodeArgs& a, int gx, int gy, cudaStream_t st, bool q, int* occ) {
-  if (kc.d == 64) return kc.fp8 ? dispatch_hpc<64, true>(kc, a, gx, gy, st, q, occ) : dispatch_hpc<64, false>(kc, a, gx, gy, st, q, occ);
-  return kc.fp8 ? dispatch_hpc<128, true>(kc, a, gx, gy, st, q, occ) : dispatch_hpc<128, false>(kc, a, gx, gy, st, q, occ);
+template <bool PAGED>
+static int dispatch_p(const KernelChoice& kc, const DecodeArgs& a, const PagedMaps* m, int gx, int gy, cudaStream_t st, bool q,
+                      int* occ) {
+  if (kc.d == 64)
+    return kc.fp8 ? dispatch_hpc<64, true, PAGED>(kc, a, m, gx, gy, st, q, occ) : dispatch_hpc<64, false, PAGED>(kc, a, m, gx, gy, st, q, occ);
+  return kc.fp8 ? dispatch_hpc<128, true, PAGED>(kc, a, m, gx, gy, st, q, occ) : dispatch_hpc<128, false, PAGED>(kc, a, m, gx, gy, st, q, occ);
+}
+
+// maps == nullptr: page size 1, row gather only
+static int dispatch(const KernelChoice& kc, const DecodeArgs& a, const PagedMaps* maps, int gx, int gy, cudaStream_t st, bool q,
+                    int* occ) {
+  return maps ? dispatch_p<true>(kc, a, maps, gx, gy, st, q, occ) : dispatch_p<false>(kc, a, nullptr, gx, gy, st, q, occ);
 }
 
 static int get_config(int max_bs, int hq, int hkv, int d, int dv, int kv_dtype, int force_path, b200_attn_config* out) {
@@ -956,7 +1125,7 @@ static int get_config(int max_bs, int hq, int hkv, int d, int dv, int kv_dtype, 
   if (rc) return rc;
   int occ = 0;
   DecodeArgs dummy{};
-  rc = dispatch(kc, dummy, 0, 0, nullptr, true, &occ);
+  rc = dispatch(kc, dummy, nullptr, 0, 0, nullptr, true, &occ);
   if (rc) return rc;
   if (occ < 1) return B200_ERR_UNSUPPORTED;
   if (occ > 2) occ = 2;
@@ -1144,7 +1313,22 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
     rc = launch_shared_prefix_tc(p, t, cas_o, cas_lse, cas_splits, st);
     if (rc) return rc;
   }
-  rc = dispatch(kc, a, cfg.grid_ctas, p->hkv / kc.hpc, st, false, nullptr);
+  // page_size > 1: slots of a page are consecutive and request position t sits at offset
+  // t % page_size of its page, so whole tiles are fetched with TMA box copies, one per page run
+  PagedMaps maps;
+  const PagedMaps* mp = nullptr;
+  a.box_tok = 0;
+  if (p->page_size > 1) {
+    const int ps = p->page_size;
+    if (ps < 16 || ps > 128 || (ps & (ps - 1)) || p->kv_pool_rows <= 0) return B200_ERR_UNSUPPORTED;
+    a.box_tok = ps < cfg.tile_tokens ? ps : cfg.tile_tokens;
+    rc = encode_pool_map(&maps.k, p->k_buf, a.k_st_bytes, p->kv_pool_rows, p->hkv, p->d, kc.fp8, a.box_tok);
+    if (rc) return rc;
+    rc = encode_pool_map(&maps.v, p->v_buf, a.v_st_bytes, p->kv_pool_rows, p->hkv, p->dv, kc.fp8, a.box_tok);
+    if (rc) return rc;
+    mp = &maps;
+  }
+  rc = dispatch(kc, a, mp, cfg.grid_ctas, p->hkv / kc.hpc, st, false, nullptr);
   if (rc) return rc;
   if (p->ev_kernel_end) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(p->ev_kernel_end), st));
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p->o);

@@ -27,6 +27,7 @@ import torch
 from . import _lib
 
 FP8_DTYPES = (torch.float8_e4m3fn,)
+PAGE_SIZES = (16, 32, 64, 128)
 
 
 class ReqToTokenPool:
@@ -100,6 +101,101 @@ class TokenToKVPoolAllocator:
         self.free_slots = torch.arange(1, self.size + 1, dtype=torch.int64, device=self.device)
 
 
+class PagedTokenToKVPoolAllocator:
+    """Page-granular free list for ``page_size > 1`` -- the allocator the reference's paged call sites expect
+    (``alloc_extend(prefix_lens, seq_lens, last_loc, extend_num_tokens)`` / ``alloc_decode(seq_lens, last_loc)`` /
+    ``page_size`` / ``backup_state``: schedule_batch.py:754-828) but does not ship.
+
+    Pages are numbered from 1 (page 0 = the dummy slots 0..page_size-1 padded tokens write to); slot =
+    page * page_size + offset, and request position t always sits at offset ``t % page_size`` of its page.  That
+    invariant is what lets the decode kernel fetch a page with one TMA box copy."""
+
+    def __init__(self, size: int, page_size: int, dtype: torch.dtype, device: str, kvcache: "MHATokenToKVPool"):
+        if page_size not in PAGE_SIZES:
+            raise NotImplementedError(f"page_size must be one of {PAGE_SIZES}, got {page_size}")
+        self.size = size
+        self.page_size = page_size
+        self.num_pages = size // page_size
+        self.dtype = dtype
+        self.device = device
+        self._kvcache = kvcache
+        self.clear()
+
+    def available_size(self):
+        return len(self.free_pages) * self.page_size
+
+    def get_kvcache(self):
+        return self._kvcache
+
+    def clear(self):
+        self.free_pages = torch.arange(1, self.num_pages + 1, dtype=torch.int64, device=self.device)
+
+    def backup_state(self):
+        return self.free_pages
+
+    def restore_state(self, free_pages):
+        self.free_pages = free_pages
+
+    def _take(self, n: int):
+        pages, self.free_pages = self.free_pages[:n], self.free_pages[n:]
+        return pages
+
+    def alloc(self, need_size: int):
+        """Whole pages for ``need_size`` tokens (page-aligned callers only)."""
+        assert need_size % self.page_size == 0, "token-granular alloc on a paged pool"
+        n = need_size // self.page_size
+        if n > len(self.free_pages):
+            return None
+        pages = self._take(n)
+        return (pages[:, None] * self.page_size + torch.arange(self.page_size, device=self.device)).reshape(-1)
+
+    def alloc_extend(self, prefix_lens: torch.Tensor, seq_lens: torch.Tensor, last_loc: torch.Tensor,
+                     extend_num_tokens: int):
+        """Slots for positions ``prefix_lens[i] .. seq_lens[i]-1`` of every request: first the rest of the page
+        ``last_loc[i]`` (slot of position ``prefix_lens[i]-1``, -1 if none) lives in, then fresh pages."""
+        ps = self.page_size
+        pre, seq, last = prefix_lens.tolist(), seq_lens.tolist(), last_loc.tolist()
+        need_pages = sum((s + ps - 1) // ps - (p + ps - 1) // ps for p, s in zip(pre, seq))
+        if need_pages > len(self.free_pages):
+            return None
+        pages = self._take(need_pages).tolist()
+        out, cur = [], 0
+        for p, s, l in zip(pre, seq, last):
+            t = p
+            while t < s and t % ps != 0:  # finish the partially filled page
+                assert l >= 0 and (l + 1) % ps == t % ps, "last_loc is not the slot of position prefix_len - 1"
+                l += 1
+                out.append(l)
+                t += 1
+            while t < s:
+                n = min(ps, s - t)
+                out.extend(range(pages[cur] * ps, pages[cur] * ps + n))
+                cur += 1
+                t += n
+        assert len(out) == extend_num_tokens
+        return torch.tensor(out, dtype=torch.int64, device=self.device)
+
+    def alloc_decode(self, seq_lens: torch.Tensor, last_loc: torch.Tensor):
+        """One slot per request for position ``seq_lens[i]-1``: the next offset of the page ``last_loc[i]`` lives
+        in, or offset 0 of a fresh page when that position starts a page."""
+        ps = self.page_size
+        pos = (seq_lens.to(torch.int64) - 1).to(last_loc.device)
+        fresh = (pos % ps) == 0
+        n = int(fresh.sum().item())
+        if n > len(self.free_pages):
+            return None
+        out = last_loc.to(torch.int64) + 1
+        out[fresh] = self._take(n).to(out.device) * ps
+        return out
+
+    def free(self, free_index: torch.Tensor):
+        """Slots back to the free list; a page returns when its first slot does (callers free page-aligned runs)."""
+        if free_index.numel() == 0:
+            return
+        firsts = free_index[free_index % self.page_size == 0] // self.page_size
+        self.free_pages = torch.cat((self.free_pages, firsts.to(torch.int64).to(self.free_pages.device)))
+
+
 class MHATokenToKVPool:
     def __init__(
         self,
@@ -114,8 +210,12 @@ class MHATokenToKVPool:
         v_head_dim: Optional[int] = None,
         fused_kv: bool = False,
     ):
-        if page_size != 1:
-            raise NotImplementedError("page_size > 1 is not supported (model_runner.py:431-432)")
+        # The reference refuses page_size > 1 at init (model_runner.py:431-432) although its scheduler and radix cache
+        # carry the paged code paths (schedule_batch.py:754-828, radix_cache.py:57-66).  The cuda_b200 backend takes
+        # pages of 16..128 tokens: req_to_token keeps one slot id per token, a page's slots are consecutive, and the
+        # decode kernel fetches whole pages with TMA box copies.
+        if page_size != 1 and page_size not in PAGE_SIZES:
+            raise NotImplementedError(f"page_size must be 1 or one of {PAGE_SIZES}, got {page_size}")
         self.size = size
         self.page_size = page_size
         self.dtype = dtype

@@ -86,7 +86,8 @@ def workload_seq_lens(w: Workload, gen: torch.Generator) -> List[int]:
 
 def make_model_runner(hq_total: int, hkv_total: int, head_dim: int, tp_size: int = 1, layer_num: int = 1,
                       pool_tokens: int = 4096, max_reqs: int = 64, context_len: int = 4096,
-                      kv_dtype: torch.dtype = torch.bfloat16, device: str = "cuda", fused_kv: bool = False):
+                      kv_dtype: torch.dtype = torch.bfloat16, device: str = "cuda", fused_kv: bool = False,
+                      page_size: int = 1):
     """The attributes AttentionBackend.__init__ may read over freshly allocated pools."""
     hkv_local = max(1, hkv_total // tp_size)  # ModelConfig.get_num_kv_heads (model_config.py:159-166)
     model_config = SimpleNamespace(
@@ -94,7 +95,7 @@ def make_model_runner(hq_total: int, hkv_total: int, head_dim: int, tp_size: int
         get_num_kv_heads=lambda tp: max(1, hkv_total // tp),
     )
     r2t = ReqToTokenPool(max_reqs + 1, context_len + 4, device)
-    kv = MHATokenToKVPool(pool_tokens, 1, kv_dtype, hkv_local, head_dim, layer_num, device, fused_kv=fused_kv)
+    kv = MHATokenToKVPool(pool_tokens, page_size, kv_dtype, hkv_local, head_dim, layer_num, device, fused_kv=fused_kv)
     return SimpleNamespace(
         model_config=model_config, tp_size=tp_size, device=device, dtype=torch.bfloat16,
         kv_cache_dtype="auto" if kv_dtype == torch.bfloat16 else "fp8_e4m3",
@@ -108,6 +109,42 @@ def make_layer(runner, layer_id: int = 0, logit_cap: float = 0.0) -> RadixAttent
     hq = cfg.num_attention_heads // runner.tp_size
     hkv = cfg.get_num_kv_heads(runner.tp_size)
     return RadixAttention(hq, cfg.head_dim, cfg.head_dim ** -0.5, hkv, layer_id, logit_cap=logit_cap)
+
+
+def build_paged_table(req_to_token: torch.Tensor, seq_lens: Sequence[int], pool_tokens: int, page_size: int,
+                      gen: torch.Generator, shared_prefix: int = 0, stale: bool = True):
+    """``build_page_table`` for ``page_size > 1``: every request owns randomly chosen pages (ids >= 1; page 0 holds
+    the dummy slots), position t sits at slot ``page(t // page_size) * page_size + t % page_size``.  A shared prefix
+    shares whole pages only (paged radix matching is page-aligned, radix_cache.py:57-66): ``shared_prefix`` is
+    rounded down to a page multiple.  ``pool_tokens`` is the pool's ``size``; the buffers have size + page_size rows."""
+    rows, cols = req_to_token.shape
+    b, ps = len(seq_lens), page_size
+    assert b <= rows and max(seq_lens, default=0) <= cols
+    if stale:
+        req_to_token.copy_(torch.randint(0, pool_tokens + 1, (rows, cols), generator=gen, dtype=torch.int32))
+    req_rows = torch.randperm(rows, generator=gen)[:b]
+    shared_pages = shared_prefix // ps
+    need = shared_pages + sum((n + ps - 1) // ps - (shared_pages if n >= shared_pages * ps and shared_pages else 0)
+                              for n in seq_lens)
+    num_pages = pool_tokens // ps
+    assert need <= num_pages, f"pool too small: need {need} pages, have {num_pages}"
+    pages = (torch.randperm(num_pages, generator=gen)[:need] + 1).to(torch.int32)
+    offs = torch.arange(ps, dtype=torch.int32)
+    shared = (pages[:shared_pages, None] * ps + offs).reshape(-1)
+    cur = shared_pages
+    for i, n in enumerate(seq_lens):
+        r = req_rows[i]
+        npg = (n + ps - 1) // ps
+        if shared_pages and n >= shared_pages * ps:
+            own = pages[cur:cur + npg - shared_pages]
+            cur += npg - shared_pages
+            ids = torch.cat([shared, (own[:, None] * ps + offs).reshape(-1)])
+        else:
+            own = pages[cur:cur + npg]
+            cur += npg
+            ids = (own[:, None] * ps + offs).reshape(-1)
+        req_to_token[r, :n] = ids[:n]
+    return req_rows.to(torch.int64)
 
 
 def build_page_table(req_to_token: torch.Tensor, seq_lens: Sequence[int], pool_tokens: int, gen: torch.Generator,
@@ -169,7 +206,11 @@ def make_decode_batch(runner, seq_lens: Sequence[int], gen: torch.Generator, mod
                       shared_prefix: int = 0, idx_dtype: torch.dtype = torch.int64, backend=None) -> ForwardBatch:
     r2t_pool = runner.req_to_token_pool
     table = torch.zeros(r2t_pool.req_to_token.shape, dtype=torch.int32)
-    rows = build_page_table(table, seq_lens, runner.token_to_kv_pool.size, gen, mode, shared_prefix)
+    ps = runner.token_to_kv_pool.page_size
+    if ps > 1:
+        rows = build_paged_table(table, seq_lens, runner.token_to_kv_pool.size, ps, gen, shared_prefix)
+    else:
+        rows = build_page_table(table, seq_lens, runner.token_to_kv_pool.size, gen, mode, shared_prefix)
     r2t_pool.req_to_token.copy_(table)
     dev = runner.device
     sl = torch.tensor(list(seq_lens), dtype=idx_dtype)

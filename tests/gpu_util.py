@@ -26,12 +26,12 @@ def assert_close(got, ref, abs_tol, rel_tol, what=""):
 FUSED_KV = False  # tests flip this to run every helper over the fused [P+1, 2, Hkv, D] pool layout
 
 
-def make_runner_from_case(k_buf, v_buf, r2t, kv_dtype, k_scale=None, v_scale=None, tp_hq=None):
+def make_runner_from_case(k_buf, v_buf, r2t, kv_dtype, k_scale=None, v_scale=None, tp_hq=None, page_size=1):
     """Pools on the GPU holding exactly the CPU case's bytes."""
     p1, hkv, d = k_buf.shape
-    runner = synth.make_model_runner(tp_hq, hkv, d, tp_size=1, layer_num=1, pool_tokens=p1 - 1,
+    runner = synth.make_model_runner(tp_hq, hkv, d, tp_size=1, layer_num=1, pool_tokens=p1 - page_size,
                                      max_reqs=r2t.shape[0] - 1, context_len=r2t.shape[1] - 4, kv_dtype=kv_dtype,
-                                     fused_kv=FUSED_KV)
+                                     fused_kv=FUSED_KV, page_size=page_size)
     pool = runner.token_to_kv_pool
     pool.k_buffer[0].copy_(k_buf.view(pool.store_dtype))
     pool.v_buffer[0].copy_(v_buf.view(pool.store_dtype))
@@ -43,9 +43,9 @@ def make_runner_from_case(k_buf, v_buf, r2t, kv_dtype, k_scale=None, v_scale=Non
 
 def run_decode_case(q, k_buf, v_buf, r2t, rpi, sl, sm_scale, logit_cap=0.0, kv_dtype=torch.bfloat16,
                     k_scale=None, v_scale=None, idx_dtype=torch.int64, q_slice_of_qkv=False, force_path=-1,
-                    cascade=None):
+                    cascade=None, page_size=1):
     b, hq, d = q.shape
-    runner = make_runner_from_case(k_buf, v_buf, r2t, kv_dtype, k_scale, v_scale, tp_hq=hq)
+    runner = make_runner_from_case(k_buf, v_buf, r2t, kv_dtype, k_scale, v_scale, tp_hq=hq, page_size=page_size)
     backend = CudaB200AttnBackend(runner, force_path=force_path, cascade=cascade)
     layer = synth.make_layer(runner, 0, logit_cap)
     layer.scaling = sm_scale
@@ -68,16 +68,22 @@ def run_decode_case(q, k_buf, v_buf, r2t, rpi, sl, sm_scale, logit_cap=0.0, kv_d
 
 
 def random_decode_case(hq, hkv, d, seq_lens, seed, kv_dtype=torch.bfloat16, shared_prefix=0, per_head=True,
-                       extra_rows=3, mode="random"):
-    """CPU tensors for one decode case (bf16-valued; fp8 pools quantised with amax/448 scales)."""
+                       extra_rows=3, mode="random", page_size=1):
+    """CPU tensors for one decode case (bf16-valued; fp8 pools quantised with amax/448 scales).
+    page_size > 1: page-granular tables (synth.build_paged_table) over a [pool + page_size, Hkv, D] buffer."""
     gen = torch.Generator().manual_seed(seed)
-    need = shared_prefix + sum(n - shared_prefix if shared_prefix and n >= shared_prefix else n for n in seq_lens)
-    pool = need + 17
     b = len(seq_lens)
     r2t = torch.zeros((b + extra_rows, max(max(seq_lens), 1) + 4), dtype=torch.int32)
-    rpi = synth.build_page_table(r2t, seq_lens, pool, gen, mode, shared_prefix)
-    kf = torch.randn((pool + 1, hkv, d), generator=gen).to(torch.bfloat16)
-    vf = torch.randn((pool + 1, hkv, d), generator=gen).to(torch.bfloat16)
+    if page_size > 1:
+        ps = page_size
+        pool = (shared_prefix // ps + sum((n + ps - 1) // ps for n in seq_lens) + 3) * ps
+        rpi = synth.build_paged_table(r2t, seq_lens, pool, ps, gen, shared_prefix)
+    else:
+        need = shared_prefix + sum(n - shared_prefix if shared_prefix and n >= shared_prefix else n for n in seq_lens)
+        pool = need + 17
+        rpi = synth.build_page_table(r2t, seq_lens, pool, gen, mode, shared_prefix)
+    kf = torch.randn((pool + page_size, hkv, d), generator=gen).to(torch.bfloat16)
+    vf = torch.randn((pool + page_size, hkv, d), generator=gen).to(torch.bfloat16)
     q = torch.randn((b, hq, d), generator=gen).to(torch.bfloat16)
     ks = vs = None
     if kv_dtype != torch.bfloat16:

@@ -142,7 +142,7 @@ def test_pool_layout_and_no_cpu_fallback():
     got = alloc.alloc(4)
     assert got.dtype == torch.int64 and got.tolist() == [1, 2, 3, 4]  # slot 0 is reserved
     with pytest.raises(NotImplementedError):
-        sb.MHATokenToKVPool(32, 16, torch.bfloat16, 2, 64, 1, "cpu")
+        sb.MHATokenToKVPool(32, 24, torch.bfloat16, 2, 64, 1, "cpu")  # pages are 16, 32, 64 or 128 tokens
 
 
 def test_synth_page_table_properties():

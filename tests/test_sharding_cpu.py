@@ -71,3 +71,51 @@ def test_two_rank_gloo_sharding_and_timing():
         err, t = ret[rank]
         assert err < 1e-6, err
         assert t == 2.0
+
+
+def test_paged_allocator_and_table_keep_the_page_invariant():
+    """Host logic of page_size > 1 (no GPU): slot = page * page_size + position % page_size, pages never shared
+    between requests except whole pages of a common prefix, page 0 never handed out."""
+    import torch
+    import scratchpad_b200 as sb
+    from scratchpad_b200 import synth
+
+    ps = 16
+    gen = torch.Generator().manual_seed(0)
+    table = torch.zeros((7, 400), dtype=torch.int32)
+    lens = [260, 33, 16, 1, 290, 48]
+    rows = synth.build_paged_table(table, lens, 4096, ps, gen, shared_prefix=40)
+    seen = {}
+    for i, n in enumerate(lens):
+        r = table[rows[i], :n]
+        pos = torch.arange(n)
+        assert torch.equal(r, r[pos - pos % ps] + (pos % ps).int()) and (r[pos - pos % ps] % ps == 0).all()
+        assert r.min() >= ps
+        for pg in set((r // ps).tolist()):
+            seen.setdefault(pg, []).append(i)
+    shared_pages = set((table[rows[0], :32] // ps).tolist())       # 40 // 16 = 2 whole pages
+    assert all(len(v) == 1 or k in shared_pages for k, v in seen.items())
+    assert all(sorted(seen[k]) == [0, 1, 4, 5] for k in shared_pages)  # every request of >= 32 tokens
+
+    pool = sb.MHATokenToKVPool(256, ps, torch.bfloat16, 2, 64, 1, "cpu")
+    assert pool.k_buffer[0].shape == (256 + ps, 2, 64)
+    al = sb.PagedTokenToKVPoolAllocator(256, ps, torch.bfloat16, "cpu", pool)
+    assert al.available_size() == 256 and al.page_size == ps
+    pre, seq = torch.tensor([0, 20]), torch.tensor([35, 41])
+    last = torch.tensor([-1, 5 * ps + 3])                            # position 19 lives at offset 3 of page 5
+    loc = al.alloc_extend(pre, seq, last, 35 + 21)
+    assert loc.numel() == 56 and al.available_size() == 256 - 4 * ps  # 3 pages + 1 fresh page behind the finished one
+    pos = torch.cat([torch.arange(0, 35), torch.arange(20, 41)])
+    assert torch.equal(loc % ps, pos % ps)
+    assert loc[35:35 + 12].tolist() == list(range(5 * ps + 4, 6 * ps))  # the partially filled page is finished first
+    state = al.backup_state()
+    d = al.alloc_decode(torch.tensor([36, 49]), torch.tensor([int(loc[34]), 100]))
+    assert d[0] == loc[34] + 1 and d[1] % ps == 0 and al.available_size() == 256 - 5 * ps
+    al.restore_state(state)
+    assert al.available_size() == 256 - 4 * ps
+    al.free(loc[:32])                                                 # two whole pages come back
+    assert al.available_size() == 256 - 2 * ps
+    assert al.alloc(10 * ps + ps * 20) is None
+    import pytest
+    with pytest.raises(NotImplementedError):
+        sb.MHATokenToKVPool(32, 8, torch.bfloat16, 2, 64, 1, "cpu")

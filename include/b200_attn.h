@@ -235,6 +235,10 @@ int b200_debug_gather(const void* buf, int64_t stride_t_bytes, int32_t row_bytes
                       const void* req_pool_indices, const void* seq_lens, int32_t idx_dtype,
                       const int64_t* out_offsets, int32_t bs, void* out, b200_stream_t stream);
 
+/* Test / bench introspection: how the last b200_attn_decode call of this process fetched whole KV tiles --
+ * 0 row gather only (page size 1), 1 one TMA box per K (V) tile (page >= tile), 2 one TMA box per head and page run. */
+int b200_debug_last_tma_mode(void);
+
 /* Test hook: straightforward one-warp-per-(request, q head) fp32 decode used to
  * cross-check the tiled kernels at sizes the CPU oracle cannot reach. */
 int b200_debug_decode_naive(const b200_decode_params* p, const void* req_pool_indices,

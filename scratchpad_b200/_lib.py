@@ -35,6 +35,7 @@ EXPORTS = (
     "b200_attn_extend",
     "b200_kv_store",
     "b200_rope_kv_store",
+    "b200_debug_last_tma_mode",
     "b200_debug_gather",
     "b200_debug_decode_naive",
 )

@@ -339,7 +339,8 @@ struct DecodeArgs {
   float sm_scale, logit_cap;
   const float* k_scale;
   const float* v_scale;
-  int box_tok;  // paged pools: token rows per TMA box = min(tile tokens, page size)
+  int box_tok;    // paged pools: token rows per TMA box = min(tile tokens, page size)
+  int tma_whole;  // 1: a box is a whole K (V) tile (4-d map over heads and column halves); 0: per-head page runs (3-d map)
 };
 
 // ---- optional per-CTA timeline (build with -DB200_DEC_TRACE; tools/dec_trace.py): %globaltimer at six points
@@ -447,11 +448,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!done && ++spins > (1 << 22)) __trap();  // a copy that never lands must not hang the GPU
   }
 }
-// one [box_tok x ROWB-byte] box of the pool viewed as (head_dim, kv heads, token rows) -> shared memory
+// one [box_tok x 128 B] box of one head of the pool viewed as (head_dim, kv heads, token rows) -> shared memory
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// one whole K (V) tile of the pool viewed as (128-byte column block, token rows, column halves, kv heads)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 
@@ -525,25 +533,37 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
             mbar_arrive_expect_tx(bar, C::STAGE_BYTES);
           }
           __syncwarp();
-          const int bt = a.box_tok, nb = TN / bt;
-          const int nops = 2 * HPC * C::HALVES * nb;
-          for (int op0 = 0; op0 < nops; op0 += 32) {
-            const int op = op0 + lane;
-            const bool live = op < nops;
-            const int j = live ? op % nb : 0;
-            int rest = op / nb;
-            const int half = rest % C::HALVES;
-            rest /= C::HALVES;
-            const int head = rest % HPC, is_v = rest / HPC;
-            const int tokb = j * bt;
-            int sreg = slot_reg[0];
+          const int bt = a.box_tok;
+          if (a.tma_whole) {
+            // page >= tile: the whole K (V) tile is ONE box (all heads of the CTA, both column halves) -- two copies
+            if (lane == 0) {
+              tma_load_4d(sk, tmk, bar, 0, slot_reg[0], 0, h0);  // lane 0 holds the slot id of the tile's first token
+              tma_load_4d(sv, tmv, bar, 0, slot_reg[0], 0, h0);
+            }
+          } else {
+            // page < tile: one box per (K|V, head, column half, page run), spread over the lanes
+            const int nb = TN / bt;
+            const int nops = 2 * HPC * C::HALVES * nb;
+            for (int op0 = 0; op0 < nops; op0 += 32) {
+              const int op = op0 + lane;
+              const bool live = op < nops;
+              const int j = live ? op % nb : 0;
+              int rest = op / nb;
+              const int half = rest % C::HALVES;
+              rest /= C::HALVES;
+              const int head = rest % HPC, is_v = rest / HPC;
+              const int tokb = j * bt;
+              // lanes ask for different page runs: the register holding a lane's slot id is chosen on the reader's side
+              int slot = 0;
 #pragma unroll
-            for (int jj = 1; jj < C::NSLOT; ++jj)
-              if ((tokb >> 5) == jj) sreg = slot_reg[jj];
-            const int slot = __shfl_sync(0xffffffffu, sreg, tokb & 31);
-            if (live) {
-              const uint32_t dst = (is_v ? sv : sk) + tile_chunk_off<CPS, TN>(head, tokb, half * 8);
-              tma_load_3d(dst, is_v ? tmv : tmk, bar, half * (C::ROWB / C::ELT), h0 + head, slot);
+              for (int jj = 0; jj < C::NSLOT; ++jj) {
+                const int cand = __shfl_sync(0xffffffffu, slot_reg[jj], tokb & 31);
+                if ((tokb >> 5) == jj) slot = cand;
+              }
+              if (live) {
+                const uint32_t dst = (is_v ? sv : sk) + tile_chunk_off<CPS, TN>(head, tokb, half * 8);
+                tma_load_3d(dst, is_v ? tmv : tmk, bar, half * (C::ROWB / C::ELT), h0 + head, slot);
+              }
             }
           }
         }
@@ -1026,9 +1046,9 @@ static int device_info(DeviceInfo* di) {
 }
 
 // ---- tensor maps of a paged pool ---------------------------------------------------------------------------------
-// The pool buffer [rows, Hkv, D] (token stride given, so the fused K|V layout works too) as a 3-d tensor
-// (D, Hkv, rows); box = (one 128-byte row segment, 1 head, box_tok token rows), shared-memory side swizzled by
-// 128 bytes (64 for 64-byte segments) -- the layout tile_chunk_off() describes.
+// The pool buffer [rows, Hkv, D] (token stride given, so the fused K|V layout works too) as a 4-d tensor
+// (128-byte column block, token rows, column halves of a head, kv heads); shared-memory side swizzled by 128 bytes
+// (64 for 64-byte segments) -- the layout tile_chunk_off() describes.
 struct PagedMaps {
   CUtensorMap k, v;
 };
@@ -1036,7 +1056,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static int encode_pool_map(CUtensorMap* out, const void* buf, int64_t stride_t_bytes, int64_t rows, int hkv, int d, bool fp8,
-                           int box_tok) {
+                           int box_tok, int hpc, bool whole) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* sym = nullptr;
@@ -1045,17 +1065,34 @@ static int encode_pool_map(CUtensorMap* out, const void* buf, int64_t stride_t_b
     if (!sym || qres != cudaDriverEntryPointSuccess) return B200_ERR_UNSUPPORTED;
     fn = reinterpret_cast<EncodeTiledFn>(sym);
   }
-  const int elt = fp8 ? 1 : 2, seg = d * elt, rowb = seg >= 128 ? 128 : seg;
-  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(hkv), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(seg), static_cast<cuuint64_t>(stride_t_bytes)};
-  const cuuint32_t box[3] = {static_cast<cuuint32_t>(rowb / elt), 1u, static_cast<cuuint32_t>(box_tok)};
-  const cuuint32_t estr[3] = {1u, 1u, 1u};
-  const CUresult r = fn(out, fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(buf), gdim,
-                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const int elt = fp8 ? 1 : 2, seg = d * elt, rowb = seg >= 128 ? 128 : seg, halves = seg / rowb;
+  const CUtensorMapDataType dt = fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r;
+  if (whole) {
+    // (128-byte column block, token rows, column halves, kv heads): a box over all heads of the CTA and both halves
+    // lands as [head][half][token][128 B] -- the tile layout -- so a page that covers the tile is ONE copy
+    const cuuint64_t gdim[4] = {static_cast<cuuint64_t>(rowb / elt), static_cast<cuuint64_t>(rows),
+                                static_cast<cuuint64_t>(halves), static_cast<cuuint64_t>(hkv)};
+    const cuuint64_t gstride[3] = {static_cast<cuuint64_t>(stride_t_bytes), static_cast<cuuint64_t>(rowb),
+                                   static_cast<cuuint64_t>(seg)};
+    const cuuint32_t box[4] = {static_cast<cuuint32_t>(rowb / elt), static_cast<cuuint32_t>(box_tok),
+                               static_cast<cuuint32_t>(halves), static_cast<cuuint32_t>(hpc)};
+    r = fn(out, dt, 4, const_cast<void*>(buf), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    // (head_dim, kv heads, token rows); box = (one 128-byte column block, 1 head, box_tok rows)
+    const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(hkv), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(seg), static_cast<cuuint64_t>(stride_t_bytes)};
+    const cuuint32_t box[3] = {static_cast<cuuint32_t>(rowb / elt), 1u, static_cast<cuuint32_t>(box_tok)};
+    r = fn(out, dt, 3, const_cast<void*>(buf), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   return r == CUDA_SUCCESS ? B200_OK : B200_ERR_INVALID;
 }
+
+static int g_last_tma_mode = 0;  // test / bench introspection: 0 row gather only, 1 whole-tile boxes, 2 per-head page runs
 
 template <class C>
 static int launch_decode_t(const DecodeArgs& a, const PagedMaps* maps, int grid_x, int grid_y, cudaStream_t st, bool query_only,
@@ -1318,16 +1355,29 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
   PagedMaps maps;
   const PagedMaps* mp = nullptr;
   a.box_tok = 0;
+  a.tma_whole = 0;
   if (p->page_size > 1) {
     const int ps = p->page_size;
     if (ps < 16 || ps > 128 || (ps & (ps - 1)) || p->kv_pool_rows <= 0) return B200_ERR_UNSUPPORTED;
     a.box_tok = ps < cfg.tile_tokens ? ps : cfg.tile_tokens;
-    rc = encode_pool_map(&maps.k, p->k_buf, a.k_st_bytes, p->kv_pool_rows, p->hkv, p->d, kc.fp8, a.box_tok);
-    if (rc) return rc;
-    rc = encode_pool_map(&maps.v, p->v_buf, a.v_st_bytes, p->kv_pool_rows, p->hkv, p->dv, kc.fp8, a.box_tok);
-    if (rc) return rc;
+    // one box per tile when the page covers it; the driver may refuse the 4-d description (its strides are not
+    // monotonic) -- then, and for smaller pages, per-head page runs through the 3-d map
+    a.tma_whole = a.box_tok == cfg.tile_tokens;
+    if (a.tma_whole) {
+      rc = encode_pool_map(&maps.k, p->k_buf, a.k_st_bytes, p->kv_pool_rows, p->hkv, p->d, kc.fp8, a.box_tok, kc.hpc, true);
+      if (!rc) rc = encode_pool_map(&maps.v, p->v_buf, a.v_st_bytes, p->kv_pool_rows, p->hkv, p->dv, kc.fp8, a.box_tok, kc.hpc, true);
+      if (rc == B200_ERR_INVALID) a.tma_whole = 0;
+      else if (rc) return rc;
+    }
+    if (!a.tma_whole) {
+      rc = encode_pool_map(&maps.k, p->k_buf, a.k_st_bytes, p->kv_pool_rows, p->hkv, p->d, kc.fp8, a.box_tok, kc.hpc, false);
+      if (rc) return rc;
+      rc = encode_pool_map(&maps.v, p->v_buf, a.v_st_bytes, p->kv_pool_rows, p->hkv, p->dv, kc.fp8, a.box_tok, kc.hpc, false);
+      if (rc) return rc;
+    }
     mp = &maps;
   }
+  g_last_tma_mode = mp ? (a.tma_whole ? 1 : 2) : 0;
   rc = dispatch(kc, a, mp, cfg.grid_ctas, p->hkv / kc.hpc, st, false, nullptr);
   if (rc) return rc;
   if (p->ev_kernel_end) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(p->ev_kernel_end), st));
@@ -1349,6 +1399,8 @@ int b200_debug_dec_trace_read(unsigned long long* host_dst) {
   return cudaMemcpyFromSymbol(host_dst, g_dec_trace, sizeof(g_dec_trace)) == cudaSuccess ? 0 : 1;
 }
 #endif
+
+int b200_debug_last_tma_mode(void) { return g_last_tma_mode; }
 
 int b200_debug_gather(const void* buf, int64_t stride_t_bytes, int32_t row_bytes, const int32_t* req_to_token,
                       int64_t req_to_token_stride, const void* req_pool_indices, const void* seq_lens,

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import attn_oracle as O
-from scratchpad_b200 import CudaB200AttnBackend, ForwardBatch, ForwardMode, synth
+from scratchpad_b200 import CudaB200AttnBackend, ForwardBatch, ForwardMode, _lib, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -45,13 +45,16 @@ def test_paged_decode_vs_oracle_and_token_granular_kernel(hq, hkv, d, kv, page_s
     for i, lens in enumerate(LENS):
         c = G.random_decode_case(hq, hkv, d, lens, seed=100 * hq + 10 * hkv + i + page_size, kv_dtype=kv_dtype,
                                  page_size=page_size)
-        got = _run(c, page_size)[0]
+        got, backend = _run(c, page_size)[:2]
+        # page >= tile: one TMA box per K (V) tile; smaller pages: one box per head and page run
+        assert _lib.load().b200_debug_last_tma_mode() == (1 if page_size >= backend.config.tile_tokens else 2)
         G.assert_close(got, _oracle(c), *tol, what=f"paged {page_size} {hq}/{hkv}/{d}/{kv}/{lens}")
         # the same bytes through the row-gather kernel (page_size 1 over the same buffers): identical arithmetic on
         # identical tiles -> bit-identical output
         cc = dict(c)
         plain = G.run_decode_case(c["q"], c["k_buf"], c["v_buf"], c["req_to_token"], c["req_pool_indices"], c["seq_lens"],
                                   c["sm_scale"], 0.0, kv_dtype, c.get("k_scale"), c.get("v_scale"))[0]
+        assert _lib.load().b200_debug_last_tma_mode() == 0
         assert torch.equal(got.view(torch.int16), plain.view(torch.int16)), f"paged {page_size} != row gather"
 
 
@@ -157,6 +160,5 @@ def test_unsupported_page_sizes_raise():
                       torch.zeros(1, dtype=torch.int64, device="cuda"), req_to_token_pool=runner.req_to_token_pool,
                       token_to_kv_pool=runner.token_to_kv_pool, attn_backend=backend)
     backend.init_forward_metadata(fb)
-    from scratchpad_b200 import _lib
     with pytest.raises(_lib.B200AttnError):
         layer(c["q"].reshape(1, -1).cuda(), None, None, fb, save_kv_cache=False)

@@ -440,7 +440,8 @@ def run_extend_bench(args, rank, world, local_rank, dist):
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tj.get(f"{w.name}/{args.index_mode}/n{world}", {}).get("dram_bytes_per_launch")
+            tkey = f"{w.name}/{args.index_mode}/n{world}" + (f"/ps{args.page_size}" if args.page_size > 1 else "")
+            traffic = tj.get(tkey, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
         line = {
@@ -726,7 +727,8 @@ def main():
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tj.get(f"{w.name}/{args.index_mode}/n{world}", {}).get("dram_bytes_per_launch")
+            tkey = f"{w.name}/{args.index_mode}/n{world}" + (f"/ps{args.page_size}" if args.page_size > 1 else "")
+            traffic = tj.get(tkey, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
         achieved = st["algo_bytes"] / k_avg / 1e9
@@ -738,7 +740,7 @@ def main():
         cfg_out["cascade"] = {"enabled": bool(backend.cascade), "launched": cascade_launched,
                               "shared_prefix_tokens_detected": shared_len,
                               "row_tiles": int(backend.workspace[:64].view(torch.int32)[8].item())}
-        roof_kernel = "decode_mma_kernel"
+        roof_kernel = "decode_paged_kernel" if args.page_size > 1 else "decode_mma_kernel"
         roof_note = None
         if shared_len > 0:
             roof_kernel = "extend_tc_kernel<shared> + decode_mma_kernel"

@@ -427,6 +427,15 @@ __device__ __forceinline__ int tile_chunk_off(int head, int tok, int chunk) {
   else return ((head * TN + tok) * CPS + swz_chunk<CPS>(chunk, tok)) * 16;
 }
 
+// x == y ? a : b as an opaque setp + selp: a chain of these over the elements of a small per-thread array keeps the array in
+// registers (written as C++ selects the compiler may turn the chain into an indexed load from local memory --
+// it did for the 4-register slot-id array of the 128-token tiles, +13-27 % kernel time at the TP8 shards)
+__device__ __forceinline__ int select_eq(int a, int b, int x, int y) {  // x == y ? a : b
+  int d;
+  asm("{\n.reg .pred p;\nsetp.eq.s32 p, %3, %4;\nselp.b32 %0, %1, %2, p;\n}" : "=r"(d) : "r"(a), "r"(b), "r"(x), "r"(y));
+  return d;
+}
+
 // ---- mbarrier / TMA wrappers (paged pools) -------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -556,10 +565,8 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
               // lanes ask for different page runs: the register holding a lane's slot id is chosen on the reader's side
               int slot = 0;
 #pragma unroll
-              for (int jj = 0; jj < C::NSLOT; ++jj) {
-                const int cand = __shfl_sync(0xffffffffu, slot_reg[jj], tokb & 31);
-                if ((tokb >> 5) == jj) slot = cand;
-              }
+              for (int jj = 0; jj < C::NSLOT; ++jj)
+                slot = select_eq(__shfl_sync(0xffffffffu, slot_reg[jj], tokb & 31), slot, tokb >> 5, jj);
               if (live) {
                 const uint32_t dst = (is_v ? sv : sk) + tile_chunk_off<CPS, TN>(head, tokb, half * 8);
                 tma_load_3d(dst, is_v ? tmv : tmk, bar, half * (C::ROWB / C::ELT), h0 + head, slot);
@@ -573,10 +580,17 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
 #pragma unroll
     for (int i = 0; i < C::PASSES; ++i) {
       const int tok = p_tok + i * C::TOK_PER_PASS;
-      int sreg = slot_reg[0];
+      // which slot-id register holds token tok = p_tok + i * TOK_PER_PASS (p_tok < TOK_PER_PASS, powers of two):
+      // known at compile time when a pass spans <= 32 tokens, else one of TOK_PER_PASS / 32 consecutive registers
+      int sreg;
+      if constexpr (C::TOK_PER_PASS <= 32) {
+        sreg = slot_reg[(i * C::TOK_PER_PASS) >> 5];
+      } else {
+        constexpr int R = C::TOK_PER_PASS / 32;
+        sreg = slot_reg[i * R];
 #pragma unroll
-      for (int j = 1; j < C::NSLOT; ++j)
-        if ((tok >> 5) == j) sreg = slot_reg[j];  // predicated select keeps slot_reg in registers
+        for (int r = 1; r < R; ++r) sreg = select_eq(slot_reg[i * R + r], sreg, p_tok >> 5, r);
+      }
       const int slot = __shfl_sync(0xffffffffu, sreg, tok & 31);
       const int nbytes = (tok0 + tok < c.seq_len) ? 16 : 0;
       const uint32_t doff = tile_chunk_off<CPS, TN>(p_head, tok, p_col);
@@ -1360,22 +1374,30 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
     const int ps = p->page_size;
     if (ps < 16 || ps > 128 || (ps & (ps - 1)) || p->kv_pool_rows <= 0) return B200_ERR_UNSUPPORTED;
     a.box_tok = ps < cfg.tile_tokens ? ps : cfg.tile_tokens;
+    // Measured: a whole-tile box (16 KB) beats the row gather by 2-5 %, 8 KB page runs match it, 2 KB
+    // page runs lose 5-10 % to it (per-copy cost of the TMA unit).  Page runs below 4 KB therefore stay on the row
+    // gather, which is still correct on a paged table (one slot id per token) and sees the pages' DRAM locality.
+    const int rowb = p->d * elt >= 128 ? 128 : p->d * elt;
+    const bool use_tma = a.box_tok == cfg.tile_tokens || a.box_tok * rowb >= 4096;
     // one box per tile when the page covers it; the driver may refuse the 4-d description (its strides are not
     // monotonic) -- then, and for smaller pages, per-head page runs through the 3-d map
     a.tma_whole = a.box_tok == cfg.tile_tokens;
-    if (a.tma_whole) {
+    if (!use_tma) {
+      a.box_tok = 0;
+      a.tma_whole = 0;
+    } else if (a.tma_whole) {
       rc = encode_pool_map(&maps.k, p->k_buf, a.k_st_bytes, p->kv_pool_rows, p->hkv, p->d, kc.fp8, a.box_tok, kc.hpc, true);
       if (!rc) rc = encode_pool_map(&maps.v, p->v_buf, a.v_st_bytes, p->kv_pool_rows, p->hkv, p->dv, kc.fp8, a.box_tok, kc.hpc, true);
       if (rc == B200_ERR_INVALID) a.tma_whole = 0;
       else if (rc) return rc;
     }
-    if (!a.tma_whole) {
+    if (use_tma && !a.tma_whole) {
       rc = encode_pool_map(&maps.k, p->k_buf, a.k_st_bytes, p->kv_pool_rows, p->hkv, p->d, kc.fp8, a.box_tok, kc.hpc, false);
       if (rc) return rc;
       rc = encode_pool_map(&maps.v, p->v_buf, a.v_st_bytes, p->kv_pool_rows, p->hkv, p->dv, kc.fp8, a.box_tok, kc.hpc, false);
       if (rc) return rc;
     }
-    mp = &maps;
+    if (use_tma) mp = &maps;
   }
   g_last_tma_mode = mp ? (a.tma_whole ? 1 : 2) : 0;
   rc = dispatch(kc, a, mp, cfg.grid_ctas, p->hkv / kc.hpc, st, false, nullptr);

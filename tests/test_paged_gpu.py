@@ -46,8 +46,11 @@ def test_paged_decode_vs_oracle_and_token_granular_kernel(hq, hkv, d, kv, page_s
         c = G.random_decode_case(hq, hkv, d, lens, seed=100 * hq + 10 * hkv + i + page_size, kv_dtype=kv_dtype,
                                  page_size=page_size)
         got, backend = _run(c, page_size)[:2]
-        # page >= tile: one TMA box per K (V) tile; smaller pages: one box per head and page run
-        assert _lib.load().b200_debug_last_tma_mode() == (1 if page_size >= backend.config.tile_tokens else 2)
+        # page >= tile: one TMA box per K (V) tile; smaller pages: one box per head and page run when a run is
+        # >= 4 KB per head, else the row gather (over the paged table)
+        rowb = min(128, d * (2 if kv == "bf16" else 1))
+        want = 1 if page_size >= backend.config.tile_tokens else (2 if page_size * rowb >= 4096 else 0)
+        assert _lib.load().b200_debug_last_tma_mode() == want
         G.assert_close(got, _oracle(c), *tol, what=f"paged {page_size} {hq}/{hkv}/{d}/{kv}/{lens}")
         # the same bytes through the row-gather kernel (page_size 1 over the same buffers): identical arithmetic on
         # identical tiles -> bit-identical output

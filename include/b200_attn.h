@@ -239,6 +239,14 @@ int b200_debug_gather(const void* buf, int64_t stride_t_bytes, int32_t row_bytes
  * 0 row gather only (page size 1), 1 one TMA box per K (V) tile (page >= tile), 2 one TMA box per head and page run. */
 int b200_debug_last_tma_mode(void);
 
+/* Debug check of the paged-table contract (b200_decode_params.page_size): writes to *violations (device int32)
+ * the number of positions t < seq_lens[i] with req_to_token[r_i, t] != page_start + t % page_size, page_start =
+ * req_to_token[r_i, t - t % page_size] a multiple of page_size.  CudaB200AttnBackend runs it once per forward batch
+ * when B200_CHECK_PAGES=1 (it synchronises to read the count; never on the normal path). */
+int b200_debug_check_paged(const int32_t* req_to_token, int64_t req_to_token_stride,
+                           const void* req_pool_indices, const void* seq_lens, int32_t idx_dtype,
+                           int32_t bs, int32_t page_size, int32_t* violations, b200_stream_t stream);
+
 /* Test hook: straightforward one-warp-per-(request, q head) fp32 decode used to
  * cross-check the tiled kernels at sizes the CPU oracle cannot reach. */
 int b200_debug_decode_naive(const b200_decode_params* p, const void* req_pool_indices,

@@ -36,6 +36,7 @@ EXPORTS = (
     "b200_kv_store",
     "b200_rope_kv_store",
     "b200_debug_last_tma_mode",
+    "b200_debug_check_paged",
     "b200_debug_gather",
     "b200_debug_decode_naive",
 )
@@ -163,6 +164,7 @@ def load() -> C.CDLL:
     lib.b200_attn_extend.argtypes = [C.POINTER(ExtendParams), vp]
     lib.b200_kv_store.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp, i64, i64, i64, i64, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.b200_rope_kv_store.argtypes = [C.POINTER(RopeStoreParams), vp]
+    lib.b200_debug_check_paged.argtypes = [vp, i64, vp, vp, i32, i32, i32, vp, vp]
     lib.b200_debug_gather.argtypes = [vp, i64, i32, vp, i64, vp, vp, i32, vp, i32, vp, vp]
     lib.b200_debug_decode_naive.argtypes = [C.POINTER(DecodeParams), vp, vp, i32, vp]
     for name in EXPORTS[3:]:

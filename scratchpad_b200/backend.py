@@ -20,6 +20,7 @@ goes through ``libb200attn.so`` and raises if it is missing.
 
 from __future__ import annotations
 
+import os
 from abc import ABC, abstractmethod
 from typing import Optional
 
@@ -107,6 +108,7 @@ class CudaB200AttnBackend(AttentionBackend):
         if model_runner.dtype != torch.bfloat16:
             raise NotImplementedError("cuda_b200 backend: model dtype must be bfloat16")
         self.cuda_graph_max_seq_len = cfg.context_len
+        self._check_pages = os.environ.get("B200_CHECK_PAGES", "0") == "1"
         self.max_bs = 0
         self.workspace = None
         self.config = None
@@ -141,6 +143,23 @@ class CudaB200AttnBackend(AttentionBackend):
         )
         _lib.check(rc, "b200_attn_plan")
         self._planned_for = bs
+        if self._check_pages and int(getattr(self.token_to_kv_pool, "page_size", 1)) > 1:
+            self._verify_paged_table(bs, req_pool_indices, seq_lens)
+
+    def _verify_paged_table(self, bs: int, req_pool_indices: torch.Tensor, seq_lens: torch.Tensor) -> None:
+        """B200_CHECK_PAGES=1 only (synchronises): the paged decode path trusts the allocator's invariant
+        slot(t) = page_start + t % page_size; a table that breaks it would be read wrongly, so fail loudly."""
+        r2t = self.req_to_token_pool.req_to_token
+        bad = torch.zeros(1, dtype=torch.int32, device=r2t.device)
+        rc = self.lib.b200_debug_check_paged(r2t.data_ptr(), r2t.stride(0), req_pool_indices.data_ptr(),
+                                             seq_lens.data_ptr(), _idx_code(req_pool_indices), bs,
+                                             int(self.token_to_kv_pool.page_size), bad.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "b200_debug_check_paged")
+        n = int(bad.item())
+        if n:
+            raise RuntimeError(f"cuda_b200 backend: req_to_token breaks the page_size={self.token_to_kv_pool.page_size} "
+                               f"layout contract at {n} positions (slot != page_start + position % page_size)")
 
     # ---- AttentionBackend surface -------------------------------------------
     def init_forward_metadata(self, forward_batch):

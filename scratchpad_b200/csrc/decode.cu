@@ -976,6 +976,22 @@ __global__ void gather_kernel(const uint8_t* __restrict__ buf, int64_t stride_t_
   }
 }
 
+// paged-table contract check: counts positions t < seq_len whose slot is not page_start + t % page_size with
+// page_start = slot of position t - t % page_size a multiple of page_size
+__global__ void check_paged_kernel(const int32_t* __restrict__ r2t, int64_t r2t_stride, const void* __restrict__ req,
+                                   const void* __restrict__ seq, int idx64, int page_size, int* __restrict__ violations) {
+  const int b = blockIdx.x;
+  const int64_t n = load_idx(seq, idx64, b);
+  const int32_t* row = r2t + load_idx(req, idx64, b) * r2t_stride;
+  int bad = 0;
+  for (int64_t t = threadIdx.x; t < n; t += blockDim.x) {
+    const int off = static_cast<int>(t % page_size);
+    const int32_t first = row[t - off];
+    bad += (first % page_size != 0) || (row[t] != first + off);
+  }
+  if (bad) atomicAdd(violations, bad);
+}
+
 // one warp per (request, q head); fp32 everywhere; the obviously-correct twin
 __global__ void __launch_bounds__(32) naive_decode_kernel(const b200_decode_params p, const void* __restrict__ req,
                                                           const void* __restrict__ seq, int idx64) {
@@ -1423,6 +1439,18 @@ int b200_debug_dec_trace_read(unsigned long long* host_dst) {
 #endif
 
 int b200_debug_last_tma_mode(void) { return g_last_tma_mode; }
+
+int b200_debug_check_paged(const int32_t* req_to_token, int64_t req_to_token_stride, const void* req_pool_indices,
+                           const void* seq_lens, int32_t idx_dtype, int32_t bs, int32_t page_size, int32_t* violations,
+                           b200_stream_t stream) {
+  if (!req_to_token || !req_pool_indices || !seq_lens || !violations || bs <= 0 || page_size <= 0) return B200_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  B200_CUDA_TRY(cudaMemsetAsync(violations, 0, sizeof(int32_t), st));
+  check_paged_kernel<<<bs, 256, 0, st>>>(req_to_token, req_to_token_stride, req_pool_indices, seq_lens,
+                                         idx_dtype == B200_IDX_I64, page_size, violations);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
 
 int b200_debug_gather(const void* buf, int64_t stride_t_bytes, int32_t row_bytes, const int32_t* req_to_token,
                       int64_t req_to_token_stride, const void* req_pool_indices, const void* seq_lens,

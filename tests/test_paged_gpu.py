@@ -165,3 +165,16 @@ def test_unsupported_page_sizes_raise():
     backend.init_forward_metadata(fb)
     with pytest.raises(_lib.B200AttnError):
         layer(c["q"].reshape(1, -1).cuda(), None, None, fb, save_kv_cache=False)
+
+
+def test_paged_contract_check_catches_a_token_granular_table(monkeypatch):
+    """B200_CHECK_PAGES=1: a table that is not page-structured (random token slots) is rejected at metadata time
+    instead of being read through page copies; a well-formed one passes."""
+    monkeypatch.setenv("B200_CHECK_PAGES", "1")
+    good = G.random_decode_case(8, 2, 64, [100, 33], seed=2, page_size=16)
+    _run(good, 16)
+    bad = G.random_decode_case(8, 2, 64, [100, 33], seed=2)             # token-granular random slots ...
+    pad = torch.zeros((15,) + tuple(bad["k_buf"].shape[1:]), dtype=bad["k_buf"].dtype)
+    bad["k_buf"], bad["v_buf"] = torch.cat([bad["k_buf"], pad]), torch.cat([bad["v_buf"], pad])
+    with pytest.raises(RuntimeError, match="layout contract"):
+        _run(bad, 16)                                                   # ... declared as a 16-token-page pool

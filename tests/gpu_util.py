@@ -102,16 +102,20 @@ def random_decode_case(hq, hkv, d, seq_lens, seed, kv_dtype=torch.bfloat16, shar
 
 
 def random_extend_case(hq, hkv, d, prefix_lens, extend_lens, seed, kv_dtype=torch.bfloat16, per_head=True,
-                       extra_rows=2, mode="random"):
+                       extra_rows=2, mode="random", page_size=1):
     """CPU tensors for one extend case: pool holding the prefixes (quantised for fp8), new q/k/v in bf16."""
     gen = torch.Generator().manual_seed(seed)
     seq_lens = [p + e for p, e in zip(prefix_lens, extend_lens)]
-    pool = sum(seq_lens) + 19
     b = len(seq_lens)
     r2t = torch.zeros((b + extra_rows, max(max(seq_lens), 1) + 4), dtype=torch.int32)
-    rpi = synth.build_page_table(r2t, seq_lens, pool, gen, mode)
-    kf = torch.randn((pool + 1, hkv, d), generator=gen).to(torch.bfloat16)
-    vf = torch.randn((pool + 1, hkv, d), generator=gen).to(torch.bfloat16)
+    if page_size > 1:
+        pool = (sum((n + page_size - 1) // page_size for n in seq_lens) + 3) * page_size
+        rpi = synth.build_paged_table(r2t, seq_lens, pool, page_size, gen)
+    else:
+        pool = sum(seq_lens) + 19
+        rpi = synth.build_page_table(r2t, seq_lens, pool, gen, mode)
+    kf = torch.randn((pool + page_size, hkv, d), generator=gen).to(torch.bfloat16)
+    vf = torch.randn((pool + page_size, hkv, d), generator=gen).to(torch.bfloat16)
     t = sum(extend_lens)
     q = torch.randn((t, hq, d), generator=gen).to(torch.bfloat16)
     k_new = torch.randn((t, hkv, d), generator=gen).to(torch.bfloat16)
@@ -133,7 +137,7 @@ def random_extend_case(hq, hkv, d, prefix_lens, extend_lens, seed, kv_dtype=torc
                 seq_lens=torch.tensor(seq_lens, dtype=torch.int64), extend_seq_lens=el,
                 extend_prefix_lens=torch.tensor(prefix_lens, dtype=torch.int32),
                 extend_start_loc=compute_extend_start_loc(el), out_cache_loc=out_loc, sm_scale=d ** -0.5,
-                k_scale=ks, v_scale=vs, kv_dtype=kv_dtype)
+                k_scale=ks, v_scale=vs, kv_dtype=kv_dtype, page_size=page_size)
 
 
 def run_extend_case(c, logit_cap=0.0, idx_dtype=torch.int64, save_kv_cache=True, qkv_slices=True,
@@ -143,7 +147,7 @@ def run_extend_case(c, logit_cap=0.0, idx_dtype=torch.int64, save_kv_cache=True,
     hkv = c["k_buf"].shape[1]
     kv_dtype = c.get("kv_dtype", torch.bfloat16)
     runner = make_runner_from_case(c["k_buf"], c["v_buf"], c["req_to_token"], kv_dtype, c.get("k_scale"),
-                                   c.get("v_scale"), tp_hq=hq)
+                                   c.get("v_scale"), tp_hq=hq, page_size=c.get("page_size", 1))
     backend = CudaB200AttnBackend(runner, force_path=force_path)
     layer = synth.make_layer(runner, 0, logit_cap)
     layer.scaling = c["sm_scale"]

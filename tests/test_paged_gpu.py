@@ -178,3 +178,21 @@ def test_paged_contract_check_catches_a_token_granular_table(monkeypatch):
     bad["k_buf"], bad["v_buf"] = torch.cat([bad["k_buf"], pad]), torch.cat([bad["v_buf"], pad])
     with pytest.raises(RuntimeError, match="layout contract"):
         _run(bad, 16)                                                   # ... declared as a 16-token-page pool
+
+
+@pytest.mark.parametrize("kv", ["bf16", "fp8"])
+@pytest.mark.parametrize("force_path", [_lib.PATH_MMA, _lib.PATH_TC])
+def test_extend_over_a_paged_pool(kv, force_path):
+    """The extend kernels gather the cached prefix by token slot and the KV store scatters by out_cache_loc, so a
+    paged table needs nothing new from them: same oracle, pool rows written at the paged slots."""
+    kv_dtype = torch.bfloat16 if kv == "bf16" else torch.float8_e4m3fn
+    tol = (G.BF16_ABS, G.BF16_REL) if kv == "bf16" else (G.FP8_ABS, G.FP8_REL)
+    c = G.random_extend_case(8, 2, 128, [130, 0, 77, 256], [140, 150, 3, 129], seed=61, kv_dtype=kv_dtype, page_size=16)
+    got, runner = G.run_extend_case(c, force_path=force_path)
+    ref = O.extend_ref(c["q"], c["k_new"], c["v_new"], c["k_buf"], c["v_buf"], c["req_to_token"], c["req_pool_indices"],
+                       c["seq_lens"], c["extend_seq_lens"], c["extend_start_loc"], c["sm_scale"], 0.0, kv_dtype,
+                       c["k_scale"], c["v_scale"])
+    G.assert_close(got, ref, *tol, what=f"paged extend {kv}")
+    kb, vb = c["k_buf"].clone(), c["v_buf"].clone()
+    O.set_kv_buffer_ref(kb, vb, c["out_cache_loc"], c["k_new"].clone(), c["v_new"].clone(), kv_dtype, c["k_scale"], c["v_scale"])
+    assert torch.equal(runner.token_to_kv_pool.k_buffer[0].cpu(), kb) and torch.equal(runner.token_to_kv_pool.v_buffer[0].cpu(), vb)

@@ -56,7 +56,7 @@ def parse_args():
                     help="decode only: include the model's rotary embedding in the layer-call -- 'separate' = the "
                          "reference's sequence rotary_emb(positions, q, k) then attention (llama.py:149-152), 'fused' = "
                          "one b200_rope_kv_store launch doing the rotation and the KV write (SURVEY 8f #1)")
-    ap.add_argument("--page-size", type=int, default=1, choices=[1, 16, 32, 64, 128],
+    ap.add_argument("--page-size", type=int, default=1, choices=[-1, 1, 16, 32, 64, 128],
                     help="decode only: KV pool page size.  1 = the reference's token-granular pool (default, the headline "
                          "configuration); > 1 = paged pool, random pages, whole tiles fetched by TMA (SURVEY 8f #4)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -203,7 +203,7 @@ def build_state(args, rank, world):
     shared = w.shared_prefix
     need = shared + sum(n - shared if shared and n >= shared else n for n in seq_lens)
     pool_tokens = need + 64
-    ps = args.page_size
+    ps = max(args.page_size, 1)
     if ps > 1:
         pool_tokens = (shared // ps + sum((n + ps - 1) // ps for n in seq_lens) + 4) * ps
     kv_elt = 2 if w.kv_dtype == torch.bfloat16 else 1
@@ -217,7 +217,7 @@ def build_state(args, rank, world):
                                      kv_dtype=w.kv_dtype, device=dev, fused_kv=fused, page_size=ps)
     fill_pool(runner.token_to_kv_pool, 1000 + rank % max(world, 1))
     cascade = args.cascade == "on" or (args.cascade == "auto" and w.shared_prefix > 0)
-    backend = CudaB200AttnBackend(runner, cascade=cascade)
+    backend = CudaB200AttnBackend(runner, cascade=cascade, tma_contiguous_runs=args.page_size == -1)
     fb = synth.make_decode_batch(runner, seq_lens, gen, mode=args.index_mode, shared_prefix=shared,
                                  idx_dtype=torch.int64, backend=backend)
     lay = [synth.make_layer(runner, i) for i in range(layers)]
@@ -440,7 +440,7 @@ def run_extend_bench(args, rank, world, local_rank, dist):
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            tkey = f"{w.name}/{args.index_mode}/n{world}" + (f"/ps{args.page_size}" if args.page_size > 1 else "")
+            tkey = f"{w.name}/{args.index_mode}/n{world}" + (f"/ps{args.page_size}" if args.page_size != 1 else "")
             traffic = tj.get(tkey, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
@@ -727,7 +727,7 @@ def main():
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            tkey = f"{w.name}/{args.index_mode}/n{world}" + (f"/ps{args.page_size}" if args.page_size > 1 else "")
+            tkey = f"{w.name}/{args.index_mode}/n{world}" + (f"/ps{args.page_size}" if args.page_size != 1 else "")
             traffic = tj.get(tkey, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
@@ -740,7 +740,7 @@ def main():
         cfg_out["cascade"] = {"enabled": bool(backend.cascade), "launched": cascade_launched,
                               "shared_prefix_tokens_detected": shared_len,
                               "row_tiles": int(backend.workspace[:64].view(torch.int32)[8].item())}
-        roof_kernel = "decode_paged_kernel" if args.page_size > 1 else "decode_mma_kernel"
+        roof_kernel = "decode_paged_kernel" if backend.lib.b200_debug_last_tma_mode() else "decode_mma_kernel"
         roof_note = None
         if shared_len > 0:
             roof_kernel = "extend_tc_kernel<shared> + decode_mma_kernel"

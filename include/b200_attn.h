@@ -42,6 +42,8 @@ extern "C" {
 /* kv_dtype */
 #define B200_KV_BF16 0
 #define B200_KV_FP8_E4M3 1
+/* b200_decode_params.page_size */
+#define B200_PAGE_AUTO (-1)
 /* idx_dtype */
 #define B200_IDX_I32 0
 #define B200_IDX_I64 1
@@ -99,12 +101,15 @@ typedef struct b200_decode_params {
   void* ev_kernel_begin;    /* optional cudaEvent_t pair recorded on `stream` around the */
   void* ev_kernel_end;      /* split-KV kernel alone (bench.py roofline timing); NULL = off */
   int32_t cascade;          /* must equal the `cascade` b200_attn_plan was called with for this batch */
-  int32_t page_size;        /* 0 / 1: token-granular pool (the reference today, model_runner.py:431-432).
-                             * 16, 32, 64 or 128: paged pool -- the caller guarantees, for every request row r and
-                             * position t < seq_len, req_to_token[r, t] = req_to_token[r, t - t % page_size] +
-                             * t % page_size with that page start a multiple of page_size (what a paged allocator
-                             * yields: schedule_batch.py:754-828, radix_cache.py:57-66 page-aligned matching).
-                             * Whole KV tiles are then fetched by TMA box copies, one per page run. */
+  int32_t page_size;        /* 0 / 1: token-granular pool, row gather only (the reference today, model_runner.py:431-432).
+                             * 16, 32, 64 or 128: paged pool -- for every request row r and position t < seq_len,
+                             * req_to_token[r, t] = req_to_token[r, t - t % page_size] + t % page_size (what a paged
+                             * allocator yields: schedule_batch.py:754-828, radix_cache.py:57-66 page-aligned matching).
+                             * KV tiles whose slot ids really are consecutive per page run are fetched by TMA box
+                             * copies; the kernel checks that per tile on device and takes the row gather for any
+                             * other tile, so the value is a performance hint, never a correctness contract.
+                             * B200_PAGE_AUTO: token-granular pool, TMA for every tile whose slots happen to be
+                             * consecutive (an unfragmented allocator hands out runs, memory/pool.py:240-253). */
   int64_t kv_pool_rows;     /* paged only: token rows of k_buf / v_buf (bounds of the tensor maps) */
 } b200_decode_params;
 

@@ -22,6 +22,7 @@ KV_BF16, KV_FP8_E4M3 = 0, 1
 IDX_I32, IDX_I64 = 0, 1
 PATH_AUTO, PATH_MMA, PATH_TC = -1, 0, 1
 CACHE_BF16, CACHE_F32 = 0, 1
+PAGE_AUTO = -1
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_NOT_PLANNED = 0, 1, 2, 3, 4
 

@@ -80,7 +80,8 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 class CudaB200AttnBackend(AttentionBackend):
-    def __init__(self, model_runner, force_path: int = _lib.PATH_AUTO, cascade: Optional[bool] = None):
+    def __init__(self, model_runner, force_path: int = _lib.PATH_AUTO, cascade: Optional[bool] = None,
+                 tma_contiguous_runs: Optional[bool] = None):
         super().__init__()
         self.lib = _lib.load()  # raises when the extension is not built
         cfg = model_runner.model_config
@@ -103,6 +104,9 @@ class CudaB200AttnBackend(AttentionBackend):
         if cascade is None:
             cascade = bool(getattr(model_runner.server_args, "b200_shared_prefix_cascade", True))
         self.cascade = 1 if cascade else 0
+        if tma_contiguous_runs is None:
+            tma_contiguous_runs = bool(getattr(model_runner.server_args, "b200_tma_contiguous_runs", False))
+        self.tma_contiguous_runs = bool(tma_contiguous_runs)
         if getattr(model_runner, "sliding_window_size", None) not in (None, -1):
             raise NotImplementedError("cuda_b200 backend: sliding-window attention is not supported")
         if model_runner.dtype != torch.bfloat16:
@@ -201,6 +205,14 @@ class CudaB200AttnBackend(AttentionBackend):
     def _scales(self, layer):
         return self.token_to_kv_pool.get_kv_scales(layer.layer_id)
 
+    def _page_hint(self, pool) -> int:
+        """b200_decode_params.page_size: the pool's page size, or PAGE_AUTO for a token-granular pool when
+        ``tma_contiguous_runs`` is on (tiles whose slots happen to be consecutive are then fetched by TMA)."""
+        ps = int(getattr(pool, "page_size", 1))
+        if ps > 1:
+            return ps
+        return _lib.PAGE_AUTO if self.tma_contiguous_runs else 1
+
     def _logit_cap(self, layer) -> float:
         cap = getattr(layer, "logit_cap", 0.0)
         return float(cap) if cap else 0.0
@@ -249,7 +261,7 @@ class CudaB200AttnBackend(AttentionBackend):
             k_scale=_ptr(ks), v_scale=_ptr(vs),
             workspace=self.workspace.data_ptr(), workspace_bytes=self.workspace.numel(),
             max_bs=self.max_bs, force_path=self.force_path, cascade=self.cascade,
-            page_size=int(getattr(pool, "page_size", 1)), kv_pool_rows=kb.shape[0],
+            page_size=self._page_hint(pool), kv_pool_rows=kb.shape[0],
         )
         if self.profile_events is not None:
             p.ev_kernel_begin, p.ev_kernel_end = self.profile_events

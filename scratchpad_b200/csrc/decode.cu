@@ -483,7 +483,8 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
   const int h0 = blockIdx.y * HPC;  // first kv head of this CTA
   DEC_TRACE(0);
   uint32_t smem_base = smem_u32(smem);
-  uint32_t bar_base = 0, phases = 0;  // paged: one "tile has landed" mbarrier per stage; parity bit per stage
+  uint32_t bar_base = 0, phases = 0, tma_bits = 0;  // paged: one "tile has landed" mbarrier per stage; its parity bit;
+                                                   // bit s of tma_bits: stage s was filled by TMA
   if constexpr (PAGED) {
     smem_base = (smem_base + 1023u) & ~1023u;  // TMA's swizzle pattern is a function of the address
     bar_base = smem_base + kStages * C::STAGE_BYTES;
@@ -530,11 +531,29 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
     const uint32_t sk = smem_base + stage * C::STAGE_BYTES;
     const uint32_t sv = sk + C::TILE_BYTES;
     if constexpr (PAGED) {
-      // A tile that lies wholly inside the sequence is page-aligned runs of consecutive slots (slot = page * page_size
-      // + offset, request position t sits at offset t % page_size): one TMA box per (K|V, head, column half, page
-      // run), issued by the lanes of warp 0, all signalling the stage's mbarrier.  The ragged last tile of a request
-      // takes the row gather below (it zero-fills rows past the end, which the softmax masking relies on for V).
-      if (tok0 + TN <= c.seq_len) {
+      // A tile that lies wholly inside the sequence and whose slots are consecutive within every run of box_tok
+      // tokens (what a paged allocator yields: slot = page * page_size + offset, request position t at offset
+      // t % page_size; or simply an unfragmented token-granular allocator) is fetched by TMA: one box per (K|V, head,
+      // column half, run) -- or one per K|V when the run covers the tile -- issued by warp 0, all signalling the
+      // stage's mbarrier.  The check is made HERE, on the slot ids every warp holds anyway (one shuffle, one vote), so
+      // the caller's page-size hint can cost speed but never correctness; any other tile -- the ragged last tile of
+      // a request included -- takes the row gather below (which zero-fills rows past the end; the PV product relies
+      // on that).  The decision is remembered per stage for the consumer side.
+      const int bt = a.box_tok;
+      bool ok = tok0 + TN <= c.seq_len;
+#pragma unroll
+      for (int j = 0; j < C::NSLOT; ++j) {
+        int prev = __shfl_up_sync(0xffffffffu, slot_reg[j], 1);
+        if (j > 0) {
+          const int carry = __shfl_sync(0xffffffffu, slot_reg[j - 1], 31);
+          if (lane == 0) prev = carry;
+        }
+        const int t = j * 32 + lane;
+        ok = ok && (t >= TN || (t & (bt - 1)) == 0 || slot_reg[j] == prev + 1);
+      }
+      const bool by_tma = __all_sync(0xffffffffu, ok);
+      tma_bits = by_tma ? (tma_bits | (1u << stage)) : (tma_bits & ~(1u << stage));
+      if (by_tma) {
         if (warp == 0) {
           const uint32_t bar = bar_base + 8 * stage;
           if (lane == 0) {
@@ -542,7 +561,6 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
             mbar_arrive_expect_tx(bar, C::STAGE_BYTES);
           }
           __syncwarp();
-          const int bt = a.box_tok;
           if (a.tma_whole) {
             // page >= tile: the whole K (V) tile is ONE box (all heads of the CTA, both column halves) -- two copies
             if (lane == 0) {
@@ -804,7 +822,7 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
   while (cursor_valid(cc)) {
     cp_async_wait<kStages - 2>();
     if constexpr (PAGED) {
-      if ((cc.gt - cc.b_begin) * TN + TN <= cc.seq_len) {  // same predicate the producer used: this tile came by TMA
+      if ((tma_bits >> stage) & 1u) {  // the producer side fetched this stage's tile by TMA
         mbar_wait(bar_base + 8 * stage, (phases >> stage) & 1u);
         phases ^= 1u << stage;
       }
@@ -1381,13 +1399,15 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
     if (rc) return rc;
   }
   // page_size > 1: slots of a page are consecutive and request position t sits at offset
-  // t % page_size of its page, so whole tiles are fetched with TMA box copies, one per page run
+  // t % page_size of its page, so whole tiles are fetched with TMA box copies, one per page run (the kernel checks
+  // every tile's slot ids before it trusts that: a wrong page_size costs speed, not correctness)
   PagedMaps maps;
   const PagedMaps* mp = nullptr;
   a.box_tok = 0;
   a.tma_whole = 0;
-  if (p->page_size > 1) {
-    const int ps = p->page_size;
+  if (p->page_size > 1 || p->page_size == B200_PAGE_AUTO) {
+    // B200_PAGE_AUTO: a token-granular pool whose allocator often hands out consecutive slots -- try whole-tile boxes
+    const int ps = p->page_size == B200_PAGE_AUTO ? cfg.tile_tokens : p->page_size;
     if (ps < 16 || ps > 128 || (ps & (ps - 1)) || p->kv_pool_rows <= 0) return B200_ERR_UNSUPPORTED;
     a.box_tok = ps < cfg.tile_tokens ? ps : cfg.tile_tokens;
     // Measured: a whole-tile box (16 KB) beats the row gather by 2-5 %, 8 KB page runs match it, 2 KB

@@ -43,10 +43,10 @@ def make_runner_from_case(k_buf, v_buf, r2t, kv_dtype, k_scale=None, v_scale=Non
 
 def run_decode_case(q, k_buf, v_buf, r2t, rpi, sl, sm_scale, logit_cap=0.0, kv_dtype=torch.bfloat16,
                     k_scale=None, v_scale=None, idx_dtype=torch.int64, q_slice_of_qkv=False, force_path=-1,
-                    cascade=None, page_size=1):
+                    cascade=None, page_size=1, tma_contiguous_runs=None):
     b, hq, d = q.shape
     runner = make_runner_from_case(k_buf, v_buf, r2t, kv_dtype, k_scale, v_scale, tp_hq=hq, page_size=page_size)
-    backend = CudaB200AttnBackend(runner, force_path=force_path, cascade=cascade)
+    backend = CudaB200AttnBackend(runner, force_path=force_path, cascade=cascade, tma_contiguous_runs=tma_contiguous_runs)
     layer = synth.make_layer(runner, 0, logit_cap)
     layer.scaling = sm_scale
     fb = ForwardBatch(forward_mode=ForwardMode.DECODE, batch_size=b,

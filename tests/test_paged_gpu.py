@@ -196,3 +196,39 @@ def test_extend_over_a_paged_pool(kv, force_path):
     kb, vb = c["k_buf"].clone(), c["v_buf"].clone()
     O.set_kv_buffer_ref(kb, vb, c["out_cache_loc"], c["k_new"].clone(), c["v_new"].clone(), kv_dtype, c["k_scale"], c["v_scale"])
     assert torch.equal(runner.token_to_kv_pool.k_buffer[0].cpu(), kb) and torch.equal(runner.token_to_kv_pool.v_buffer[0].cpu(), vb)
+
+
+@pytest.mark.parametrize("kv", ["bf16", "fp8"])
+def test_wrong_page_hint_costs_speed_not_correctness(kv):
+    """The kernel checks every tile's slot ids before fetching it as page runs: a token-granular table with random
+    slots declared as a 16-token-page pool is still read correctly (every tile falls back to the row gather), and so
+    is a table where only some runs are consecutive."""
+    kv_dtype = torch.bfloat16 if kv == "bf16" else torch.float8_e4m3fn
+    tol = (G.BF16_ABS, G.BF16_REL) if kv == "bf16" else (G.FP8_ABS, G.FP8_REL)
+    c = G.random_decode_case(32, 8, 64, [100, 333, 16, 64, 257], seed=12, kv_dtype=kv_dtype)   # random token slots
+    pad = torch.zeros((15,) + tuple(c["k_buf"].shape[1:]), dtype=c["k_buf"].dtype)
+    c["k_buf"], c["v_buf"] = torch.cat([c["k_buf"], pad]), torch.cat([c["v_buf"], pad])
+    G.assert_close(_run(c, 16)[0], _oracle(c), *tol, what="random slots, page hint 16")
+    # a paged table with a few entries swapped inside pages: those tiles must take the row gather, the rest TMA
+    c = G.random_decode_case(32, 8, 64, [100, 333, 16, 64, 257], seed=13, kv_dtype=kv_dtype, page_size=16)
+    row = int(c["req_pool_indices"][1])
+    for t in (5, 40, 41, 200, 319):
+        a, b = c["req_to_token"][row, t].item(), c["req_to_token"][row, t + 1].item()
+        c["req_to_token"][row, t], c["req_to_token"][row, t + 1] = b, a
+    G.assert_close(_run(c, 16)[0], _oracle(c), *tol, what="paged table with swapped entries")
+
+
+def test_token_granular_pool_with_consecutive_slots_uses_tma():
+    """PAGE_AUTO (tma_contiguous_runs=True): a page_size=1 pool whose allocator handed out consecutive runs
+    (pool.py:240-253 on an unfragmented free list) gets whole-tile TMA copies; output identical to the row gather."""
+    gen = torch.Generator().manual_seed(3)
+    lens = [int(x) for x in torch.randint(1, 900, (24,), generator=gen)]
+    c = G.random_decode_case(32, 8, 128, lens, seed=14, mode="contiguous")
+    got = _run(c, 1, tma_contiguous_runs=True)[0]
+    assert _lib.load().b200_debug_last_tma_mode() == 1
+    G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, what="auto TMA on consecutive slots")
+    plain = _run(c, 1)[0]
+    assert _lib.load().b200_debug_last_tma_mode() == 0
+    assert torch.equal(got.view(torch.int16), plain.view(torch.int16))
+    c = G.random_decode_case(32, 8, 128, lens, seed=15)                     # random slots: nothing consecutive
+    G.assert_close(_run(c, 1, tma_contiguous_runs=True)[0], _oracle(c), G.BF16_ABS, G.BF16_REL, what="auto TMA, random slots")

@@ -407,8 +407,9 @@ struct DecodeCfg {
   static constexpr int STAGE_BYTES = 2 * TILE_BYTES;
   static constexpr int ROWB = SEG >= 128 ? 128 : SEG;  // bytes of one shared-memory row = inner extent of a TMA box
   static constexpr int HALVES = SEG / ROWB;            // 256-byte segments are kept as two 128-byte column halves
-  // paged: + slack to align the ring to the 1024-byte swizzle atom, + kStages mbarriers behind it
-  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + (PAGED ? 1024 + 64 : 0);
+  // paged: + kStages mbarriers behind the ring.  No alignment slack (the dynamic segment is declared 1024-aligned):
+  // two CTAs of 98,368 B (+1 KiB each that the system reserves) stay inside the 196 KiB shared-memory carve-out
+  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + (PAGED ? 64 : 0);
   static constexpr int NSLOT = (TN + 31) / 32;  // slot-id registers per lane
   static constexpr int KC = D / 16;             // MMA k-chunks (bf16) == 16-elt chunks (fp8)
   static constexpr int MT = D / 16;             // PV m-tiles
@@ -474,7 +475,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 
 template <class C>
 __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorMap* tmk, const CUtensorMap* tmv) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem[];  // TMA's swizzle pattern is a function of the address
   constexpr int D = C::D, HPC = C::HPC, TN = C::TN, SEG = C::SEG, CPS = C::CPS, CPT = C::CPT;
   constexpr bool FP8 = C::FP8, PAGED = C::PAGED;
 
@@ -486,7 +487,7 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
   uint32_t bar_base = 0, phases = 0, tma_bits = 0;  // paged: one "tile has landed" mbarrier per stage; its parity bit;
                                                    // bit s of tma_bits: stage s was filled by TMA
   if constexpr (PAGED) {
-    smem_base = (smem_base + 1023u) & ~1023u;  // TMA's swizzle pattern is a function of the address
+    if (smem_base & 1023u) __trap();  // the ring must start on a swizzle atom (it does: no static shared memory)
     bar_base = smem_base + kStages * C::STAGE_BYTES;
     if (tid == 0) {
 #pragma unroll

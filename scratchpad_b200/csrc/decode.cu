@@ -553,12 +553,16 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
         ok = ok && (t >= TN || (t & (bt - 1)) == 0 || slot_reg[j] == prev + 1);
       }
       const bool by_tma = __all_sync(0xffffffffu, ok);
+      const bool prev_by_tma = (tma_bits >> stage) & 1u;  // how this ring stage was filled three tiles ago
       tma_bits = by_tma ? (tma_bits | (1u << stage)) : (tma_bits & ~(1u << stage));
       if (by_tma) {
         if (warp == 0) {
           const uint32_t bar = bar_base + 8 * stage;
           if (lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy traffic on this stage
+            // a stage last written by the row gather (generic proxy) changes hands to the async proxy: fence once
+            // (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC); TMA after TMA needs none -- the reads in between were ordered by
+            // the barrier at the top of the tile loop
+            if (!prev_by_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive_expect_tx(bar, C::STAGE_BYTES);
           }
           __syncwarp();

@@ -66,6 +66,8 @@ class RotaryEmbedding(nn.Module):
             raise NotImplementedError(f"cos_sin_cache dtype {cache.dtype}")
         hs = self.head_size
         positions = positions.flatten()
+        if positions.dtype not in (torch.int64, torch.int32):
+            raise TypeError(f"positions must be int32 or int64, got {positions.dtype}")
         t = positions.shape[0]
         k3 = k.view(t, -1, hs)
         q3 = q.view(t, -1, hs) if q is not None else None
@@ -81,8 +83,6 @@ class RotaryEmbedding(nn.Module):
             num_tokens=t, hq=q3.shape[1] if q3 is not None else 0, hkv=k3.shape[1], d=hs, dv=hs,
             kv_dtype=_lib.KV_BF16, write_back_k=int(write_back_k),
         )
-        if positions.dtype not in (torch.int64, torch.int32):
-            raise TypeError(f"positions must be int32 or int64, got {positions.dtype}")
         if pool is not None:
             kb, vb = pool.k_buffer[layer_id], pool.v_buffer[layer_id]
             v3 = v.view(t, k3.shape[1], -1)

@@ -232,3 +232,17 @@ def test_token_granular_pool_with_consecutive_slots_uses_tma():
     assert torch.equal(got.view(torch.int16), plain.view(torch.int16))
     c = G.random_decode_case(32, 8, 128, lens, seed=15)                     # random slots: nothing consecutive
     G.assert_close(_run(c, 1, tma_contiguous_runs=True)[0], _oracle(c), G.BF16_ABS, G.BF16_REL, what="auto TMA, random slots")
+
+
+@pytest.mark.parametrize("hq,hkv,d,kv,page_size", [(32, 8, 64, "bf16", 16), (8, 1, 128, "fp8", 128), (8, 1, 128, "bf16", 64),
+                                                   (32, 8, 128, "fp8", 32)])
+def test_paged_decode_over_the_fused_kv_layout(hq, hkv, d, kv, page_size, monkeypatch):
+    """Fused [P + page, 2, Hkv, D] pool (K and V rows of a token adjacent): the tensor maps take the doubled token
+    stride and the V view's base pointer; whole-tile boxes and per-run boxes both land where the row gather would."""
+    monkeypatch.setattr(G, "FUSED_KV", True)
+    kv_dtype = torch.bfloat16 if kv == "bf16" else torch.float8_e4m3fn
+    tol = (G.BF16_ABS, G.BF16_REL) if kv == "bf16" else (G.FP8_ABS, G.FP8_REL)
+    c = G.random_decode_case(hq, hkv, d, [300, 128, 17, 640, 129], seed=31 + page_size, kv_dtype=kv_dtype, page_size=page_size)
+    got, backend, runner = _run(c, page_size)[:3]
+    assert runner.token_to_kv_pool.fused_kv and _lib.load().b200_debug_last_tma_mode() in (1, 2)
+    G.assert_close(got, _oracle(c), *tol, what=f"paged fused {hq}/{hkv}/{d}/{kv}/{page_size}")

@@ -735,8 +735,8 @@ def main():
         shared_len = int(backend.workspace[:64].view(torch.int32)[7].item())
         cfg_out = workload_config(w, world * args.shard, args, st)
         cfg_out["rope"] = args.rope
-        cfg_out["tile_fetch"] = {0: "LDGSTS row gather", 1: "TMA, one box per K/V tile",
-                                 2: "TMA, one box per head and page run"}[backend.lib.b200_debug_last_tma_mode()]
+        cfg_out["tile_fetch"] = {0: "LDGSTS row gather", 1: "TMA, one box per K/V tile of consecutive slots (row gather "
+                                 "for the rest)"}[backend.lib.b200_debug_last_tma_mode()]
         cfg_out["cascade"] = {"enabled": bool(backend.cascade), "launched": cascade_launched,
                               "shared_prefix_tokens_detected": shared_len,
                               "row_tiles": int(backend.workspace[:64].view(torch.int32)[8].item())}

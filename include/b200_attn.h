@@ -105,9 +105,11 @@ typedef struct b200_decode_params {
                              * 16, 32, 64 or 128: paged pool -- for every request row r and position t < seq_len,
                              * req_to_token[r, t] = req_to_token[r, t - t % page_size] + t % page_size (what a paged
                              * allocator yields: schedule_batch.py:754-828, radix_cache.py:57-66 page-aligned matching).
-                             * KV tiles whose slot ids really are consecutive per page run are fetched by TMA box
-                             * copies; the kernel checks that per tile on device and takes the row gather for any
-                             * other tile, so the value is a performance hint, never a correctness contract.
+                             * When a page covers a KV tile (b200_attn_config.tile_tokens; always at TP1), tiles whose
+                             * slot ids really are consecutive are fetched by one TMA box copy each for K and V; the
+                             * kernel checks that per tile on device and takes the row gather for any other tile, so
+                             * the value is a performance hint, never a correctness contract.  Smaller pages use the
+                             * row gather (which sees the pages' DRAM locality).
                              * B200_PAGE_AUTO: token-granular pool, TMA for every tile whose slots happen to be
                              * consecutive (an unfragmented allocator hands out runs, memory/pool.py:240-253). */
   int64_t kv_pool_rows;     /* paged only: token rows of k_buf / v_buf (bounds of the tensor maps) */
@@ -240,8 +242,8 @@ int b200_debug_gather(const void* buf, int64_t stride_t_bytes, int32_t row_bytes
                       const void* req_pool_indices, const void* seq_lens, int32_t idx_dtype,
                       const int64_t* out_offsets, int32_t bs, void* out, b200_stream_t stream);
 
-/* Test / bench introspection: how the last b200_attn_decode call of this process fetched whole KV tiles --
- * 0 row gather only (page size 1), 1 one TMA box per K (V) tile (page >= tile), 2 one TMA box per head and page run. */
+/* Test / bench introspection: how the last b200_attn_decode call of this process fetched KV tiles --
+ * 0 row gather only, 1 TMA (one box per K / V tile) for every tile whose slots are consecutive, row gather for the rest. */
 int b200_debug_last_tma_mode(void);
 
 /* Debug check of the paged-table contract (b200_decode_params.page_size): writes to *violations (device int32)

@@ -339,8 +339,6 @@ struct DecodeArgs {
   float sm_scale, logit_cap;
   const float* k_scale;
   const float* v_scale;
-  int box_tok;    // paged pools: token rows per TMA box = min(tile tokens, page size)
-  int tma_whole;  // 1: a box is a whole K (V) tile (4-d map over heads and column halves); 0: per-head page runs (3-d map)
 };
 
 // ---- optional per-CTA timeline (build with -DB200_DEC_TRACE; tools/dec_trace.py): %globaltimer at six points
@@ -458,13 +456,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!done && ++spins > (1 << 22)) __trap();  // a copy that never lands must not hang the GPU
   }
 }
-// one [box_tok x 128 B] box of one head of the pool viewed as (head_dim, kv heads, token rows) -> shared memory
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
 // one whole K (V) tile of the pool viewed as (128-byte column block, token rows, column halves, kv heads)
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -532,15 +523,14 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
     const uint32_t sk = smem_base + stage * C::STAGE_BYTES;
     const uint32_t sv = sk + C::TILE_BYTES;
     if constexpr (PAGED) {
-      // A tile that lies wholly inside the sequence and whose slots are consecutive within every run of box_tok
-      // tokens (what a paged allocator yields: slot = page * page_size + offset, request position t at offset
-      // t % page_size; or simply an unfragmented token-granular allocator) is fetched by TMA: one box per (K|V, head,
-      // column half, run) -- or one per K|V when the run covers the tile -- issued by warp 0, all signalling the
-      // stage's mbarrier.  The check is made HERE, on the slot ids every warp holds anyway (one shuffle, one vote), so
-      // the caller's page-size hint can cost speed but never correctness; any other tile -- the ragged last tile of
-      // a request included -- takes the row gather below (which zero-fills rows past the end; the PV product relies
-      // on that).  The decision is remembered per stage for the consumer side.
-      const int bt = a.box_tok;
+      // A tile that lies wholly inside the sequence and whose TN slots are consecutive (pages of >= TN tokens from a
+      // paged allocator: slot = page * page_size + offset, request position t at offset t % page_size; or simply an
+      // unfragmented token-granular allocator) is fetched by TMA: one box for K, one for V, issued by thread 0,
+      // signalling the stage's mbarrier.  The check is made HERE, on the slot ids every warp holds anyway (one
+      // shuffle, one vote), so the caller's page-size hint can cost speed but never correctness; any other tile --
+      // the ragged last tile of a request included -- takes the row gather below (which zero-fills rows past the end;
+      // the PV product relies on that).  The decision is remembered per stage for the consumer side.
+      constexpr int bt = TN;
       bool ok = tok0 + TN <= c.seq_len;
 #pragma unroll
       for (int j = 0; j < C::NSLOT; ++j) {
@@ -556,46 +546,16 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
       const bool prev_by_tma = (tma_bits >> stage) & 1u;  // how this ring stage was filled three tiles ago
       tma_bits = by_tma ? (tma_bits | (1u << stage)) : (tma_bits & ~(1u << stage));
       if (by_tma) {
-        if (warp == 0) {
+        if (tid == 0) {
           const uint32_t bar = bar_base + 8 * stage;
-          if (lane == 0) {
-            // a stage last written by the row gather (generic proxy) changes hands to the async proxy: fence once
-            // (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC); TMA after TMA needs none -- the reads in between were ordered by
-            // the barrier at the top of the tile loop
-            if (!prev_by_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive_expect_tx(bar, C::STAGE_BYTES);
-          }
-          __syncwarp();
-          if (a.tma_whole) {
-            // page >= tile: the whole K (V) tile is ONE box (all heads of the CTA, both column halves) -- two copies
-            if (lane == 0) {
-              tma_load_4d(sk, tmk, bar, 0, slot_reg[0], 0, h0);  // lane 0 holds the slot id of the tile's first token
-              tma_load_4d(sv, tmv, bar, 0, slot_reg[0], 0, h0);
-            }
-          } else {
-            // page < tile: one box per (K|V, head, column half, page run), spread over the lanes
-            const int nb = TN / bt;
-            const int nops = 2 * HPC * C::HALVES * nb;
-            for (int op0 = 0; op0 < nops; op0 += 32) {
-              const int op = op0 + lane;
-              const bool live = op < nops;
-              const int j = live ? op % nb : 0;
-              int rest = op / nb;
-              const int half = rest % C::HALVES;
-              rest /= C::HALVES;
-              const int head = rest % HPC, is_v = rest / HPC;
-              const int tokb = j * bt;
-              // lanes ask for different page runs: the register holding a lane's slot id is chosen on the reader's side
-              int slot = 0;
-#pragma unroll
-              for (int jj = 0; jj < C::NSLOT; ++jj)
-                slot = select_eq(__shfl_sync(0xffffffffu, slot_reg[jj], tokb & 31), slot, tokb >> 5, jj);
-              if (live) {
-                const uint32_t dst = (is_v ? sv : sk) + tile_chunk_off<CPS, TN>(head, tokb, half * 8);
-                tma_load_3d(dst, is_v ? tmv : tmk, bar, half * (C::ROWB / C::ELT), h0 + head, slot);
-              }
-            }
-          }
+          // a stage last written by the row gather (generic proxy) changes hands to the async proxy: fence once
+          // (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC); TMA after TMA needs none -- the reads in between were ordered by
+          // the barrier at the top of the tile loop
+          if (!prev_by_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive_expect_tx(bar, C::STAGE_BYTES);
+          // the whole K (V) tile is ONE box (all heads of the CTA, both column halves): two copies per tile
+          tma_load_4d(sk, tmk, bar, 0, slot_reg[0], 0, h0);  // thread 0 holds the slot id of the tile's first token
+          tma_load_4d(sv, tmv, bar, 0, slot_reg[0], 0, h0);
         }
         return;
       }
@@ -1109,7 +1069,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static int encode_pool_map(CUtensorMap* out, const void* buf, int64_t stride_t_bytes, int64_t rows, int hkv, int d, bool fp8,
-                           int box_tok, int hpc, bool whole) {
+                           int tile_tokens, int hpc) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* sym = nullptr;
@@ -1119,33 +1079,23 @@ static int encode_pool_map(CUtensorMap* out, const void* buf, int64_t stride_t_b
     fn = reinterpret_cast<EncodeTiledFn>(sym);
   }
   const int elt = fp8 ? 1 : 2, seg = d * elt, rowb = seg >= 128 ? 128 : seg, halves = seg / rowb;
-  const CUtensorMapDataType dt = fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  const CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  // (128-byte column block, token rows, column halves, kv heads): a box over all heads of the CTA and both halves
+  // lands as [head][half][token][128 B] -- the tile layout -- so a tile of consecutive slots is ONE copy.  The strides
+  // (row, 128 B, D*elt) are not monotonic; the driver accepts that.
+  const cuuint64_t gdim[4] = {static_cast<cuuint64_t>(rowb / elt), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(halves),
+                              static_cast<cuuint64_t>(hkv)};
+  const cuuint64_t gstride[3] = {static_cast<cuuint64_t>(stride_t_bytes), static_cast<cuuint64_t>(rowb), static_cast<cuuint64_t>(seg)};
+  const cuuint32_t box[4] = {static_cast<cuuint32_t>(rowb / elt), static_cast<cuuint32_t>(tile_tokens),
+                             static_cast<cuuint32_t>(halves), static_cast<cuuint32_t>(hpc)};
   const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-  CUresult r;
-  if (whole) {
-    // (128-byte column block, token rows, column halves, kv heads): a box over all heads of the CTA and both halves
-    // lands as [head][half][token][128 B] -- the tile layout -- so a page that covers the tile is ONE copy
-    const cuuint64_t gdim[4] = {static_cast<cuuint64_t>(rowb / elt), static_cast<cuuint64_t>(rows),
-                                static_cast<cuuint64_t>(halves), static_cast<cuuint64_t>(hkv)};
-    const cuuint64_t gstride[3] = {static_cast<cuuint64_t>(stride_t_bytes), static_cast<cuuint64_t>(rowb),
-                                   static_cast<cuuint64_t>(seg)};
-    const cuuint32_t box[4] = {static_cast<cuuint32_t>(rowb / elt), static_cast<cuuint32_t>(box_tok),
-                               static_cast<cuuint32_t>(halves), static_cast<cuuint32_t>(hpc)};
-    r = fn(out, dt, 4, const_cast<void*>(buf), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  } else {
-    // (head_dim, kv heads, token rows); box = (one 128-byte column block, 1 head, box_tok rows)
-    const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(hkv), static_cast<cuuint64_t>(rows)};
-    const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(seg), static_cast<cuuint64_t>(stride_t_bytes)};
-    const cuuint32_t box[3] = {static_cast<cuuint32_t>(rowb / elt), 1u, static_cast<cuuint32_t>(box_tok)};
-    r = fn(out, dt, 3, const_cast<void*>(buf), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  }
+  const CUresult r = fn(out, fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(buf), gdim,
+                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? B200_OK : B200_ERR_INVALID;
 }
 
-static int g_last_tma_mode = 0;  // test / bench introspection: 0 row gather only, 1 whole-tile boxes, 2 per-head page runs
+static int g_last_tma_mode = 0;  // test / bench introspection: 0 row gather only, 1 TMA for tiles of consecutive slots
 
 template <class C>
 static int launch_decode_t(const DecodeArgs& a, const PagedMaps* maps, int grid_x, int grid_y, cudaStream_t st, bool query_only,
@@ -1404,43 +1354,26 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
     if (rc) return rc;
   }
   // page_size > 1: slots of a page are consecutive and request position t sits at offset
-  // t % page_size of its page, so whole tiles are fetched with TMA box copies, one per page run (the kernel checks
+  // t % page_size of its page, so a tile inside a page is fetched with one TMA box copy for K and one for V (the kernel checks
   // every tile's slot ids before it trusts that: a wrong page_size costs speed, not correctness)
   PagedMaps maps;
   const PagedMaps* mp = nullptr;
-  a.box_tok = 0;
-  a.tma_whole = 0;
   if (p->page_size > 1 || p->page_size == B200_PAGE_AUTO) {
-    // B200_PAGE_AUTO: a token-granular pool whose allocator often hands out consecutive slots -- try whole-tile boxes
+    // B200_PAGE_AUTO: a token-granular pool whose allocator often hands out consecutive slots
     const int ps = p->page_size == B200_PAGE_AUTO ? cfg.tile_tokens : p->page_size;
     if (ps < 16 || ps > 128 || (ps & (ps - 1)) || p->kv_pool_rows <= 0) return B200_ERR_UNSUPPORTED;
-    a.box_tok = ps < cfg.tile_tokens ? ps : cfg.tile_tokens;
-    // Measured: a whole-tile box (16 KB) beats the row gather by 2-5 %, 8 KB page runs match it, 2 KB
-    // page runs lose 5-10 % to it (per-copy cost of the TMA unit).  Page runs below 4 KB therefore stay on the row
-    // gather, which is still correct on a paged table (one slot id per token) and sees the pages' DRAM locality.
-    const int rowb = p->d * elt >= 128 ? 128 : p->d * elt;
-    const bool use_tma = a.box_tok == cfg.tile_tokens || a.box_tok * rowb >= 4096;
-    // one box per tile when the page covers it; the driver may refuse the 4-d description (its strides are not
-    // monotonic) -- then, and for smaller pages, per-head page runs through the 3-d map
-    a.tma_whole = a.box_tok == cfg.tile_tokens;
-    if (!use_tma) {
-      a.box_tok = 0;
-      a.tma_whole = 0;
-    } else if (a.tma_whole) {
-      rc = encode_pool_map(&maps.k, p->k_buf, a.k_st_bytes, p->kv_pool_rows, p->hkv, p->d, kc.fp8, a.box_tok, kc.hpc, true);
-      if (!rc) rc = encode_pool_map(&maps.v, p->v_buf, a.v_st_bytes, p->kv_pool_rows, p->hkv, p->dv, kc.fp8, a.box_tok, kc.hpc, true);
-      if (rc == B200_ERR_INVALID) a.tma_whole = 0;
-      else if (rc) return rc;
+    // Measured: one box per K (V) tile (16 KB) beats the row gather by 2-5 %; page runs smaller than the
+    // tile, fetched as one box per head and run (2-8 KB), never did -- per-copy cost of the TMA unit -- while the
+    // row gather over a paged table gains the pages' DRAM locality by itself.  So: TMA when a page covers the tile,
+    // the row gather (correct on any table: one slot id per token) otherwise.
+    if (ps >= cfg.tile_tokens) {
+      rc = encode_pool_map(&maps.k, p->k_buf, a.k_st_bytes, p->kv_pool_rows, p->hkv, p->d, kc.fp8, cfg.tile_tokens, kc.hpc);
+      if (!rc) rc = encode_pool_map(&maps.v, p->v_buf, a.v_st_bytes, p->kv_pool_rows, p->hkv, p->dv, kc.fp8, cfg.tile_tokens, kc.hpc);
+      if (!rc) mp = &maps;
+      else if (rc != B200_ERR_INVALID) return rc;  // a driver that refuses the map: row gather
     }
-    if (use_tma && !a.tma_whole) {
-      rc = encode_pool_map(&maps.k, p->k_buf, a.k_st_bytes, p->kv_pool_rows, p->hkv, p->d, kc.fp8, a.box_tok, kc.hpc, false);
-      if (rc) return rc;
-      rc = encode_pool_map(&maps.v, p->v_buf, a.v_st_bytes, p->kv_pool_rows, p->hkv, p->dv, kc.fp8, a.box_tok, kc.hpc, false);
-      if (rc) return rc;
-    }
-    if (use_tma) mp = &maps;
   }
-  g_last_tma_mode = mp ? (a.tma_whole ? 1 : 2) : 0;
+  g_last_tma_mode = mp ? 1 : 0;
   rc = dispatch(kc, a, mp, cfg.grid_ctas, p->hkv / kc.hpc, st, false, nullptr);
   if (rc) return rc;
   if (p->ev_kernel_end) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(p->ev_kernel_end), st));

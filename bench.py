@@ -191,7 +191,8 @@ def pick_layers(per_layer_bytes: int, want: int, total_layers: int) -> int:
 
 
 def build_state(args, rank, world):
-    from scratchpad_b200 import CudaB200AttnBackend, synth
+    from scratchpad_b200 import CudaB200AttnBackend
+    from harness import synth
 
     w = synth.WORKLOADS[args.workload]
     assert w.hkv_total % world == 0 and w.hq_total % world == 0, "kv heads must divide over the GPUs"
@@ -234,7 +235,7 @@ def build_state(args, rank, world):
 # ----------------------------------------------------------------------------
 def cpu_sample_state(w, seq_lens, hq, hkv, sample_reqs: int, seed: int):
     from oracle import attn_oracle as O
-    from scratchpad_b200 import synth
+    from harness import synth
 
     gen = torch.Generator().manual_seed(seed)
     lens = list(seq_lens[:sample_reqs])
@@ -289,7 +290,7 @@ def run_reference(args, rank, world):
     times the oracle port ("port") with every host thread, on a bounded sample of the same workload."""
     if rank != 0:
         return
-    from scratchpad_b200 import synth
+    from harness import synth
 
     w = synth.WORKLOADS[args.workload]
     gen = torch.Generator().manual_seed(args.seed)
@@ -349,7 +350,8 @@ def workload_config(w, world, args, st):
 # extend / chunked-prefill workloads (C4): tensor-bound, metric TFLOP/s
 # ----------------------------------------------------------------------------
 def run_extend_bench(args, rank, world, local_rank, dist):
-    from scratchpad_b200 import CudaB200AttnBackend, synth
+    from scratchpad_b200 import CudaB200AttnBackend
+    from harness import synth
 
     w = synth.WORKLOADS[args.workload]
     tp = world * args.shard
@@ -498,7 +500,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 
-    from scratchpad_b200 import synth as _synth
+    from harness import synth as _synth
     if _synth.WORKLOADS[args.workload].extend_len:
         run_extend_bench(args, rank, world, local_rank, dist)
         return
@@ -510,7 +512,7 @@ def main():
 
     gq = torch.Generator(device=dev).manual_seed(77 + rank)
     # q/k/v as column slices of the fused qkv GEMM output (llama.py:149-152)
-    from scratchpad_b200 import ForwardMode
+    from harness import ForwardMode
 
     # Static step inputs, like the buffers of a graph runner: the activations (q/k/v as column slices of the fused qkv
     # GEMM output, llama.py:149-152) and the batch metadata the forward pass reads (seq_lens, req_pool_indices,

@@ -17,7 +17,8 @@ from typing import List, Optional, Sequence
 import torch
 
 from .forward_info import ForwardBatch, ForwardMode, compute_extend_start_loc
-from .pool import MHATokenToKVPool, ReqToTokenPool
+from scratchpad_b200.pool import MHATokenToKVPool
+from .pools import ReqToTokenPool
 from .radix_attention import RadixAttention
 
 

@@ -5,19 +5,11 @@ library behind it.  See DESIGN.md / INTEGRATION.md.
 """
 
 from .backend import AttentionBackend, CudaB200AttnBackend
-from .forward_info import ForwardBatch, ForwardMode, compute_extend_start_loc
-from .pool import MHATokenToKVPool, PagedTokenToKVPoolAllocator, ReqToTokenPool, TokenToKVPoolAllocator
-from .radix_attention import RadixAttention
+from .pool import MHATokenToKVPool, PagedTokenToKVPoolAllocator
 
 __all__ = [
     "AttentionBackend",
     "CudaB200AttnBackend",
-    "ForwardBatch",
-    "ForwardMode",
-    "compute_extend_start_loc",
     "MHATokenToKVPool",
     "PagedTokenToKVPoolAllocator",
-    "ReqToTokenPool",
-    "TokenToKVPoolAllocator",
-    "RadixAttention",
 ]

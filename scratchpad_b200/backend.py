@@ -27,6 +27,7 @@ from typing import Optional
 import torch
 
 from . import _lib
+from .pool import kv_dtype_code, kv_store
 
 
 class AttentionBackend(ABC):
@@ -79,6 +80,22 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+def _i32(t: torch.Tensor, what: str) -> torch.Tensor:
+    """The C ABI reads these as contiguous int32 (forward_info.py:258-263,408-410 produce exactly that); another
+    integration's int64 or strided tensor is converted here instead of being misread."""
+    if t.dtype != torch.int32 or not t.is_contiguous():
+        if t.dtype not in (torch.int32, torch.int64):
+            raise TypeError(f"{what} must be an integer tensor, got {t.dtype}")
+        t = t.to(torch.int32).contiguous()
+    return t
+
+
+def _idx(t: torch.Tensor, what: str) -> torch.Tensor:
+    if t.dtype not in (torch.int32, torch.int64):
+        raise TypeError(f"{what} must be int32 or int64, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
 class CudaB200AttnBackend(AttentionBackend):
     def __init__(self, model_runner, force_path: int = _lib.PATH_AUTO, cascade: Optional[bool] = None,
                  tma_contiguous_runs: Optional[bool] = None):
@@ -96,7 +113,10 @@ class CudaB200AttnBackend(AttentionBackend):
         self.req_to_token_pool = model_runner.req_to_token_pool
         self.token_to_kv_pool = model_runner.token_to_kv_pool
         self.v_head_dim = self.token_to_kv_pool.get_value_buffer(0).shape[-1]
-        self.kv_dtype = self.token_to_kv_pool.kv_dtype_code()
+        # any pool with the reference's layout works (k_buffer / v_buffer lists of [P+page, Hkv, D], .dtype); the
+        # fp8 scale metadata of scratchpad_b200.pool.MHATokenToKVPool is used when the pool has it
+        self.kv_dtype = kv_dtype_code(self.token_to_kv_pool.dtype)
+        self._layer_scales = {}
         self.force_path = force_path
         # Shared-prefix cascade decode: the prefix every request of a decode batch shares (same slot ids in
         # req_to_token, which is how RadixAttention represents a shared system prompt) is attended once per
@@ -111,6 +131,7 @@ class CudaB200AttnBackend(AttentionBackend):
             raise NotImplementedError("cuda_b200 backend: sliding-window attention is not supported")
         if model_runner.dtype != torch.bfloat16:
             raise NotImplementedError("cuda_b200 backend: model dtype must be bfloat16")
+        self._graph_state_frozen = False
         self.cuda_graph_max_seq_len = cfg.context_len
         self._check_pages = os.environ.get("B200_CHECK_PAGES", "0") == "1"
         self.max_bs = 0
@@ -126,6 +147,12 @@ class CudaB200AttnBackend(AttentionBackend):
     def _ensure_workspace(self, max_bs: int) -> None:
         if self.workspace is not None and max_bs <= self.max_bs:
             return
+        if self.workspace is not None and self._graph_state_frozen:
+            # captured graphs hold this workspace's address and a layout that depends on max_bs: growing would leave
+            # them reading freed memory (the reference sizes its graph state once, cuda_graph_runner.py:178-181)
+            raise RuntimeError(f"cuda_b200 backend: batch size {max_bs} exceeds the workspace sized for {self.max_bs} "
+                               "after CUDA-graph capture; call init_cuda_graph_state(max_bs) with the largest batch "
+                               "before capturing")
         cfg = _lib.AttnConfig()
         rc = self.lib.b200_attn_get_config(max_bs, self.num_head, self.num_kv_head, self.head_dim,
                                            self.v_head_dim, self.kv_dtype, self.force_path, cfg)
@@ -135,6 +162,8 @@ class CudaB200AttnBackend(AttentionBackend):
         self.workspace = torch.empty(int(cfg.workspace_bytes), dtype=torch.uint8, device=self.device)
 
     def _plan(self, bs: int, req_pool_indices: torch.Tensor, seq_lens: torch.Tensor) -> None:
+        req_pool_indices = _idx(req_pool_indices, "req_pool_indices")
+        seq_lens = _idx(seq_lens, "seq_lens")
         if req_pool_indices.dtype != seq_lens.dtype:
             seq_lens = seq_lens.to(req_pool_indices.dtype)
         rc = self.lib.b200_attn_plan(
@@ -190,6 +219,7 @@ class CudaB200AttnBackend(AttentionBackend):
         assert forward_mode.is_decode(), "Not supported"
         assert spec_info is None, "Not supported"
         assert bs <= self.max_bs, "init_cuda_graph_state(max_bs) must cover every captured batch size"
+        self._graph_state_frozen = True
         self._plan(bs, req_pool_indices[:bs], seq_lens[:bs])
         self.forward_metadata = ("decode", bs)
 
@@ -202,8 +232,30 @@ class CudaB200AttnBackend(AttentionBackend):
     def get_cuda_graph_seq_len_fill_value(self):
         return 1
 
-    def _scales(self, layer):
-        return self.token_to_kv_pool.get_kv_scales(layer.layer_id)
+    def _scales(self, layer, pool=None):
+        """Device fp32 [Hkv] dequantisation scales of this layer's K and V, or (None, None) = 1.0."""
+        pool = pool if pool is not None else self.token_to_kv_pool
+        if hasattr(pool, "get_kv_scales"):
+            return pool.get_kv_scales(layer.layer_id)
+        if self.kv_dtype == _lib.KV_BF16:
+            return None, None
+        # a pool without scale metadata (the reference's class): per-tensor floats carried by the layer, the way
+        # the reference's FlashInfer backend reads them (flashinfer_backend.py:387-388,457-458)
+        ks = getattr(layer, "k_scale_float", None)
+        vs = getattr(layer, "v_scale_float", None)
+        key = (layer.layer_id, ks, vs)
+        hit = self._layer_scales.get(layer.layer_id)
+        if hit is None or hit[0] != key:
+            mk = lambda x: torch.full((self.num_kv_head,), 1.0 if x is None else float(x), dtype=torch.float32,
+                                      device=self.device)
+            hit = (key, mk(ks), mk(vs))
+            self._layer_scales[layer.layer_id] = hit
+        return hit[1], hit[2]
+
+    def _store_kv(self, pool, layer, loc, k, v) -> None:
+        """MHATokenToKVPool.set_kv_buffer (pool.py:392-424) as one launch, on whatever pool class the engine uses."""
+        ks, vs = self._scales(layer, pool)
+        kv_store(pool.k_buffer[layer.layer_id], pool.v_buffer[layer.layer_id], loc, k, v, self.kv_dtype, ks, vs)
 
     def _page_hint(self, pool) -> int:
         """b200_decode_params.page_size: the pool's page size, or PAGE_AUTO for a token-granular pool when
@@ -228,8 +280,9 @@ class CudaB200AttnBackend(AttentionBackend):
         (llama.py:149-152) plus set_kv_buffer's two index_put_ (pool.py:392-424)."""
         rotary_emb, positions = rope
         if save_kv_cache:
-            rotary_emb.rope_kv_store(positions, q, k, v, forward_batch.token_to_kv_pool, layer.layer_id,
-                                     forward_batch.out_cache_loc, write_back_k)
+            pool = forward_batch.token_to_kv_pool
+            rotary_emb.rope_kv_store(positions, q, k, v, pool, layer.layer_id, forward_batch.out_cache_loc,
+                                     write_back_k, scales=self._scales(layer, pool))
         else:
             rotary_emb(positions, q, k)
 
@@ -245,12 +298,12 @@ class CudaB200AttnBackend(AttentionBackend):
             # decode reads the new token's K from the pool, so the rotated k is not written back
             self._rope_and_store(rope, q, k, v, layer, forward_batch, save_kv_cache, write_back_k=not save_kv_cache)
         elif save_kv_cache:
-            pool.set_kv_buffer(layer, forward_batch.out_cache_loc, k, v)
+            self._store_kv(pool, layer, forward_batch.out_cache_loc, k, v)
         kind, bs = self.forward_metadata
         assert kind == "decode" and bs == q.shape[0], "init_forward_metadata was not called for this batch"
         kb, vb = pool.k_buffer[layer.layer_id], pool.v_buffer[layer.layer_id]
         r2t = forward_batch.req_to_token_pool.req_to_token
-        ks, vs = self._scales(layer)
+        ks, vs = self._scales(layer, pool)
         p = _lib.DecodeParams(
             q=q.data_ptr(), q_stride_t=q.stride(0), q_stride_h=d,
             k_buf=kb.data_ptr(), v_buf=vb.data_ptr(), k_stride_t=kb.stride(0), v_stride_t=vb.stride(0),
@@ -281,7 +334,7 @@ class CudaB200AttnBackend(AttentionBackend):
             # the extend kernels read the new tokens' K from the k argument: rotated k is written back in place
             self._rope_and_store(rope, q3, k, v, layer, forward_batch, save_kv_cache, write_back_k=True)
         elif save_kv_cache:
-            pool.set_kv_buffer(layer, forward_batch.out_cache_loc, k, v)
+            self._store_kv(pool, layer, forward_batch.out_cache_loc, k, v)
         kind, max_extend_len = self.forward_metadata
         assert kind == "extend", "init_forward_metadata was not called for this batch"
         k3, v3 = k.view(-1, hkv, d), v.view(-1, hkv, dv)
@@ -289,10 +342,12 @@ class CudaB200AttnBackend(AttentionBackend):
             k3, v3 = k3.contiguous(), v3.contiguous()
         kb, vb = pool.k_buffer[layer.layer_id], pool.v_buffer[layer.layer_id]
         r2t = forward_batch.req_to_token_pool.req_to_token
-        ks, vs = self._scales(layer)
-        rpi, sl = forward_batch.req_pool_indices, forward_batch.seq_lens
+        ks, vs = self._scales(layer, pool)
+        rpi, sl = _idx(forward_batch.req_pool_indices, "req_pool_indices"), _idx(forward_batch.seq_lens, "seq_lens")
         if rpi.dtype != sl.dtype:
             sl = sl.to(rpi.dtype)
+        ext_lens = _i32(forward_batch.extend_seq_lens, "extend_seq_lens")
+        ext_start = _i32(forward_batch.extend_start_loc, "extend_start_loc")
         p = _lib.ExtendParams(
             q=q3.data_ptr(), q_stride_t=q3.stride(0), q_stride_h=q3.stride(1),
             k_new=k3.data_ptr(), v_new=v3.data_ptr(),
@@ -301,8 +356,7 @@ class CudaB200AttnBackend(AttentionBackend):
             o=o.data_ptr(), o_stride_t=o.stride(0), o_stride_h=dv,
             req_to_token=r2t.data_ptr(), req_to_token_stride=r2t.stride(0),
             req_pool_indices=rpi.data_ptr(), seq_lens=sl.data_ptr(), idx_dtype=_idx_code(rpi),
-            extend_seq_lens=forward_batch.extend_seq_lens.data_ptr(),
-            extend_start_loc=forward_batch.extend_start_loc.data_ptr(),
+            extend_seq_lens=ext_lens.data_ptr(), extend_start_loc=ext_start.data_ptr(),
             bs=forward_batch.batch_size, hq=hq, hkv=hkv, d=d, dv=dv,
             total_tokens=q3.shape[0], max_extend_len=int(max_extend_len), kv_dtype=self.kv_dtype,
             sm_scale=float(layer.scaling), logit_cap=self._logit_cap(layer),

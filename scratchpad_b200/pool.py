@@ -1,10 +1,11 @@
-"""Paged KV pool types with the layout the reference engine uses, plus the
-fp8-e4m3 scale metadata the new backend needs.
+"""The KV pool with the layout the reference engine uses, plus the fp8-e4m3 scale
+metadata the new backend needs, and a page-granular allocator.
 
-Mirrors ``scratchpad/memory/pool.py`` (reference): ``ReqToTokenPool`` (:13-72),
-``TokenToKVPoolAllocator`` (:189-255, page size 1, slot 0 reserved for padded
-tokens) and ``MHATokenToKVPool`` (:258-424, per-layer ``[size+1, Hkv, D]``
-buffers, fp8 stored as uint8).  What changes for the cuda_b200 backend
+``MHATokenToKVPool`` keeps the reference's layout (``scratchpad/memory/pool.py:258-424``:
+per-layer ``[size+page, Hkv, D]`` buffers, fp8 stored as uint8, slot 0 = padding).  The
+backend itself only duck-types a pool (``k_buffer`` / ``v_buffer`` / ``dtype``), so the
+reference's own unmodified class works too (tests/test_engine_boundary_gpu.py); this class is what
+the reference's would become for the cuda_b200 backend
 (BASELINE.json north_star, "KV pool layout/scale metadata"):
 
 * ``kv_cache_dtype`` may be ``torch.float8_e4m3fn``; the pool then carries
@@ -30,77 +31,6 @@ FP8_DTYPES = (torch.float8_e4m3fn,)
 PAGE_SIZES = (16, 32, 64, 128)
 
 
-class ReqToTokenPool:
-    """Request row -> KV slot ids (``int32 [size, max_context_len]``)."""
-
-    def __init__(self, size: int, max_context_len: int, device: str, use_records: bool = False):
-        self.size = size
-        self.max_context_len = max_context_len
-        self.device = device
-        self.req_to_token = torch.zeros((size, max_context_len), dtype=torch.int32, device=device)
-        self.free_slots = list(range(size))
-        self.write_records = []
-        self.use_records = use_records
-
-    def write(self, indices, values):
-        self.req_to_token[indices] = values
-        if self.use_records:
-            self.write_records.append((indices, values))
-
-    def available_size(self):
-        return len(self.free_slots)
-
-    def alloc(self, need_size: int) -> Optional[List[int]]:
-        if need_size > len(self.free_slots):
-            return None
-        select_index = self.free_slots[:need_size]
-        self.free_slots = self.free_slots[need_size:]
-        return select_index
-
-    def free(self, free_index: Union[int, List[int]]):
-        if isinstance(free_index, int):
-            self.free_slots.append(free_index)
-        else:
-            self.free_slots.extend(free_index)
-
-    def clear(self):
-        self.free_slots = list(range(self.size))
-        self.write_records = []
-
-
-class TokenToKVPoolAllocator:
-    """Free list of int64 KV slot ids; slot 0 is the dummy slot for padded tokens."""
-
-    def __init__(self, size: int, dtype: torch.dtype, device: str, kvcache: "MHATokenToKVPool"):
-        self.size = size
-        self.dtype = dtype
-        self.device = device
-        self.page_size = 1
-        self._kvcache = kvcache
-        self.clear()
-
-    def available_size(self):
-        return len(self.free_slots)
-
-    def get_kvcache(self):
-        return self._kvcache
-
-    def alloc(self, need_size: int):
-        if need_size > len(self.free_slots):
-            return None
-        select_index = self.free_slots[:need_size]
-        self.free_slots = self.free_slots[need_size:]
-        return select_index
-
-    def free(self, free_index: torch.Tensor):
-        if free_index.numel() == 0:
-            return
-        self.free_slots = torch.cat((self.free_slots, free_index))
-
-    def clear(self):
-        self.free_slots = torch.arange(1, self.size + 1, dtype=torch.int64, device=self.device)
-
-
 class PagedTokenToKVPoolAllocator:
     """Page-granular free list for ``page_size > 1`` -- the allocator the reference's paged call sites expect
     (``alloc_extend(prefix_lens, seq_lens, last_loc, extend_num_tokens)`` / ``alloc_decode(seq_lens, last_loc)`` /
@@ -119,6 +49,7 @@ class PagedTokenToKVPoolAllocator:
         self.dtype = dtype
         self.device = device
         self._kvcache = kvcache
+        self.debug_checks = False  # True: a double free raises instead of being ignored
         self.clear()
 
     def available_size(self):
@@ -189,11 +120,18 @@ class PagedTokenToKVPoolAllocator:
         return out
 
     def free(self, free_index: torch.Tensor):
-        """Slots back to the free list; a page returns when its first slot does (callers free page-aligned runs)."""
+        """Slots back to the free list.  The engine frees whole requests / radix nodes, i.e. runs that cover every
+        used slot of a page; a page returns once, whichever of its slots are named (``unique(slot // page_size)``),
+        and a page that is already free is not added twice."""
         if free_index.numel() == 0:
             return
-        firsts = free_index[free_index % self.page_size == 0] // self.page_size
-        self.free_pages = torch.cat((self.free_pages, firsts.to(torch.int64).to(self.free_pages.device)))
+        pages = torch.unique(free_index.to(torch.int64) // self.page_size).to(self.free_pages.device)
+        pages = pages[pages > 0]  # page 0 holds the dummy slots and is never handed out
+        if self.debug_checks:
+            assert not torch.isin(pages, self.free_pages).any(), "double free of a KV page"
+        else:
+            pages = pages[~torch.isin(pages, self.free_pages)]
+        self.free_pages = torch.cat((self.free_pages, pages))
 
 
 class MHATokenToKVPool:
@@ -293,11 +231,7 @@ class MHATokenToKVPool:
         return k, v
 
     def kv_dtype_code(self) -> int:
-        if self.dtype == torch.bfloat16:
-            return _lib.KV_BF16
-        if self.dtype == torch.float8_e4m3fn:
-            return _lib.KV_FP8_E4M3
-        raise NotImplementedError(f"kv cache dtype {self.dtype} is not supported by the cuda_b200 backend")
+        return kv_dtype_code(self.dtype)
 
     def set_kv_buffer(self, layer, loc: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor,
                       k_scale=None, v_scale=None) -> None:
@@ -306,26 +240,46 @@ class MHATokenToKVPool:
         ``k_scale``/``v_scale`` override the pool's stored scales when given
         (floats, the reference's calling convention)."""
         layer_id = layer.layer_id
-        if not cache_k.is_cuda:
-            raise RuntimeError("MHATokenToKVPool.set_kv_buffer needs CUDA tensors (no CPU fallback)")
-        if cache_k.dtype != torch.bfloat16:
-            raise NotImplementedError("the cuda_b200 backend stores from bf16 activations")
         if k_scale is not None or v_scale is not None:
             self.set_kv_scales(layer_id, 1.0 if k_scale is None else k_scale, 1.0 if v_scale is None else v_scale)
         ks, vs = self.get_kv_scales(layer_id)
-        kb, vb = self.k_buffer[layer_id], self.v_buffer[layer_id]
-        cache_k = cache_k.view(-1, self.head_num, self.head_dim)
-        cache_v = cache_v.view(-1, self.head_num, self.v_head_dim)
-        if cache_k.stride(2) != 1 or cache_v.stride(2) != 1:
-            cache_k, cache_v = cache_k.contiguous(), cache_v.contiguous()
-        loc_code = {torch.int64: _lib.IDX_I64, torch.int32: _lib.IDX_I32}[loc.dtype]
-        lib = _lib.load()
-        rc = lib.b200_kv_store(
-            kb.data_ptr(), vb.data_ptr(), kb.stride(0), vb.stride(0),
-            loc.data_ptr(), loc_code, cache_k.data_ptr(), cache_v.data_ptr(),
-            cache_k.stride(0), cache_k.stride(1), cache_v.stride(0), cache_v.stride(1),
-            cache_k.shape[0], self.head_num, self.head_dim, self.v_head_dim, self.kv_dtype_code(),
-            ks.data_ptr() if ks is not None else None, vs.data_ptr() if vs is not None else None,
-            torch.cuda.current_stream().cuda_stream,
-        )
-        _lib.check(rc, "b200_kv_store")
+        kv_store(self.k_buffer[layer_id], self.v_buffer[layer_id], loc, cache_k, cache_v, self.kv_dtype_code(), ks, vs)
+
+
+def kv_dtype_code(dtype: torch.dtype) -> int:
+    if dtype == torch.bfloat16:
+        return _lib.KV_BF16
+    if dtype == torch.float8_e4m3fn:
+        return _lib.KV_FP8_E4M3
+    raise NotImplementedError(f"kv cache dtype {dtype} is not supported by the cuda_b200 backend")
+
+
+def kv_store(kb: torch.Tensor, vb: torch.Tensor, loc: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor,
+             kv_code: int, k_scale: Optional[torch.Tensor], v_scale: Optional[torch.Tensor]) -> None:
+    """``kb[loc] = quant(cache_k); vb[loc] = quant(cache_v)`` -- one ``b200_kv_store`` launch on the current stream.
+    ``kb``/``vb``: one layer's ``[P+page, Hkv, D]`` pool buffers (bf16, or uint8 / fp8 storage); ``cache_k``/``cache_v``
+    bf16 ``[T, Hkv, D]`` (or ``[T, Hkv*D]``), possibly column slices of the qkv GEMM output; scales: device fp32
+    ``[Hkv]`` or None.  The caller's k/v are not modified (the reference divides them in place, pool.py:404-412)."""
+    if not cache_k.is_cuda:
+        raise RuntimeError("cuda_b200 kv_store needs CUDA tensors (no CPU fallback)")
+    if cache_k.dtype != torch.bfloat16 or cache_v.dtype != torch.bfloat16:
+        raise NotImplementedError("the cuda_b200 backend stores from bf16 activations")
+    if loc.dtype not in (torch.int64, torch.int32) or not loc.is_contiguous():
+        raise TypeError(f"out_cache_loc must be a contiguous int64/int32 tensor, got {loc.dtype}")
+    hkv, d, dv = kb.shape[1], kb.shape[2], vb.shape[2]
+    cache_k = cache_k.view(-1, hkv, d)
+    cache_v = cache_v.view(-1, hkv, dv)
+    if cache_k.stride(2) != 1 or cache_v.stride(2) != 1:
+        cache_k, cache_v = cache_k.contiguous(), cache_v.contiguous()
+    if loc.numel() != cache_k.shape[0]:
+        raise ValueError(f"out_cache_loc has {loc.numel()} entries for {cache_k.shape[0]} tokens")
+    loc_code = _lib.IDX_I64 if loc.dtype == torch.int64 else _lib.IDX_I32
+    rc = _lib.load().b200_kv_store(
+        kb.data_ptr(), vb.data_ptr(), kb.stride(0), vb.stride(0),
+        loc.data_ptr(), loc_code, cache_k.data_ptr(), cache_v.data_ptr(),
+        cache_k.stride(0), cache_k.stride(1), cache_v.stride(0), cache_v.stride(1),
+        cache_k.shape[0], hkv, d, dv, kv_code,
+        k_scale.data_ptr() if k_scale is not None else None, v_scale.data_ptr() if v_scale is not None else None,
+        torch.cuda.current_stream().cuda_stream,
+    )
+    _lib.check(rc, "b200_kv_store")

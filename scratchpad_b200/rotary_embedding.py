@@ -24,6 +24,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from .pool import kv_dtype_code
 
 
 class RotaryEmbedding(nn.Module):
@@ -50,7 +51,7 @@ class RotaryEmbedding(nn.Module):
         return torch.cat((freqs.cos(), freqs.sin()), dim=-1)
 
     # ---- the one launcher -------------------------------------------------------
-    def _launch(self, positions, q, k, v=None, pool=None, layer_id=None, loc=None, write_back_k=True) -> None:
+    def _launch(self, positions, q, k, v=None, pool=None, layer_id=None, loc=None, write_back_k=True, scales=None) -> None:
         if not k.is_cuda:
             raise RuntimeError("cuda_b200 rotary embedding needs CUDA tensors (no CPU fallback)")
         if k.dtype != torch.bfloat16 or (q is not None and q.dtype != torch.bfloat16):
@@ -88,13 +89,20 @@ class RotaryEmbedding(nn.Module):
             v3 = v.view(t, k3.shape[1], -1)
             if v3.stride(2) != 1:
                 v3 = v3.contiguous()
-            ks, vs = pool.get_kv_scales(layer_id)
+            if scales is not None:
+                ks, vs = scales
+            elif hasattr(pool, "get_kv_scales"):
+                ks, vs = pool.get_kv_scales(layer_id)
+            else:  # a pool without scale metadata (the reference's own class): unit scales
+                ks = vs = None
+            if loc.dtype not in (torch.int64, torch.int32) or not loc.is_contiguous():
+                raise TypeError(f"out_cache_loc must be a contiguous int64/int32 tensor, got {loc.dtype}")
             p.v, p.v_src_stride_t, p.v_src_stride_h = v3.data_ptr(), v3.stride(0), v3.stride(1)
             p.k_buf, p.v_buf, p.k_stride_t, p.v_stride_t = kb.data_ptr(), vb.data_ptr(), kb.stride(0), vb.stride(0)
             p.loc = loc.data_ptr()
             p.loc_dtype = {torch.int64: _lib.IDX_I64, torch.int32: _lib.IDX_I32}[loc.dtype]
             p.dv = v3.shape[2]
-            p.kv_dtype = pool.kv_dtype_code()
+            p.kv_dtype = kv_dtype_code(pool.dtype)
             p.k_scale = ks.data_ptr() if ks is not None else None
             p.v_scale = vs.data_ptr() if vs is not None else None
         rc = _lib.load().b200_rope_kv_store(p, torch.cuda.current_stream().cuda_stream)
@@ -108,9 +116,11 @@ class RotaryEmbedding(nn.Module):
         self._launch(positions, query, key)
         return query, key
 
-    def rope_kv_store(self, positions, query, key, value, pool, layer_id: int, loc, write_back_k: bool) -> None:
-        """Rotate q in place, rotate k and write (k, v) into the pool at ``loc`` -- one launch."""
-        self._launch(positions, query, key, value, pool, layer_id, loc, write_back_k)
+    def rope_kv_store(self, positions, query, key, value, pool, layer_id: int, loc, write_back_k: bool,
+                      scales=None) -> None:
+        """Rotate q in place, rotate k and write (k, v) into the pool at ``loc`` -- one launch.  ``scales``:
+        (k_scale, v_scale) device fp32 ``[Hkv]`` tensors overriding the pool's own metadata."""
+        self._launch(positions, query, key, value, pool, layer_id, loc, write_back_k, scales)
 
     def extra_repr(self) -> str:
         return (f"head_size={self.head_size}, rotary_dim={self.rotary_dim}, "

@@ -2,8 +2,8 @@
 cuda_b200 backend (Python surface -> ctypes -> C ABI -> sm_100a kernels)."""
 import torch
 
-from scratchpad_b200 import CudaB200AttnBackend, ForwardBatch, ForwardMode, compute_extend_start_loc
-from scratchpad_b200 import synth
+from scratchpad_b200 import CudaB200AttnBackend
+from harness import ForwardBatch, ForwardMode, compute_extend_start_loc, synth
 
 BF16_ABS, BF16_REL = 2e-2, 1e-2   # BASELINE.json north_star tolerance, bf16 KV
 FP8_ABS, FP8_REL = 5e-2, 5e-2     # fp8-e4m3 KV

@@ -8,6 +8,7 @@ import re
 import pytest
 import torch
 
+import harness
 import scratchpad_b200 as sb
 from scratchpad_b200 import _lib
 
@@ -112,7 +113,7 @@ def test_rotary_module_builds_the_reference_cache():
 
 
 def test_forward_mode_values_and_dispatch():
-    fm = sb.ForwardMode
+    fm = harness.ForwardMode
     assert (fm.EXTEND, fm.DECODE, fm.MIXED, fm.IDLE) == (1, 2, 3, 4)
     assert fm.MIXED.is_extend() and not fm.MIXED.is_decode() and fm.DECODE.is_cuda_graph()
 
@@ -121,7 +122,7 @@ def test_forward_mode_values_and_dispatch():
         def forward_decode(self, *a, **k): return "decode"
         def forward_extend(self, *a, **k): return "extend"
 
-    fb = sb.ForwardBatch(fm.MIXED, 1, torch.zeros(1), torch.zeros(1), torch.zeros(1))
+    fb = harness.ForwardBatch(fm.MIXED, 1, torch.zeros(1), torch.zeros(1), torch.zeros(1))
     assert Probe().forward(None, None, None, None, fb) == "extend"   # EXTEND and MIXED both go to extend
     fb.forward_mode = fm.DECODE
     assert Probe().forward(None, None, None, None, fb) == "decode"
@@ -134,11 +135,11 @@ def test_pool_layout_and_no_cpu_fallback():
     pool.set_kv_scales(1, 0.5, torch.tensor([0.25, 2.0]))
     ks, vs = pool.get_kv_scales(1)
     assert ks.tolist() == [0.5, 0.5] and vs.tolist() == [0.25, 2.0]
-    layer = sb.RadixAttention(4, 64, 0.125, 2, 0)
+    layer = harness.RadixAttention(4, 64, 0.125, 2, 0)
     with pytest.raises(RuntimeError):
         pool.set_kv_buffer(layer, torch.tensor([1]), torch.zeros(1, 2, 64, dtype=torch.bfloat16),
                            torch.zeros(1, 2, 64, dtype=torch.bfloat16))
-    alloc = sb.TokenToKVPoolAllocator(32, torch.bfloat16, "cpu", pool)
+    alloc = harness.TokenToKVPoolAllocator(32, torch.bfloat16, "cpu", pool)
     got = alloc.alloc(4)
     assert got.dtype == torch.int64 and got.tolist() == [1, 2, 3, 4]  # slot 0 is reserved
     with pytest.raises(NotImplementedError):
@@ -146,7 +147,7 @@ def test_pool_layout_and_no_cpu_fallback():
 
 
 def test_synth_page_table_properties():
-    from scratchpad_b200 import synth
+    from harness import synth
     gen = torch.Generator().manual_seed(0)
     r2t = torch.zeros((9, 300), dtype=torch.int32)
     lens = [260, 260, 290, 5]

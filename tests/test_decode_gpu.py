@@ -157,7 +157,8 @@ def test_kv_store_bit_exact_then_decode(kv):
     v_new = torch.randn((b, hkv, d), generator=gen).to(torch.bfloat16)
     loc = torch.stack([c["req_to_token"][c["req_pool_indices"][i], c["seq_lens"][i] - 1] for i in range(b)]).long()
     runner = G.make_runner_from_case(c["k_buf"], c["v_buf"], c["req_to_token"], kv_dtype, c["k_scale"], c["v_scale"], 32)
-    from scratchpad_b200 import CudaB200AttnBackend, ForwardBatch, ForwardMode, synth
+    from scratchpad_b200 import CudaB200AttnBackend
+    from harness import ForwardBatch, ForwardMode, synth
     backend = CudaB200AttnBackend(runner)
     layer = synth.make_layer(runner)
     fb = ForwardBatch(ForwardMode.DECODE, b, c["req_pool_indices"].cuda(), c["seq_lens"].cuda(), loc.cuda(),
@@ -186,7 +187,8 @@ def test_kv_store_bit_exact_then_decode(kv):
 def test_decode_under_cuda_graph_capture_and_replay():
     """Capture at a padded batch size with static int32 buffers, then replay twice with different
     sequence lengths after the replay hook (cuda_graph_runner.py:394-423,443-510)."""
-    from scratchpad_b200 import CudaB200AttnBackend, ForwardBatch, ForwardMode, synth
+    from scratchpad_b200 import CudaB200AttnBackend
+    from harness import ForwardBatch, ForwardMode, synth
     hq, hkv, d, bs = 32, 8, 64, 8
     lens_a = [100, 200, 17, 64, 1, 1, 1, 1]
     lens_b = [31, 500, 333, 128, 250, 1, 1, 1]
@@ -224,7 +226,8 @@ def test_decode_under_cuda_graph_capture_and_replay():
 
 
 def test_unsupported_configs_raise():
-    from scratchpad_b200 import CudaB200AttnBackend, synth
+    from scratchpad_b200 import CudaB200AttnBackend
+    from harness import synth
     runner = synth.make_model_runner(32, 8, 96, pool_tokens=64, max_reqs=4, context_len=64)
     with pytest.raises(_lib.B200AttnError):
         CudaB200AttnBackend(runner)
@@ -326,7 +329,8 @@ def test_decode_cascade_logit_cap_and_int32_indices():
 def test_decode_cascade_under_cuda_graph_with_padded_rows():
     """One captured graph serves a batch that shares a prefix (cascade on, detected on device), with the rows the
     graph runner pads the batch with (seq_len = fill value, req_pool_index 0), and then a batch that shares nothing."""
-    from scratchpad_b200 import CudaB200AttnBackend, ForwardBatch, ForwardMode, synth
+    from scratchpad_b200 import CudaB200AttnBackend
+    from harness import ForwardBatch, ForwardMode, synth
     hq, hkv, d, bs, real = 32, 8, 128, 24, 20
     shared = 1300
     lens_shared = [shared + 3 + 11 * i for i in range(real)]

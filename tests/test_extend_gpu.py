@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 if torch.cuda.is_available():
     import gpu_util as G
-    from scratchpad_b200 import ForwardMode
+    from harness import ForwardMode
 
 
 def _oracle(c, logit_cap=0.0):

@@ -5,7 +5,8 @@ import pytest
 import torch
 
 from oracle import attn_oracle as O
-from scratchpad_b200 import CudaB200AttnBackend, ForwardBatch, ForwardMode, _lib, synth
+from scratchpad_b200 import CudaB200AttnBackend, _lib
+from harness import ForwardBatch, ForwardMode, synth
 
 pytestmark = pytest.mark.gpu
 

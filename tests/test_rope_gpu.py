@@ -7,7 +7,8 @@ import torch
 from oracle import attn_oracle as O
 from oracle import rope_oracle as R
 from golden_util import golden_names, load_golden
-from scratchpad_b200 import ForwardBatch, ForwardMode, CudaB200AttnBackend, synth
+from scratchpad_b200 import CudaB200AttnBackend
+from harness import ForwardBatch, ForwardMode, synth
 from scratchpad_b200.rotary_embedding import RotaryEmbedding, get_rope
 
 import gpu_util as G

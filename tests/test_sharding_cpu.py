@@ -78,7 +78,7 @@ def test_paged_allocator_and_table_keep_the_page_invariant():
     between requests except whole pages of a common prefix, page 0 never handed out."""
     import torch
     import scratchpad_b200 as sb
-    from scratchpad_b200 import synth
+    from harness import synth
 
     ps = 16
     gen = torch.Generator().manual_seed(0)

@@ -7,7 +7,7 @@ import torch
 
 sys.path.insert(0, ".")
 import bench  # noqa: E402
-from scratchpad_b200 import ForwardMode  # noqa: E402
+from harness import ForwardMode  # noqa: E402
 
 sys.argv = ["bench.py", "--workload", sys.argv[1] if len(sys.argv) > 1 else "C2"]
 args = bench.parse_args()

@@ -74,6 +74,30 @@ static inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
   return B200_OK;
 }
 
+// ---- per-device one-time function attributes ------------------------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and occupancy are properties of (kernel, device): a process that
+// drives several GPUs (one backend instance per device) must set / query them once per device, not once per process.
+constexpr int kMaxDevices = 64;
+struct PerDevice {
+  bool attr_done[kMaxDevices] = {};
+  int occupancy[kMaxDevices] = {};  // 0 = not queried yet
+};
+static inline int current_device(int* dev) {
+  B200_CUDA_TRY(cudaGetDevice(dev));
+  if (*dev < 0 || *dev >= kMaxDevices) return B200_ERR_UNSUPPORTED;
+  return B200_OK;
+}
+template <class K>
+static inline int ensure_smem_attr(K kern, int smem_bytes, PerDevice& pd) {
+  int dev = 0;
+  if (int rc = current_device(&dev)) return rc;
+  if (!pd.attr_done[dev]) {
+    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    pd.attr_done[dev] = true;
+  }
+  return B200_OK;
+}
+
 // ---- PTX wrappers ------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -36,11 +36,15 @@
 
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
+#include <cstring>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace b200 {
 
 constexpr int kStages = 3;
+constexpr int kPartsPerSlot = 1;  // partials per (cta, request): the token sub-slices of a tile are combined inside the CTA
 constexpr int kPlanMagic = 0x62323030;  // "b200"
 constexpr int kHdrInts = 16;
 // header words: 0 total tiles, 1 tiles per CTA, 2 CTAs used, 3 bs, 4 tile tokens, 5 grid, 6 magic,
@@ -76,8 +80,11 @@ static WsLayout ws_layout(int max_bs, int grid, int nsub, int hq, int dv) {
   off = align_up(off + nparts * sizeof(float), 256);
   L.part_o = off;
   off = align_up(off + nparts * dv * sizeof(float), 256);
-  // shared-prefix ("cascade") partials: [split, request, q head]
-  const size_t ncas = (size_t)kMaxCasSplits * max_bs * hq;
+  // shared-prefix ("cascade") partials: [split, request, q head], indexed with a stride of bs (not max_bs); the
+  // cascade only runs for bs <= kMaxGroupBs, so a backend sized for thousands of request rows does not pin
+  // kMaxCasSplits * max_bs * hq * dv floats it can never use
+  const int cas_bs = max_bs < kMaxGroupBs ? max_bs : kMaxGroupBs;
+  const size_t ncas = (size_t)kMaxCasSplits * cas_bs * hq;
   L.cas_lse = off;
   off = align_up(off + ncas * sizeof(float), 256);
   L.cas_o = off;
@@ -85,7 +92,7 @@ static WsLayout ws_layout(int max_bs, int grid, int nsub, int hq, int dv) {
   size_t* ints[] = {&L.shared32, &L.perm, &L.grp_of, &L.grp_min, &L.grp_size, &L.grp_fin, &L.ct_first, &L.ct_cnt, &L.ct_leader, &L.ct_shared};
   for (size_t* f : ints) {
     *f = off;
-    off = align_up(off + (size_t)max_bs * sizeof(int), 16);
+    off = align_up(off + (size_t)cas_bs * sizeof(int), 16);
   }
   L.total = align_up(off, 256);
   return L;
@@ -336,6 +343,7 @@ struct DecodeArgs {
   float* part_o;
   float* part_lse;
   int hq, hkv, g;
+  int bs;  // what the caller says the batch is; must equal what the plan in the workspace was made for
   float sm_scale, logit_cap;
   const float* k_scale;
   const float* v_scale;
@@ -491,7 +499,11 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
   pdl_launch_dependents();  // let the merge grid get scheduled behind us; it waits for our completion
   DEC_TRACE(1);
 
-  const int total = __ldg(a.hdr + 0), tpc = __ldg(a.hdr + 1), bs = __ldg(a.hdr + 3);
+  const int total = __ldg(a.hdr + 0), tpc = __ldg(a.hdr + 1);
+  // Belt and braces behind the host-side B200_ERR_NOT_PLANNED check (a graph replayed without its plan refresh, a
+  // workspace overwritten by someone else): without a plan for exactly this batch there is nothing safe to read.
+  // The merge kernel makes the same test and writes NaN, so the failure is visible in the output.
+  if (__ldg(a.hdr + 6) != kPlanMagic || __ldg(a.hdr + 3) != a.bs) return;
   const int gt_begin = cta * tpc;
   const int gt_end = min(gt_begin + tpc, total);
   if (gt_begin >= gt_end) return;
@@ -729,12 +741,58 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
     }
   };
 
-  // one partial per (cta, request, sub-slice): slot = cta + b is unique along the
-  // monotone staircase of (cta, request) pairs.  (A fused "last CTA to arrive merges" variant was
-  // measured in round 1 and was slower -- 184 vs 169 us at C2: the fence + atomic round trip + merge
-  // reads stall the copy pipeline at every request boundary -- so the merge stays a separate,
-  // programmatically-dependent launch.)
-  auto flush = [&](int b) {
+  // one partial per (cta, request): slot = cta + b is unique along the monotone staircase of (cta, request)
+  // pairs.  (A fused "last CTA to arrive merges" variant was measured in round 1 and was slower -- 184 vs 169 us
+  // at C2: the fence + atomic round trip + merge reads stall the copy pipeline at every request boundary -- so the
+  // merge stays a separate, programmatically-dependent launch.)
+  // With several token sub-slices per tile (NSUB > 1: the one- and two-head CTAs of tensor-parallel shards) the
+  // NSUB softmax states of a head are first combined inside the CTA: a tree over the sub-slice index through the
+  // ring stage that has just been consumed (free until the next iteration's copy is issued into it).  Partner warps
+  // hold the same (head, dim) fragment in the same lane, so the exchange is lane-local: no shuffles, log2(NSUB)
+  // rounds, and the workspace and the merge kernel see ONE partial per (cta, request) instead of NSUB.
+  auto flush = [&](int b, int free_stage) {
+    if constexpr (C::NSUB > 1) {
+      constexpr int kStateF = C::MT * 4 + 4;  // floats of softmax state per lane: o, m[2], l[2]
+      static_assert((C::NSUB / 2) * HPC * kStateF * 32 * 4 <= C::STAGE_BYTES, "reduction scratch must fit one ring stage");
+      float* red = reinterpret_cast<float*>(smem + free_stage * C::STAGE_BYTES);
+#pragma unroll
+      for (int half = C::NSUB / 2; half >= 1; half >>= 1) {
+        __syncthreads();  // round 1: every warp is done reading the stage; later rounds: the previous round's reads
+        if (w_sub >= half && w_sub < 2 * half) {
+          float* dst = red + (static_cast<size_t>((w_sub - half) * HPC + w_head) * kStateF) * 32 + lane;
+#pragma unroll
+          for (int mt = 0; mt < C::MT; ++mt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dst[(mt * 4 + e) * 32] = o[mt][e];
+          dst[(C::MT * 4 + 0) * 32] = m[0];
+          dst[(C::MT * 4 + 1) * 32] = m[1];
+          dst[(C::MT * 4 + 2) * 32] = l[0];
+          dst[(C::MT * 4 + 3) * 32] = l[1];
+        }
+        __syncthreads();
+        if (w_sub < half) {
+          const float* src = red + (static_cast<size_t>(w_sub * HPC + w_head) * kStateF) * 32 + lane;
+          const float pm0 = src[(C::MT * 4 + 0) * 32], pm1 = src[(C::MT * 4 + 1) * 32];
+          const float mn0 = fmaxf(m[0], pm0), mn1 = fmaxf(m[1], pm1);
+          // a slice that saw no token has m = -inf (and l = 0, o = 0): weight 0, never exp2(-inf - -inf)
+          const float a0 = m[0] == -INFINITY ? 0.f : ex2(m[0] - mn0), a1 = m[1] == -INFINITY ? 0.f : ex2(m[1] - mn1);
+          const float b0 = pm0 == -INFINITY ? 0.f : ex2(pm0 - mn0), b1 = pm1 == -INFINITY ? 0.f : ex2(pm1 - mn1);
+#pragma unroll
+          for (int mt = 0; mt < C::MT; ++mt) {
+            o[mt][0] = o[mt][0] * a0 + src[(mt * 4 + 0) * 32] * b0;
+            o[mt][1] = o[mt][1] * a1 + src[(mt * 4 + 1) * 32] * b1;
+            o[mt][2] = o[mt][2] * a0 + src[(mt * 4 + 2) * 32] * b0;
+            o[mt][3] = o[mt][3] * a1 + src[(mt * 4 + 3) * 32] * b1;
+          }
+          l[0] = l[0] * a0 + src[(C::MT * 4 + 2) * 32] * b0;
+          l[1] = l[1] * a1 + src[(C::MT * 4 + 3) * 32] * b1;
+          m[0] = mn0;
+          m[1] = mn1;
+        }
+      }
+      if constexpr (PAGED) tma_bits &= ~(1u << free_stage);  // generic-proxy writes: the next TMA fill of this stage fences
+      if (w_sub != 0) return;
+    }
     float l0 = l[0], l1 = l[1];
 #pragma unroll
     for (int x = 4; x < 32; x <<= 1) {
@@ -742,7 +800,7 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
       l1 += __shfl_xor_sync(0xffffffffu, l1, x);
     }
     const float inv0 = l0 > 0.f ? vs / l0 : 0.f, inv1 = l1 > 0.f ? vs / l1 : 0.f;
-    const int64_t slot = static_cast<int64_t>(cta + b) * C::NSUB + w_sub;
+    const int64_t slot = cta + b;
     const int n0 = 2 * cid, n1 = 2 * cid + 1;  // q-head index inside the group
     const int64_t pi0 = slot * a.hq + kvh * G + n0;
     const int64_t pi1 = pi0 + 1;
@@ -817,7 +875,7 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
     const bool req_done = (cc.gt + 1 >= cc.gt_end) || (cc.gt + 1 >= cc.b_end);
     cursor_advance(cc, a);
     if (req_done) {
-      flush(b_cur);
+      flush(b_cur, stage);
       if (cursor_valid(cc)) {
         reset_state();
         load_q(cc.b);
@@ -862,6 +920,12 @@ __global__ void __launch_bounds__(256, 4) merge_kernel(const int* __restrict__ h
   if (pair >= bs * hq) return;
   const int b = pair / hq, h = pair % hq;
   const int tpc = __ldg(hdr + 1);
+  if (__ldg(hdr + 6) != kPlanMagic || __ldg(hdr + 3) != bs) {  // no plan for this batch in the workspace: poison o
+    __nv_bfloat16* bad = o + static_cast<int64_t>(b) * o_st + static_cast<int64_t>(h) * o_sh + lane * (DV / 32);
+#pragma unroll
+    for (int j = 0; j < DV / 32; ++j) bad[j] = __ushort_as_bfloat16(0x7fc0);
+    return;
+  }
   const int t0 = __ldg(tile_off + b), t1 = __ldg(tile_off + b + 1);
   // partials of the shared-prefix leg (one per KV split), present when the plan found a shared prefix
   const int ncas = (cas_splits > 0 && __ldg(shared32 + b) > 0) ? cas_splits : 0;
@@ -1046,15 +1110,12 @@ struct DeviceInfo {
   int num_sms = 0;
 };
 static int device_info(DeviceInfo* di) {
-  static int cached_dev = -1;
-  static DeviceInfo cached;
+  static DeviceInfo cached[kMaxDevices];
   int dev = 0;
-  B200_CUDA_TRY(cudaGetDevice(&dev));
-  if (dev != cached_dev) {
-    B200_CUDA_TRY(cudaDeviceGetAttribute(&cached.num_sms, cudaDevAttrMultiProcessorCount, dev));
-    cached_dev = dev;
-  }
-  *di = cached;
+  if (int rc = current_device(&dev)) return rc;
+  if (cached[dev].num_sms == 0)
+    B200_CUDA_TRY(cudaDeviceGetAttribute(&cached[dev].num_sms, cudaDevAttrMultiProcessorCount, dev));
+  *di = cached[dev];
   return B200_OK;
 }
 
@@ -1095,33 +1156,105 @@ static int encode_pool_map(CUtensorMap* out, const void* buf, int64_t stride_t_b
   return r == CUDA_SUCCESS ? B200_OK : B200_ERR_INVALID;
 }
 
+// The two maps of a layer's pool depend only on (buffer, stride, rows, shape, tile): encoded once and kept, so a
+// layer-call over a paged pool does no driver work on the host after the first one.
+struct MapKey {
+  const void* buf;
+  int64_t stride_t_bytes, rows;
+  int hkv, d, fp8, tile_tokens, hpc, dev;
+};
+struct MapSlot {
+  MapKey key;
+  CUtensorMap map;
+  bool used = false;
+};
+static int cached_pool_map(CUtensorMap* out, const void* buf, int64_t stride_t_bytes, int64_t rows, int hkv, int d, bool fp8,
+                           int tile_tokens, int hpc) {
+  constexpr int kSlots = 1024;  // direct-mapped: K and V of a few hundred layers
+  static MapSlot slots[kSlots];
+  static std::mutex mu;
+  int dev = 0;
+  if (int rc = current_device(&dev)) return rc;
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.buf = buf; key.stride_t_bytes = stride_t_bytes; key.rows = rows;
+  key.hkv = hkv; key.d = d; key.fp8 = fp8; key.tile_tokens = tile_tokens; key.hpc = hpc; key.dev = dev;
+  const uint64_t h = (reinterpret_cast<uint64_t>(buf) >> 8) * 0x9E3779B97F4A7C15ull;
+  MapSlot& s = slots[(h >> 40) % kSlots];
+  std::lock_guard<std::mutex> lock(mu);
+  if (!s.used || memcmp(&s.key, &key, sizeof(key)) != 0) {
+    if (int rc = encode_pool_map(&s.map, buf, stride_t_bytes, rows, hkv, d, fp8, tile_tokens, hpc)) {
+      s.used = false;
+      return rc;
+    }
+    s.key = key;
+    s.used = true;
+  }
+  *out = s.map;
+  return B200_OK;
+}
+
+// Which workspaces hold a plan, and for what: b200_attn_plan records it, b200_attn_decode refuses a workspace that
+// was never planned, or was planned for another batch size / shape / cascade setting (B200_ERR_NOT_PLANNED).  Host
+// bookkeeping only -- no sync; the kernels re-check the plan header on device.
+struct PlanRecord {
+  const void* ws = nullptr;
+  int bs = 0, hq = 0, hkv = 0, d = 0, kv_dtype = 0, cascade = 0, max_bs = 0;
+};
+constexpr int kPlanSlots = 64;
+static PlanRecord g_plans[kPlanSlots];
+static int g_plan_next = 0;
+static std::mutex g_plan_mu;
+static void plan_record(const PlanRecord& r) {
+  std::lock_guard<std::mutex> lock(g_plan_mu);
+  for (int i = 0; i < kPlanSlots; ++i)
+    if (g_plans[i].ws == r.ws) {
+      g_plans[i] = r;
+      return;
+    }
+  g_plans[g_plan_next] = r;
+  g_plan_next = (g_plan_next + 1) % kPlanSlots;
+}
+static bool plan_matches(const PlanRecord& r) {
+  std::lock_guard<std::mutex> lock(g_plan_mu);
+  for (int i = 0; i < kPlanSlots; ++i) {
+    const PlanRecord& x = g_plans[i];
+    if (x.ws == r.ws)
+      return x.bs == r.bs && x.hq == r.hq && x.hkv == r.hkv && x.d == r.d && x.kv_dtype == r.kv_dtype &&
+             x.cascade == r.cascade && x.max_bs == r.max_bs;
+  }
+  return false;
+}
+
 static int g_last_tma_mode = 0;  // test / bench introspection: 0 row gather only, 1 TMA for tiles of consecutive slots
 
 template <class C>
 static int launch_decode_t(const DecodeArgs& a, const PagedMaps* maps, int grid_x, int grid_y, cudaStream_t st, bool query_only,
                            int* occ_out) {
-  static bool attr_set = false;  // per instantiation
+  static PerDevice pd;  // per instantiation: shared-memory attribute and occupancy, remembered per device
+  auto prepare = [&](auto kern) -> int {
+    if (int rc = ensure_smem_attr(kern, C::SMEM_BYTES, pd)) return rc;
+    if (query_only) {
+      int dev = 0;
+      if (int rc = current_device(&dev)) return rc;
+      if (pd.occupancy[dev] == 0) {
+        int occ = 0;
+        B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, C::SMEM_BYTES));
+        pd.occupancy[dev] = occ > 0 ? occ : -1;
+      }
+      *occ_out = pd.occupancy[dev] > 0 ? pd.occupancy[dev] : 0;
+    }
+    return B200_OK;
+  };
   if constexpr (C::PAGED) {
     auto kern = decode_paged_kernel<C>;
-    if (!attr_set) {
-      B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-      attr_set = true;
-    }
-    if (query_only) {
-      B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, C::NT, C::SMEM_BYTES));
-      return B200_OK;
-    }
+    if (int rc = prepare(kern)) return rc;
+    if (query_only) return B200_OK;
     return launch_pdl(kern, dim3(grid_x, grid_y), dim3(C::NT), C::SMEM_BYTES, st, a, maps->k, maps->v);
   } else {
     auto kern = decode_mma_kernel<C>;
-    if (!attr_set) {
-      B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-      attr_set = true;
-    }
-    if (query_only) {
-      B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, C::NT, C::SMEM_BYTES));
-      return B200_OK;
-    }
+    if (int rc = prepare(kern)) return rc;
+    if (query_only) return B200_OK;
     return launch_pdl(kern, dim3(grid_x, grid_y), dim3(C::NT), C::SMEM_BYTES, st, a);
   }
 }
@@ -1182,7 +1315,7 @@ static int get_config(int max_bs, int hq, int hkv, int d, int dv, int kv_dtype, 
   out->stages = kStages;
   out->smem_bytes = kStages * 2 * kc.hpc * out->tile_tokens * d * elt;
   out->num_sms = di.num_sms;
-  out->workspace_bytes = ws_layout(max_bs, gx, out->sub_splits, hq, dv).total;
+  out->workspace_bytes = ws_layout(max_bs, gx, kPartsPerSlot, hq, dv).total;
   return B200_OK;
 }
 
@@ -1213,7 +1346,7 @@ const char* b200_attn_error_string(int code) {
     case B200_ERR_INVALID: return "invalid argument (null pointer, bad size or misaligned stride)";
     case B200_ERR_UNSUPPORTED: return "unsupported configuration (head_dim must be 64 or 128 with d == dv, group size <= 8, kv dtype bf16 or fp8-e4m3)";
     case B200_ERR_WORKSPACE: return "workspace too small for this configuration";
-    case B200_ERR_NOT_PLANNED: return "workspace has not been planned (call b200_attn_plan first)";
+    case B200_ERR_NOT_PLANNED: return "workspace holds no plan for this batch (call b200_attn_plan with the same bs, shape and cascade flag first)";
     default:
       if (code >= 1000) return cudaGetErrorString(static_cast<cudaError_t>(code - 1000));
       return "unknown error";
@@ -1249,7 +1382,7 @@ int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs, co
   int rc = get_config(max_bs, hq, hkv, d, dv, kv_dtype, force_path, &cfg);
   if (rc) return rc;
   if (workspace_bytes < cfg.workspace_bytes) return B200_ERR_WORKSPACE;
-  const WsLayout L = ws_layout(max_bs, cfg.grid_ctas, cfg.sub_splits, hq, dv);
+  const WsLayout L = ws_layout(max_bs, cfg.grid_ctas, kPartsPerSlot, hq, dv);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int use_cascade = cascade && bs <= kMaxGroupBs && cascade_supported(bs, hq, hkv, d, dv, kv_dtype);
@@ -1281,6 +1414,10 @@ int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs, co
       reinterpret_cast<int*>(ws + L.req_idx), reinterpret_cast<int*>(ws + L.cta_b0), req_pool_indices, seq_lens, idx_dtype == B200_IDX_I64, bs,
       cfg.tile_tokens, cfg.grid_ctas, cp);
   B200_CUDA_TRY(cudaGetLastError());
+  PlanRecord rec;
+  rec.ws = workspace; rec.bs = bs; rec.hq = hq; rec.hkv = hkv; rec.d = d; rec.kv_dtype = kv_dtype;
+  rec.cascade = cascade != 0; rec.max_bs = max_bs;
+  plan_record(rec);
   return B200_OK;
 }
 
@@ -1301,7 +1438,13 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
   rc = get_config(p->max_bs, p->hq, p->hkv, p->d, p->dv, p->kv_dtype, p->force_path, &cfg);
   if (rc) return rc;
   if (p->workspace_bytes < cfg.workspace_bytes) return B200_ERR_WORKSPACE;
-  const WsLayout L = ws_layout(p->max_bs, cfg.grid_ctas, cfg.sub_splits, p->hq, p->dv);
+  {
+    PlanRecord rec;
+    rec.ws = p->workspace; rec.bs = p->bs; rec.hq = p->hq; rec.hkv = p->hkv; rec.d = p->d; rec.kv_dtype = p->kv_dtype;
+    rec.cascade = p->cascade != 0; rec.max_bs = p->max_bs;
+    if (!plan_matches(rec)) return B200_ERR_NOT_PLANNED;
+  }
+  const WsLayout L = ws_layout(p->max_bs, cfg.grid_ctas, kPartsPerSlot, p->hq, p->dv);
   uint8_t* ws = static_cast<uint8_t*>(p->workspace);
   DecodeArgs a;
   a.q = static_cast<const __nv_bfloat16*>(p->q);
@@ -1323,6 +1466,7 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
   a.hq = p->hq;
   a.hkv = p->hkv;
   a.g = p->hq / p->hkv;
+  a.bs = p->bs;
   a.sm_scale = p->sm_scale;
   a.logit_cap = p->logit_cap;
   a.k_scale = p->k_scale;
@@ -1367,8 +1511,8 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
     // row gather over a paged table gains the pages' DRAM locality by itself.  So: TMA when a page covers the tile,
     // the row gather (correct on any table: one slot id per token) otherwise.
     if (ps >= cfg.tile_tokens) {
-      rc = encode_pool_map(&maps.k, p->k_buf, a.k_st_bytes, p->kv_pool_rows, p->hkv, p->d, kc.fp8, cfg.tile_tokens, kc.hpc);
-      if (!rc) rc = encode_pool_map(&maps.v, p->v_buf, a.v_st_bytes, p->kv_pool_rows, p->hkv, p->dv, kc.fp8, cfg.tile_tokens, kc.hpc);
+      rc = cached_pool_map(&maps.k, p->k_buf, a.k_st_bytes, p->kv_pool_rows, p->hkv, p->d, kc.fp8, cfg.tile_tokens, kc.hpc);
+      if (!rc) rc = cached_pool_map(&maps.v, p->v_buf, a.v_st_bytes, p->kv_pool_rows, p->hkv, p->dv, kc.fp8, cfg.tile_tokens, kc.hpc);
       if (!rc) mp = &maps;
       else if (rc != B200_ERR_INVALID) return rc;  // a driver that refuses the map: row gather
     }
@@ -1383,11 +1527,11 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
     return launch_pdl(merge_kernel<64>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
                       static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
                       static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
-                      static_cast<int>(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
+                      kPartsPerSlot, static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
   return launch_pdl(merge_kernel<128>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
                     static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
                     static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
-                    static_cast<int>(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
+                    kPartsPerSlot, static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
 }
 
 #ifdef B200_DEC_TRACE

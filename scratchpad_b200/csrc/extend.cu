@@ -371,11 +371,8 @@ __global__ void __launch_bounds__(kExtNT, 1) extend_mma_kernel(const ExtendArgs 
 template <class C>
 static int launch_extend_t(const ExtendArgs& a, dim3 grid, cudaStream_t st) {
   auto kern = extend_mma_kernel<C>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDevice pd;  // per instantiation
+  if (int rc = ensure_smem_attr(kern, C::SMEM_BYTES, pd)) return rc;
   return launch_pdl(kern, grid, dim3(kExtNT), C::SMEM_BYTES, st, a);
 }
 

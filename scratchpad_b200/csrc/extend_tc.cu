@@ -964,11 +964,8 @@ extern "C" int b200_debug_tc_trace_read(long long* host_dst) {
 template <int MODE, bool F16, int D>
 static int launch_tc(const tc::Args& a, dim3 grid, cudaStream_t st) {
   auto kern = tc::extend_tc_kernel<MODE, F16, D>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
-    attr_set = true;
-  }
+  static PerDevice pd;  // per instantiation
+  if (int rc = ensure_smem_attr(kern, tc::kSmemBytes, pd)) return rc;
   return launch_pdl(kern, grid, dim3(tc::kThreads), tc::kSmemBytes, st, a);
 }
 

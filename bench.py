@@ -61,8 +61,9 @@ def parse_args():
                          "is on).  auto = what an operator would set for the deployment the workload stands for: on when "
                          "its requests share a prompt prefix (C3), off otherwise -- an idle cascade costs one early-exit "
                          "launch (~2 us) per layer-call")
-    ap.add_argument("--force-path", default="auto", choices=["auto", "mma", "tc"],
-                    help="extend workloads: kernel family (mma = legacy mma.sync kernel, tc = tcgen05/TMEM kernel)")
+    ap.add_argument("--force-path", default="auto", choices=["auto", "mma", "tc", "tc2"],
+                    help="extend workloads: kernel family (mma = legacy mma.sync kernel, tc = tcgen05/TMEM kernel, one CTA "
+                         "per tile, tc2 = the opt-in CTA-pair tcgen05 kernel)")
     ap.add_argument("--rope", default="off", choices=["off", "separate", "fused"],
                     help="decode only: include the model's rotary embedding in the layer-call -- 'separate' = the "
                          "reference's sequence rotary_emb(positions, q, k) then attention (llama.py:149-152), 'fused' = "
@@ -573,7 +574,7 @@ def measure_extend(args, rank, world, local_rank, dist, K, W, want_e2e=True, wan
                                      max_reqs=w.batch, context_len=w.prefix_len + w.extend_len + 1,
                                      kv_dtype=w.kv_dtype, device=str(dev))
     fill_pool(runner.token_to_kv_pool, 1000 + rank % max(world, 1))
-    backend = CudaB200AttnBackend(runner, force_path={"auto": -1, "mma": 0, "tc": 1}[args.force_path])
+    backend = CudaB200AttnBackend(runner, force_path={"auto": -1, "mma": 0, "tc": 1, "tc2": 2}[args.force_path])
     gen = torch.Generator().manual_seed(args.seed)
     fb = synth.make_extend_batch(runner, pre, ext, gen, mode=args.index_mode, backend=backend)
     layers = [synth.make_layer(runner, i) for i in range(L)]

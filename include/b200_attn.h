@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define B200_ATTN_ABI_VERSION 8
+#define B200_ATTN_ABI_VERSION 9
 
 /* kv_dtype */
 #define B200_KV_BF16 0
@@ -49,7 +49,10 @@ extern "C" {
 #define B200_IDX_I64 1
 /* compute path (b200_attn_config.path) */
 #define B200_PATH_MMA 0  /* GQA-packed register-level tensor-core path (mma.sync m16n8k16): decode, generic extend */
-#define B200_PATH_TC 1   /* extend only: tcgen05 + TMEM path (head_dim 128, bf16 or fp8 pool; head_dim 64, bf16 pool) */
+#define B200_PATH_TC 1   /* extend only: tcgen05 + TMEM path, one CTA per 256-row tile (head_dim 128, bf16 or fp8 pool; head_dim 64,
+                          * bf16 pool) */
+#define B200_PATH_TC2 2  /* extend only: tcgen05 cta_group::2 path, CTA pairs (head_dim 128 over a bf16 pool).  Opt-in: correct
+                          * and tested, measured slower than B200_PATH_TC */
 
 /* error codes (cuda errors are reported as 1000 + cudaError_t) */
 #define B200_OK 0
@@ -245,6 +248,11 @@ int b200_debug_gather(const void* buf, int64_t stride_t_bytes, int32_t row_bytes
 /* Test / bench introspection: how the last b200_attn_decode call of this process fetched KV tiles --
  * 0 row gather only, 1 TMA (one box per K / V tile) for every tile whose slots are consecutive, row gather for the rest. */
 int b200_debug_last_tma_mode(void);
+
+/* Test hook (synchronises the device): KV tiles the decode kernels fetched by TMA box copies on the current device
+ * since the last call with reset != 0 (-1 on a CUDA error).  b200_debug_last_tma_mode() says the TMA-capable kernel
+ * was launched; this says how often its TMA branch was actually taken. */
+int64_t b200_debug_tma_tiles(int32_t reset);
 
 /* Debug check of the paged-table contract (b200_decode_params.page_size): writes to *violations (device int32)
  * the number of positions t < seq_lens[i] with req_to_token[r_i, t] != page_start + t % page_size, page_start =

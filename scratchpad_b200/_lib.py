@@ -16,11 +16,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200_ATTN_LIB") or os.path.join(_HERE, "csrc", "libb200attn.so")
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 KV_BF16, KV_FP8_E4M3 = 0, 1
 IDX_I32, IDX_I64 = 0, 1
-PATH_AUTO, PATH_MMA, PATH_TC = -1, 0, 1
+PATH_AUTO, PATH_MMA, PATH_TC, PATH_TC2 = -1, 0, 1, 2
 CACHE_BF16, CACHE_F32 = 0, 1
 PAGE_AUTO = -1
 
@@ -37,6 +37,7 @@ EXPORTS = (
     "b200_kv_store",
     "b200_rope_kv_store",
     "b200_debug_last_tma_mode",
+    "b200_debug_tma_tiles",
     "b200_debug_check_paged",
     "b200_debug_gather",
     "b200_debug_decode_naive",
@@ -170,6 +171,8 @@ def load() -> C.CDLL:
     lib.b200_debug_decode_naive.argtypes = [C.POINTER(DecodeParams), vp, vp, i32, vp]
     for name in EXPORTS[3:]:
         getattr(lib, name).restype = C.c_int
+    lib.b200_debug_tma_tiles.restype = C.c_int64
+    lib.b200_debug_tma_tiles.argtypes = [i32]
     _lib = lib
     return lib
 

@@ -124,8 +124,11 @@ class CudaB200AttnBackend(AttentionBackend):
         if cascade is None:
             cascade = bool(getattr(model_runner.server_args, "b200_shared_prefix_cascade", True))
         self.cascade = 1 if cascade else 0
+        # TMA for KV tiles whose slots are consecutive in the token-granular pool (an unfragmented allocator hands out
+        # runs, memory/pool.py:240-253): on by default -- a CTA whose first tile is scattered runs the pure row-gather
+        # loop at the plain kernel's speed, so the setting costs nothing on a fragmented pool
         if tma_contiguous_runs is None:
-            tma_contiguous_runs = bool(getattr(model_runner.server_args, "b200_tma_contiguous_runs", False))
+            tma_contiguous_runs = bool(getattr(model_runner.server_args, "b200_tma_contiguous_runs", True))
         self.tma_contiguous_runs = bool(tma_contiguous_runs)
         if getattr(model_runner, "sliding_window_size", None) not in (None, -1):
             raise NotImplementedError("cuda_b200 backend: sliding-window attention is not supported")

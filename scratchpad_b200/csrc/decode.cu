@@ -38,13 +38,28 @@
 
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 
 namespace b200 {
 
 constexpr int kStages = 3;
-constexpr int kPartsPerSlot = 1;  // partials per (cta, request): the token sub-slices of a tile are combined inside the CTA
+// Partials per (cta, request): the token sub-slices of a tile are combined inside the CTA, so one.  The two build
+// switches below exist for A/B measurements of exactly these two design decisions (tools/gpu_ab_lib.sh):
+//   -DB200_NO_CTA_REDUCE  every sub-slice flushes its own partial (round-1 behaviour)
+//   -DB200_ONE_LOOP       the TMA-capable kernel always runs its two-producer loop (round-1 behaviour)
+#ifdef B200_NO_CTA_REDUCE
+constexpr bool kCtaReduce = false;
+#else
+constexpr bool kCtaReduce = true;
+#endif
+#ifdef B200_ONE_LOOP
+constexpr bool kTwoLoops = false;
+#else
+constexpr bool kTwoLoops = true;
+#endif
+static inline int parts_per_slot(int sub_splits) { return kCtaReduce ? 1 : sub_splits; }
 constexpr int kPlanMagic = 0x62323030;  // "b200"
 constexpr int kHdrInts = 16;
 // header words: 0 total tiles, 1 tiles per CTA, 2 CTAs used, 3 bs, 4 tile tokens, 5 grid, 6 magic,
@@ -366,6 +381,8 @@ __device__ unsigned long long g_dec_trace[1024][6];
   } while (0)
 #endif
 
+__device__ unsigned long long g_tma_tiles;  // debug counter: KV tiles fetched by TMA box copies since the last reset
+
 struct Cursor {
   int gt, gt_end;  // global tile index / end of this CTA's range
   int b;           // request (batch row) the tile belongs to
@@ -530,11 +547,28 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
       slot_reg[j] = (j * 32 + lane < TN && t < c.seq_len) ? __ldg(c.row + t) : 0;
     }
   };
-  auto issue_tile = [&](const Cursor& c, int stage) {
+  // slots of the first `nvalid` tokens of the tile in slot_reg consecutive?  (one shuffle, one compare, one vote)
+  auto slots_consecutive = [&](int nvalid) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < C::NSLOT; ++j) {
+      int prev = __shfl_up_sync(0xffffffffu, slot_reg[j], 1);
+      if (j > 0) {
+        const int carry = __shfl_sync(0xffffffffu, slot_reg[j - 1], 31);
+        if (lane == 0) prev = carry;
+      }
+      const int t = j * 32 + lane;
+      ok = ok && (t >= nvalid || t == 0 || slot_reg[j] == prev + 1);
+    }
+    return __all_sync(0xffffffffu, ok);
+  };
+  int n_tma_tiles = 0;  // tiles this CTA fetched by TMA (debug counter, summed into g_tma_tiles at exit)
+  auto issue_tile = [&](auto tma_tag, const Cursor& c, int stage) {
+    constexpr bool TMA = decltype(tma_tag)::value;
     const int tok0 = (c.gt - c.b_begin) * TN;
     const uint32_t sk = smem_base + stage * C::STAGE_BYTES;
     const uint32_t sv = sk + C::TILE_BYTES;
-    if constexpr (PAGED) {
+    if constexpr (TMA) {
       // A tile that lies wholly inside the sequence and whose TN slots are consecutive (pages of >= TN tokens from a
       // paged allocator: slot = page * page_size + offset, request position t at offset t % page_size; or simply an
       // unfragmented token-granular allocator) is fetched by TMA: one box for K, one for V, issued by thread 0,
@@ -542,19 +576,7 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
       // shuffle, one vote), so the caller's page-size hint can cost speed but never correctness; any other tile --
       // the ragged last tile of a request included -- takes the row gather below (which zero-fills rows past the end;
       // the PV product relies on that).  The decision is remembered per stage for the consumer side.
-      constexpr int bt = TN;
-      bool ok = tok0 + TN <= c.seq_len;
-#pragma unroll
-      for (int j = 0; j < C::NSLOT; ++j) {
-        int prev = __shfl_up_sync(0xffffffffu, slot_reg[j], 1);
-        if (j > 0) {
-          const int carry = __shfl_sync(0xffffffffu, slot_reg[j - 1], 31);
-          if (lane == 0) prev = carry;
-        }
-        const int t = j * 32 + lane;
-        ok = ok && (t >= TN || (t & (bt - 1)) == 0 || slot_reg[j] == prev + 1);
-      }
-      const bool by_tma = __all_sync(0xffffffffu, ok);
+      const bool by_tma = tok0 + TN <= c.seq_len && slots_consecutive(TN);
       const bool prev_by_tma = (tma_bits >> stage) & 1u;  // how this ring stage was filled three tiles ago
       tma_bits = by_tma ? (tma_bits | (1u << stage)) : (tma_bits & ~(1u << stage));
       if (by_tma) {
@@ -568,6 +590,7 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
           // the whole K (V) tile is ONE box (all heads of the CTA, both column halves): two copies per tile
           tma_load_4d(sk, tmk, bar, 0, slot_reg[0], 0, h0);  // thread 0 holds the slot id of the tile's first token
           tma_load_4d(sv, tmv, bar, 0, slot_reg[0], 0, h0);
+          ++n_tma_tiles;
         }
         return;
       }
@@ -751,7 +774,7 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
   // hold the same (head, dim) fragment in the same lane, so the exchange is lane-local: no shuffles, log2(NSUB)
   // rounds, and the workspace and the merge kernel see ONE partial per (cta, request) instead of NSUB.
   auto flush = [&](int b, int free_stage) {
-    if constexpr (C::NSUB > 1) {
+    if constexpr (C::NSUB > 1 && kCtaReduce) {
       constexpr int kStateF = C::MT * 4 + 4;  // floats of softmax state per lane: o, m[2], l[2]
       static_assert((C::NSUB / 2) * HPC * kStateF * 32 * 4 <= C::STAGE_BYTES, "reduction scratch must fit one ring stage");
       float* red = reinterpret_cast<float*>(smem + free_stage * C::STAGE_BYTES);
@@ -800,7 +823,7 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
       l1 += __shfl_xor_sync(0xffffffffu, l1, x);
     }
     const float inv0 = l0 > 0.f ? vs / l0 : 0.f, inv1 = l1 > 0.f ? vs / l1 : 0.f;
-    const int64_t slot = cta + b;
+    const int64_t slot = kCtaReduce ? static_cast<int64_t>(cta + b) : static_cast<int64_t>(cta + b) * C::NSUB + w_sub;
     const int n0 = 2 * cid, n1 = 2 * cid + 1;  // q-head index inside the group
     const int64_t pi0 = slot * a.hq + kvh * G + n0;
     const int64_t pi1 = pi0 + 1;
@@ -824,11 +847,19 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
   };
 
   // ---- pipeline ---------------------------------------------------------------
-  prefetch_slots(pc);
+  // The tile loop exists in two copies inside the TMA-capable kernel: one that can fetch a tile either way (TMA box
+  // copy when its slots are consecutive, row gather otherwise) and one that only gathers rows -- the very loop of
+  // decode_mma_kernel.  A row gather inside the two-producer loop runs 6 % below its speed in a loop of its own
+  // (the second producer's code in the loop body changes how the gather is scheduled), so a CTA picks
+  // ONE copy for its whole tile range from what it sees in its first tile: consecutive slots (a paged pool, or an
+  // unfragmented token-granular allocator) -> the TMA-capable loop; scattered slots -> the pure row-gather loop, at
+  // the plain kernel's speed.  Either loop reads any table correctly; the choice is about speed only.
+  auto pipeline = [&](auto tma_tag) {
+  constexpr bool TMA = decltype(tma_tag)::value;
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) {
     if (cursor_valid(pc)) {
-      issue_tile(pc, s);
+      issue_tile(tma_tag, pc, s);
       cursor_advance(pc, a);
       if (cursor_valid(pc)) prefetch_slots(pc);
     }
@@ -842,27 +873,70 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
 #ifdef B200_DEC_TRACE
   bool first_tile = true;
 #endif
+  // Nested loops: the inner loop streams the tiles of ONE request inside this CTA's range and contains nothing but
+  // wait -> issue -> compute; the partial flush (with its in-CTA reduction) and the switch to the next request sit
+  // between two inner loops.  (-DB200_FLAT_LOOP keeps the round-1 single loop with the flush inside, for A/B.)
+#ifndef B200_FLAT_LOOP
+  while (cursor_valid(cc)) {
+    const int seg_end = min(cc.b_end, cc.gt_end);
+    int tok0 = (cc.gt - cc.b_begin) * TN + w_sub * 16;
+    int last_stage = stage;
+    for (; cc.gt < seg_end; ++cc.gt, tok0 += TN) {
+      cp_async_wait<kStages - 2>();
+      if constexpr (TMA) {
+        if ((tma_bits >> stage) & 1u) {  // the producer side fetched this stage's tile by TMA
+          mbar_wait(bar_base + 8 * stage, (phases >> stage) & 1u);
+          phases ^= 1u << stage;
+        }
+      }
+      __syncthreads();
+#ifdef B200_DEC_TRACE
+      if (first_tile) {
+        DEC_TRACE(3);
+        first_tile = false;
+      }
+#endif
+      {
+        int pstage = stage + kStages - 1;
+        if (pstage >= kStages) pstage -= kStages;
+        if (cursor_valid(pc)) {
+          issue_tile(tma_tag, pc, pstage);
+          cursor_advance(pc, a);
+          if (cursor_valid(pc)) prefetch_slots(pc);
+        }
+        cp_async_commit();
+      }
+      const int nvalid = min(16, cc.seq_len - tok0);
+      if (nvalid > 0) compute_tile(stage, nvalid);
+      last_stage = stage;
+      stage = stage + 1 == kStages ? 0 : stage + 1;
+    }
+    flush(cc.b, last_stage);
+    if (cc.gt < cc.gt_end) {  // next request with tiles in this CTA's range (requests without tiles are skipped)
+      do {
+        cc.b++;
+      } while (cc.gt >= __ldg(a.tile_off + cc.b + 1));
+      cursor_load_req(cc, a);
+      reset_state();
+      load_q(cc.b);
+    }
+  }
+#else
   while (cursor_valid(cc)) {
     cp_async_wait<kStages - 2>();
-    if constexpr (PAGED) {
+    if constexpr (TMA) {
       if ((tma_bits >> stage) & 1u) {  // the producer side fetched this stage's tile by TMA
         mbar_wait(bar_base + 8 * stage, (phases >> stage) & 1u);
         phases ^= 1u << stage;
       }
     }
     __syncthreads();
-#ifdef B200_DEC_TRACE
-    if (first_tile) {
-      DEC_TRACE(3);
-      first_tile = false;
-    }
-#endif
     {
       int pstage = stage + kStages - 1;
       if (pstage >= kStages) pstage -= kStages;
       if (cursor_valid(pc)) {
-        issue_tile(pc, pstage);
-          cursor_advance(pc, a);
+        issue_tile(tma_tag, pc, pstage);
+        cursor_advance(pc, a);
         if (cursor_valid(pc)) prefetch_slots(pc);
       }
       cp_async_commit();
@@ -882,6 +956,19 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
       }
     }
     stage = stage + 1 == kStages ? 0 : stage + 1;
+  }
+#endif
+  };  // pipeline
+
+  prefetch_slots(pc);
+  if constexpr (PAGED) {
+    // consecutive slots among the valid tokens of this CTA's first tile?  (a single valid token says nothing)
+    const int nvalid0 = min(TN, pc.seq_len - (pc.gt - pc.b_begin) * TN);
+    if (!kTwoLoops || (nvalid0 >= 2 && slots_consecutive(nvalid0))) pipeline(std::true_type{});
+    else pipeline(std::false_type{});
+    if (tid == 0 && n_tma_tiles) atomicAdd(&g_tma_tiles, static_cast<unsigned long long>(n_tma_tiles));
+  } else {
+    pipeline(std::false_type{});
   }
   DEC_TRACE(4);
   cp_async_wait<0>();
@@ -1315,7 +1402,7 @@ static int get_config(int max_bs, int hq, int hkv, int d, int dv, int kv_dtype, 
   out->stages = kStages;
   out->smem_bytes = kStages * 2 * kc.hpc * out->tile_tokens * d * elt;
   out->num_sms = di.num_sms;
-  out->workspace_bytes = ws_layout(max_bs, gx, kPartsPerSlot, hq, dv).total;
+  out->workspace_bytes = ws_layout(max_bs, gx, parts_per_slot(out->sub_splits), hq, dv).total;
   return B200_OK;
 }
 
@@ -1382,7 +1469,7 @@ int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs, co
   int rc = get_config(max_bs, hq, hkv, d, dv, kv_dtype, force_path, &cfg);
   if (rc) return rc;
   if (workspace_bytes < cfg.workspace_bytes) return B200_ERR_WORKSPACE;
-  const WsLayout L = ws_layout(max_bs, cfg.grid_ctas, kPartsPerSlot, hq, dv);
+  const WsLayout L = ws_layout(max_bs, cfg.grid_ctas, parts_per_slot(cfg.sub_splits), hq, dv);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int use_cascade = cascade && bs <= kMaxGroupBs && cascade_supported(bs, hq, hkv, d, dv, kv_dtype);
@@ -1444,7 +1531,7 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
     rec.cascade = p->cascade != 0; rec.max_bs = p->max_bs;
     if (!plan_matches(rec)) return B200_ERR_NOT_PLANNED;
   }
-  const WsLayout L = ws_layout(p->max_bs, cfg.grid_ctas, kPartsPerSlot, p->hq, p->dv);
+  const WsLayout L = ws_layout(p->max_bs, cfg.grid_ctas, parts_per_slot(cfg.sub_splits), p->hq, p->dv);
   uint8_t* ws = static_cast<uint8_t*>(p->workspace);
   DecodeArgs a;
   a.q = static_cast<const __nv_bfloat16*>(p->q);
@@ -1527,11 +1614,11 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
     return launch_pdl(merge_kernel<64>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
                       static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
                       static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
-                      kPartsPerSlot, static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
+                      parts_per_slot(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
   return launch_pdl(merge_kernel<128>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
                     static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
                     static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
-                    kPartsPerSlot, static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
+                    parts_per_slot(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
 }
 
 #ifdef B200_DEC_TRACE
@@ -1541,6 +1628,19 @@ int b200_debug_dec_trace_read(unsigned long long* host_dst) {
 #endif
 
 int b200_debug_last_tma_mode(void) { return g_last_tma_mode; }
+
+// Test hook (synchronises): number of KV tiles the decode kernels fetched by TMA box copies on the current device since
+// the last call with reset != 0; proves that the TMA branch is taken, not merely that the TMA-capable kernel ran.
+int64_t b200_debug_tma_tiles(int32_t reset) {
+  unsigned long long n = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(&n, g_tma_tiles, sizeof(n)) != cudaSuccess) return -1;
+  if (reset) {
+    const unsigned long long zero = 0;
+    if (cudaMemcpyToSymbol(g_tma_tiles, &zero, sizeof(zero)) != cudaSuccess) return -1;
+  }
+  return static_cast<int64_t>(n);
+}
 
 int b200_debug_check_paged(const int32_t* req_to_token, int64_t req_to_token_stride, const void* req_pool_indices,
                            const void* seq_lens, int32_t idx_dtype, int32_t bs, int32_t page_size, int32_t* violations,

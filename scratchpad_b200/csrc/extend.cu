@@ -376,7 +376,8 @@ static int launch_extend_t(const ExtendArgs& a, dim3 grid, cudaStream_t st) {
   return launch_pdl(kern, grid, dim3(kExtNT), C::SMEM_BYTES, st, a);
 }
 
-int launch_extend_tc(const b200_extend_params* p, cudaStream_t st);  // extend_tc.cu
+int launch_extend_tc(const b200_extend_params* p, cudaStream_t st);   // extend_tc.cu: one CTA per 256-row tile
+int launch_extend_tc2(const b200_extend_params* p, cudaStream_t st);  // extend_tc2.cu: CTA pairs (cta_group::2)
 
 }  // namespace b200
 
@@ -405,9 +406,18 @@ extern "C" int b200_attn_extend(const b200_extend_params* p, b200_stream_t strea
   // (k_new / v_new heads contiguous inside a token row, as in the fused qkv GEMM output)
   const bool tc_ok = (p->d == 128 || (p->d == 64 && !fp8)) && p->o_stride_t % 8 == 0 && p->o_stride_h % 8 == 0 && !mis16(p->o) && g <= 128 &&
                      p->kn_stride_h == p->d && p->vn_stride_h == p->dv;
+  const bool pair_ok = tc_ok && p->d == 128 && !fp8;
   if (p->force_path == B200_PATH_TC && !tc_ok) return B200_ERR_UNSUPPORTED;
-  if (tc_ok && (p->force_path == B200_PATH_TC || (p->force_path < 0 && static_cast<int64_t>(p->max_extend_len) * g >= 128)))
-    return launch_extend_tc(p, static_cast<cudaStream_t>(stream));
+  if (p->force_path == B200_PATH_TC2 && !pair_ok) return B200_ERR_UNSUPPORTED;
+  if (tc_ok && (p->force_path == B200_PATH_TC || p->force_path == B200_PATH_TC2 ||
+                (p->force_path < 0 && static_cast<int64_t>(p->max_extend_len) * g >= 128))) {
+    // The CTA-pair kernel (tcgen05 cta_group::2, extend_tc2.cu) is correct and tested but measured SLOWER than the
+    // one-CTA kernel (C4: 925 vs 1180 TFLOP/s), so it is opt-in: B200_PATH_TC2, or B200_EXTEND_PAIR=1 to
+    // make the automatic choice take it where it exists (head_dim 128 over a bf16 pool).
+    static const bool pair_auto = getenv("B200_EXTEND_PAIR") != nullptr && getenv("B200_EXTEND_PAIR")[0] == '1';
+    const bool pair = pair_ok && (p->force_path == B200_PATH_TC2 || (p->force_path < 0 && pair_auto));
+    return pair ? launch_extend_tc2(p, static_cast<cudaStream_t>(stream)) : launch_extend_tc(p, static_cast<cudaStream_t>(stream));
+  }
   ExtendArgs a;
   a.q = static_cast<const __nv_bfloat16*>(p->q);
   a.q_st = p->q_stride_t;

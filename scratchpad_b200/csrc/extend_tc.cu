@@ -39,6 +39,7 @@
 // K/V ring: 5 x 32 KiB slots (K_j, V_j alternate), mbarrier full (producers) / empty (tcgen05.commit).
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace b200 {
 namespace tc {
@@ -82,172 +83,6 @@ constexpr int kSmemBytes = kSmemTmemPtr + 16 + 1024;       // + alignment slack
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 384;
 constexpr float kRescaleThreshold = 8.0f;  // log2 domain
-constexpr uint32_t kSuspendHintNs = 20000;  // a waiting thread sleeps in hardware until the phase flips (or this long)
-
-// ---- PTX: mbarrier ------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity), "r"(kSuspendHintNs)
-      : "memory");
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t (&v)[4]) {
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-// ---- PTX: tcgen05 ---------------------------------------------------------------------------------
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] . B[smem]
-__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] . B[smem]
-__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// this thread's TMEM lane, 32 consecutive 32-bit columns
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
-      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
-      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-      : "memory");
-}
-__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-
-// ---- packed fp32 pairs (FFMA2 / FADD2 on sm_100) ---------------------------------------------------
-__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
-  uint64_t d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
-  return d;
-}
-__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
-  uint32_t a, b;
-  asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
-  lo = __uint_as_float(a);
-  hi = __uint_as_float(b);
-}
-__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
-// 2^x for a pair, on the FMA pipe instead of the MUFU: x = n + f with n = round(x), f in [-0.5, 0.5];
-// 2^f by a degree-3 minimax polynomial (relative error 7.5e-5, 50x below the bf16 rounding of P) and
-// 2^n by adding n to the exponent field.  The MUFU retires 4 ex2 per clock and SM sub-partition, which
-// for head_dim 128 is exactly as many clocks as the two MMAs of the tile take; moving a share of the
-// exponentials to the (otherwise idle) FMA pipe takes the softmax off the critical path.
-// x must be <= ~120 (it is <= kRescaleThreshold) and is clamped to >= -126 here.
-__device__ __forceinline__ void exp2_poly_x2(uint64_t x2, float& p0, float& p1) {
-  float x0, x1;
-  unpack_f32x2(x2, x0, x1);
-  x2 = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
-  const uint64_t magic = pack_f32x2(12582912.f, 12582912.f);  // 1.5 * 2^23: x + magic has round(x) in its low mantissa bits
-  const uint64_t t = add_f32x2(x2, magic);
-  const uint64_t nf = add_f32x2(t, pack_f32x2(-12582912.f, -12582912.f));
-  const uint64_t f = fma_f32x2(nf, pack_f32x2(-1.f, -1.f), x2);
-  uint64_t p = fma_f32x2(f, pack_f32x2(0.0551716685f, 0.0551716685f), pack_f32x2(0.2426111251f, 0.2426111251f));
-  p = fma_f32x2(p, f, pack_f32x2(0.6932609678f, 0.6932609678f));
-  p = fma_f32x2(p, f, pack_f32x2(0.9999280572f, 0.9999280572f));
-  float t0, t1, q0, q1;
-  unpack_f32x2(t, t0, t1);
-  unpack_f32x2(p, q0, q1);
-  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
-  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
-}
-
-// ---- UMMA descriptors (cute/arch/mma_sm100_desc.hpp layout of the bit fields) ----------------------
-// shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr >> 4) & 0x3fffu);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
-  d |= static_cast<uint64_t>(1) << 46;  // descriptor version
-  d |= static_cast<uint64_t>(2) << 61;  // LayoutType::SWIZZLE_128B
-  return d;
-}
-// the same descriptor split in two words: low = start address | LBO (advancing the start address by
-// `bytes` is low + (bytes >> 4); shared-memory addresses stay below the 14-bit field), high = SBO | version | swizzle
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
-  return ((saddr >> 4) & 0x3fffu) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
-}
-__device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t sbo_bytes) {
-  const uint32_t hi = ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14) | (2u << 29);
-  uint64_t d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
-  return d;
-}
-// instruction descriptor: bf16 x bf16 -> fp32, M x N, A K-major, B K-major or MN-major
-__host__ __device__ constexpr uint32_t instr_desc(int m, int n, bool b_mn_major, bool f16 = false) {
-  const uint32_t ab = f16 ? 0u : 1u;  // operand format: 0 = f16, 1 = bf16
-  return (1u << 4) | (ab << 7) | (ab << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
-         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
-}
 
 // ---- optional timeline trace of CTA (0,0,0) (build with -DB200_TC_TRACE; tools/tc_trace.py) ----------------
 #ifdef B200_TC_TRACE
@@ -780,6 +615,104 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       tc_ld32(s_addr + 96, v + 96);
       tc_wait_ld();
       if (r == 0) TC_TRACE(7 + 3 * i, j);
+      // Optimistic order for interior tiles behind the first: the exponentials of keys 0..63 FIRST, against the running
+      // maximum m, with the maximum of the whole row computed in their shadow (FMNMX on the ALU pipe while the MUFU
+      // works).  The rescale is lazy anyway -- m may lag the true maximum by 2^8 -- so in all but a few tiles of a row the
+      // check finds nothing to do and the separate max pass is gone.  If a row's maximum did jump, O is rescaled and the
+      // half recomputed from the scores still in registers (an overflowed P is simply overwritten) before it is
+      // released.  Measured (same box, gpurun_out/r2l_*): head_dim 64 (exponentials per flop doubled, the MUFU-bound
+      // variant) 681 -> 705 TFLOP/s at C4S; head_dim 128 within +-1 % (C4 1158 / 1147, C4F 1047 / 1035, C4P 897 / 906,
+      // C3 cascade 66.9 / 66.9 us) -- there the max pass already ran under the other Q tile's exponentials -- so the
+      // order is used for head_dim 64 only (-DB200_TC_OPTIMISTIC_ALL / -DB200_TC_NO_OPTIMISTIC for re-measuring).
+#if defined(B200_TC_NO_OPTIMISTIC)
+      constexpr bool kOptimistic = false;
+#elif defined(B200_TC_OPTIMISTIC_ALL)
+      constexpr bool kOptimistic = kPolyTile0 == 0 && kPolyTile1 == 0;
+#else
+      constexpr bool kOptimistic = D == 64 && kPolyTile0 == 0 && kPolyTile1 == 0;
+#endif
+      const bool optimistic = kOptimistic && fast && j > 0;
+      if (optimistic) {
+        const float l_before = l;
+        float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
+        const uint64_t sc2 = pack_f32x2(sc_log2, sc_log2);
+        uint64_t nm2 = pack_f32x2(-m, -m);
+        uint64_t l2 = pack_f32x2(l, 0.f);
+#pragma unroll
+        for (int c4 = 0; c4 < 2; ++c4) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            const float x0 = __uint_as_float(v[c4 * 32 + k]), x1 = __uint_as_float(v[c4 * 32 + k + 1]);
+            c0 = fmaxf(c0, x0);
+            c1 = fmaxf(c1, x1);
+            c2 = fmaxf(c2, __uint_as_float(v[64 + c4 * 32 + k]));
+            c3 = fmaxf(c3, __uint_as_float(v[64 + c4 * 32 + k + 1]));
+            const uint64_t y = fma_f32x2(pack_f32x2(x0, x1), sc2, nm2);
+            float y0, y1;
+            unpack_f32x2(y, y0, y1);
+            const float p0 = ex2(y0), p1 = ex2(y1);
+            l2 = add_f32x2(l2, pack_f32x2(p0, p1));
+            pk[k >> 1] = pack2<F16>(p0, p1);
+          }
+          tc_st16(s_addr + c4 * 16, pk);
+        }
+        const float mxs = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)) * sc_log2;  // no soft cap on this path
+        const bool need = mxs > m + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          // lazy rescale: O_i *= 2^(m_old - m_new); P.V(j-1) must have landed, P.V(j) waits for our arrive
+          mbar_wait(bar_pv(i), (j - 1) & 1);
+          tc_fence_after();
+          const float mn = fmaxf(m, mxs);
+          const float alpha = ex2(m - mn);
+          m = mn;
+#pragma unroll 1
+          for (int c4 = 0; c4 < D / 32; ++c4) {
+            uint32_t w[32];
+            tc_ld32(o_addr + c4 * 32, w);
+            tc_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) w[k] = __float_as_uint(__uint_as_float(w[k]) * alpha);
+            tc_st32(o_addr + c4 * 32, w);
+          }
+          nm2 = pack_f32x2(-m, -m);
+          l2 = pack_f32x2(l_before * alpha, 0.f);
+#pragma unroll
+          for (int c4 = 0; c4 < 2; ++c4) {  // keys 0..63 again, against the new maximum
+            uint32_t pk[16];
+#pragma unroll
+            for (int k = 0; k < 32; k += 2) {
+              const uint64_t y = fma_f32x2(pack_f32x2(__uint_as_float(v[c4 * 32 + k]), __uint_as_float(v[c4 * 32 + k + 1])), sc2, nm2);
+              float y0, y1;
+              unpack_f32x2(y, y0, y1);
+              const float p0 = ex2(y0), p1 = ex2(y1);
+              l2 = add_f32x2(l2, pack_f32x2(p0, p1));
+              pk[k >> 1] = pack2<F16>(p0, p1);
+            }
+            tc_st16(s_addr + c4 * 16, pk);
+          }
+        }
+        tc_wait_st();  // keys 0..63 of P are in TMEM: release them to the MMA warp
+        tc_fence_before();
+        mbar_arrive(bar_p(i, 0));
+#pragma unroll
+        for (int c4 = 2; c4 < 4; ++c4) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            const uint64_t y = fma_f32x2(pack_f32x2(__uint_as_float(v[c4 * 32 + k]), __uint_as_float(v[c4 * 32 + k + 1])), sc2, nm2);
+            float y0, y1;
+            unpack_f32x2(y, y0, y1);
+            const float p0 = ex2(y0), p1 = ex2(y1);
+            l2 = add_f32x2(l2, pack_f32x2(p0, p1));
+            pk[k >> 1] = pack2<F16>(p0, p1);
+          }
+          tc_st16(s_addr + c4 * 16, pk);
+        }
+        float la, lb;
+        unpack_f32x2(l2, la, lb);
+        l = la + lb;
+      } else {
       float mx;
       if (masked) {
         mx = -INFINITY;
@@ -892,6 +825,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
           }
         }
       }
+      }  // !optimistic
       if (R == 0) TC_TRACE(14, j);
       tc_wait_st();
       if (R == 0) TC_TRACE(15, j);

@@ -105,10 +105,12 @@ def test_extend_tcgen05_path_vs_oracle(hq, hkv, d, pre, ext, kv):
     kv_dtype = torch.bfloat16 if kv == "bf16" else torch.float8_e4m3fn
     tol = (G.BF16_ABS, G.BF16_REL) if kv == "bf16" else (G.FP8_ABS, G.FP8_REL)
     c = G.random_extend_case(hq, hkv, d, pre, ext, seed=hq * 11 + hkv + len(pre), kv_dtype=kv_dtype)
-    got = G.run_extend_case(c, force_path=_lib.PATH_TC)[0]
-    G.assert_close(got, _oracle(c), *tol, what=f"tc {hq}/{hkv}/{d}/{kv}/{pre}/{ext}")
     ref_path = G.run_extend_case(c, force_path=_lib.PATH_MMA)[0]
-    G.assert_close(got, ref_path, *tol, what="tcgen05 vs mma.sync path")
+    # PATH_TC: the one-CTA tcgen05 kernel; PATH_TC2: CTA pairs (cta_group::2), bf16 pools at head_dim 128
+    for path in ((_lib.PATH_TC, _lib.PATH_TC2) if kv == "bf16" else (_lib.PATH_TC,)):
+        got = G.run_extend_case(c, force_path=path)[0]
+        G.assert_close(got, _oracle(c), *tol, what=f"tc path {path} {hq}/{hkv}/{d}/{kv}/{pre}/{ext}")
+        G.assert_close(got, ref_path, *tol, what=f"tcgen05 path {path} vs mma.sync path")
 
 
 def test_extend_tcgen05_fp8_pool_per_tensor_scale_and_no_prefix():
@@ -124,11 +126,12 @@ def test_extend_tcgen05_golden_and_logit_cap():
     from scratchpad_b200 import _lib
     g = load_golden("extend_gqa4_d128")
     c = dict(g, req_pool_indices=g["req_pool_indices"].long(), seq_lens=g["seq_lens"].long())
-    got = G.run_extend_case(c, logit_cap=g["logit_cap"], save_kv_cache=False, force_path=_lib.PATH_TC)[0]
-    G.assert_close(got, g["out"], G.BF16_ABS, G.BF16_REL, "tc golden")
-    c = G.random_extend_case(16, 4, 128, [50, 0, 129], [40, 65, 1], seed=3)
-    got = G.run_extend_case(c, logit_cap=30.0, idx_dtype=torch.int32, force_path=_lib.PATH_TC)[0]
-    G.assert_close(got, _oracle(c, 30.0), G.BF16_ABS, G.BF16_REL, "tc logit cap")
+    c2 = G.random_extend_case(16, 4, 128, [50, 0, 129], [40, 65, 1], seed=3)
+    for path in (_lib.PATH_TC, _lib.PATH_TC2):
+        got = G.run_extend_case(c, logit_cap=g["logit_cap"], save_kv_cache=False, force_path=path)[0]
+        G.assert_close(got, g["out"], G.BF16_ABS, G.BF16_REL, f"tc golden path {path}")
+        got = G.run_extend_case(c2, logit_cap=30.0, idx_dtype=torch.int32, force_path=path)[0]
+        G.assert_close(got, _oracle(c2, 30.0), G.BF16_ABS, G.BF16_REL, f"tc logit cap path {path}")
 
 
 def test_extend_tcgen05_large_outliers_trigger_rescale():
@@ -138,8 +141,9 @@ def test_extend_tcgen05_large_outliers_trigger_rescale():
     ramp = torch.linspace(0.2, 3.0, c["k_new"].shape[0]).view(-1, 1, 1)
     c["k_new"] = (c["k_new"].float() * ramp).to(torch.bfloat16)
     c["q"] = (c["q"].float() * 2.0).to(torch.bfloat16)
-    got = G.run_extend_case(c, force_path=_lib.PATH_TC)[0]
-    G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, "tc rescale")
+    for path in (_lib.PATH_TC, _lib.PATH_TC2):
+        got = G.run_extend_case(c, force_path=path)[0]
+        G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, f"tc rescale path {path}")
 
 
 TC64_CASES = [

@@ -56,7 +56,7 @@ def test_fuzz_extend_both_kernel_families(seed):
                         c["seq_lens"], c["extend_seq_lens"], c["extend_start_loc"], c["sm_scale"], 0.0, c.get("kv_dtype"),
                         c.get("k_scale"), c.get("v_scale"))
     tc_ok = d == 128 or not fp8  # head_dim 64 over an fp8 pool has no tcgen05 variant
-    for path in ([_lib.PATH_MMA, _lib.PATH_TC] if tc_ok else [_lib.PATH_MMA]):
+    for path in ([_lib.PATH_MMA] + ([_lib.PATH_TC] if tc_ok else []) + ([_lib.PATH_TC2] if d == 128 and not fp8 else [])):
         got = G.run_extend_case(c, force_path=path, save_kv_cache=rng.random() < 0.5)[0]
         G.assert_close(got, want, *tol, what=f"fuzz extend seed {seed} path {path}: {hq}/{hkv}/{d} fp8={fp8} pre={pre} ext={ext}")
 
@@ -84,6 +84,6 @@ def test_large_logits_decode_extend_cascade(kv):
     want = O.extend_ref(e["q"], e["k_new"], e["v_new"], e["k_buf"], e["v_buf"], e["req_to_token"], e["req_pool_indices"],
                         e["seq_lens"], e["extend_seq_lens"], e["extend_start_loc"], e["sm_scale"], 0.0, e.get("kv_dtype"),
                         e.get("k_scale"), e.get("v_scale"))
-    for path in (_lib.PATH_MMA, _lib.PATH_TC):
+    for path in ((_lib.PATH_MMA, _lib.PATH_TC, _lib.PATH_TC2) if kv == "bf16" else (_lib.PATH_MMA, _lib.PATH_TC)):
         got = G.run_extend_case(e, force_path=path)[0]
         G.assert_close(got, want, *tol, what=f"large logits extend {kv} path {path}")

@@ -46,15 +46,29 @@ def test_paged_decode_vs_oracle_and_token_granular_kernel(hq, hkv, d, kv, page_s
     for i, lens in enumerate(LENS):
         c = G.random_decode_case(hq, hkv, d, lens, seed=100 * hq + 10 * hkv + i + page_size, kv_dtype=kv_dtype,
                                  page_size=page_size)
+        lib = _lib.load()
+        lib.b200_debug_tma_tiles(1)
         got, backend = _run(c, page_size)[:2]
         # page >= tile: one TMA box per K (V) tile; smaller pages: the row gather over the paged table
-        assert _lib.load().b200_debug_last_tma_mode() == (1 if page_size >= backend.config.tile_tokens else 0)
+        tn = backend.config.tile_tokens
+        assert lib.b200_debug_last_tma_mode() == (1 if page_size >= tn else 0)
+        # ... and the TMA branch is really taken: every full tile of a paged table has consecutive slots.  A CTA picks
+        # its loop (TMA-capable / row gather only) from its first tile, so with one tile per CTA the count is exact
+        n_tma = lib.b200_debug_tma_tiles(1)
+        full_tiles = sum(n // tn for n in lens) * (hkv // backend.config.heads_per_cta)
+        tiles_per_cta = int(backend.workspace[:64].view(torch.int32)[1].item())
+        if page_size >= tn:
+            assert n_tma <= full_tiles and (n_tma == full_tiles if tiles_per_cta == 1 else n_tma > 0 or full_tiles == 0), \
+                (n_tma, full_tiles, tiles_per_cta)
+        else:
+            assert n_tma == 0
         G.assert_close(got, _oracle(c), *tol, what=f"paged {page_size} {hq}/{hkv}/{d}/{kv}/{lens}")
         # the same bytes through the row-gather kernel (page_size 1 over the same buffers): identical arithmetic on
         # identical tiles -> bit-identical output
         cc = dict(c)
         plain = G.run_decode_case(c["q"], c["k_buf"], c["v_buf"], c["req_to_token"], c["req_pool_indices"], c["seq_lens"],
-                                  c["sm_scale"], 0.0, kv_dtype, c.get("k_scale"), c.get("v_scale"))[0]
+                                  c["sm_scale"], 0.0, kv_dtype, c.get("k_scale"), c.get("v_scale"),
+                                  tma_contiguous_runs=False)[0]
         assert _lib.load().b200_debug_last_tma_mode() == 0
         assert torch.equal(got.view(torch.int16), plain.view(torch.int16)), f"paged {page_size} != row gather"
 
@@ -179,10 +193,12 @@ def test_paged_contract_check_catches_a_token_granular_table(monkeypatch):
 
 
 @pytest.mark.parametrize("kv", ["bf16", "fp8"])
-@pytest.mark.parametrize("force_path", [_lib.PATH_MMA, _lib.PATH_TC])
+@pytest.mark.parametrize("force_path", [_lib.PATH_MMA, _lib.PATH_TC, _lib.PATH_TC2])
 def test_extend_over_a_paged_pool(kv, force_path):
     """The extend kernels gather the cached prefix by token slot and the KV store scatters by out_cache_loc, so a
     paged table needs nothing new from them: same oracle, pool rows written at the paged slots."""
+    if force_path == _lib.PATH_TC2 and kv != "bf16":
+        pytest.skip("the CTA-pair kernel is built for bf16 pools")
     kv_dtype = torch.bfloat16 if kv == "bf16" else torch.float8_e4m3fn
     tol = (G.BF16_ABS, G.BF16_REL) if kv == "bf16" else (G.FP8_ABS, G.FP8_REL)
     c = G.random_extend_case(8, 2, 128, [130, 0, 77, 256], [140, 150, 3, 129], seed=61, kv_dtype=kv_dtype, page_size=16)
@@ -222,14 +238,22 @@ def test_token_granular_pool_with_consecutive_slots_uses_tma():
     gen = torch.Generator().manual_seed(3)
     lens = [int(x) for x in torch.randint(1, 900, (24,), generator=gen)]
     c = G.random_decode_case(32, 8, 128, lens, seed=14, mode="contiguous")
+    _lib.load().b200_debug_tma_tiles(1)
     got = _run(c, 1, tma_contiguous_runs=True)[0]
     assert _lib.load().b200_debug_last_tma_mode() == 1
+    assert _lib.load().b200_debug_tma_tiles(1) >= sum(n // 16 for n in lens) // 2, "consecutive slots must be fetched by TMA"
     G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, what="auto TMA on consecutive slots")
-    plain = _run(c, 1)[0]
+    plain = _run(c, 1, tma_contiguous_runs=False)[0]
     assert _lib.load().b200_debug_last_tma_mode() == 0
+    # and it is the default: a backend built without the argument fetches consecutive slots by TMA
+    _lib.load().b200_debug_tma_tiles(1)
+    dflt = _run(c, 1)[0]
+    assert _lib.load().b200_debug_last_tma_mode() == 1 and _lib.load().b200_debug_tma_tiles(1) > 0
+    assert torch.equal(dflt.view(torch.int16), plain.view(torch.int16))
     assert torch.equal(got.view(torch.int16), plain.view(torch.int16))
     c = G.random_decode_case(32, 8, 128, lens, seed=15)                     # random slots: nothing consecutive
     G.assert_close(_run(c, 1, tma_contiguous_runs=True)[0], _oracle(c), G.BF16_ABS, G.BF16_REL, what="auto TMA, random slots")
+    assert _lib.load().b200_debug_tma_tiles(1) == 0, "scattered slots must all take the row gather"
 
 
 @pytest.mark.parametrize("hq,hkv,d,kv,page_size", [(32, 8, 64, "bf16", 16), (8, 1, 128, "fp8", 128), (8, 1, 128, "bf16", 64),

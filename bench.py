@@ -985,11 +985,13 @@ def measure_decode(args, rank, world, local_rank, dist, K, W, want_e2e=True, wan
         a.record(); b.record()  # materialise the handles
         evs.append((a, b))
     torch.cuda.synchronize()
+    backend.lib.b200_debug_tma_tiles(1)  # reset the debug counter of TMA-fetched KV tiles
     for i, (a, b) in enumerate(evs):
         backend.profile_events = (a.cuda_event, b.cuda_event)
         run_layer(i % L)
     backend.profile_events = None
     torch.cuda.synchronize()
+    tma_tiles = int(backend.lib.b200_debug_tma_tiles(1)) / len(evs)
     kt = sorted(a.elapsed_time(b) * 1e-3 for a, b in evs[8:])
     k_avg = sum(kt) / len(kt)
     k_med = kt[len(kt) // 2]
@@ -1061,6 +1063,7 @@ def measure_decode(args, rank, world, local_rank, dist, K, W, want_e2e=True, wan
                K=K, W=max(W, 0), t_max=t_max, k_avg=k_avg, k_med=k_med, n_kernel=len(kt), e2e=e2e, parity=parity,
                comparators=comparators, clocks=sampler.summary(), algo_bytes=st["algo_bytes"],
                timed_launches=timed_launches, shared_len=shared_len, row_tiles=row_tiles, tma_mode=tma_mode,
+               tma_tiles=tma_tiles, total_tiles=int(hdr[0].item()) * (hkv // int(backend.config.heads_per_cta)),
                cascade_enabled=bool(backend.cascade), cascade_launched=cascade_launched, tp=tp)
     graphs.clear()
     last_outs.clear()
@@ -1091,8 +1094,10 @@ def decode_roofline(r, args, world):
 
 
 def decode_runtime(r):
-    return {"tile_fetch": {0: "LDGSTS row gather", 1: "TMA, one box per K/V tile of consecutive slots (row gather "
-                           "for the rest)"}[r["tma_mode"]],
+    return {"tile_fetch": {0: "LDGSTS row gather (TMA disabled or pages smaller than the tile)",
+                           1: "TMA-capable kernel: one box per K/V tile whose slots are consecutive, row gather for "
+                              "the rest; CTAs that start on scattered slots run the pure row-gather loop"}[r["tma_mode"]],
+            "kv_tiles_per_launch": r["total_tiles"], "kv_tiles_fetched_by_tma_per_launch": r["tma_tiles"],
             "cascade": {"enabled": r["cascade_enabled"], "launched": r["cascade_launched"],
                         "shared_prefix_tokens_detected": r["shared_len"], "row_tiles": r["row_tiles"]}}
 

@@ -75,6 +75,8 @@ typedef struct b200_attn_config {
   int32_t stages;          /* cp.async pipeline depth */
   int32_t smem_bytes;      /* dynamic shared memory per CTA */
   int32_t num_sms;
+  int32_t partials_per_slot; /* split-KV partials per (cta, request): 1 where the sub-slices are combined inside the CTA */
+  int32_t q_tiles;           /* N=8 tiles of q heads per kv head: 1 (group size <= 8) or 2 (9..16, head_dim 128) */
   uint64_t workspace_bytes; /* for the max_bs passed to b200_attn_get_config */
 } b200_attn_config;
 

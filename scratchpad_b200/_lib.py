@@ -54,6 +54,8 @@ class AttnConfig(C.Structure):
         ("stages", C.c_int32),
         ("smem_bytes", C.c_int32),
         ("num_sms", C.c_int32),
+        ("partials_per_slot", C.c_int32),
+        ("q_tiles", C.c_int32),
         ("workspace_bytes", C.c_uint64),
     ]
 

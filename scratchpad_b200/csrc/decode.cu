@@ -59,7 +59,12 @@ constexpr bool kTwoLoops = false;
 #else
 constexpr bool kTwoLoops = true;
 #endif
-static inline int parts_per_slot(int sub_splits) { return kCtaReduce ? 1 : sub_splits; }
+// bytes of reduction scratch the in-CTA combination of `nsub` sub-slice states needs (first tree round: nsub / 2 writers
+// per virtual head, per lane 4 * (d / 16) accumulator floats + m[2] + l[2]) -- it must fit the ring stage just consumed
+constexpr int reduce_scratch_bytes(int nsub, int vh, int d) { return (nsub / 2) * vh * (4 * (d / 16) + 4) * 32 * 4; }
+constexpr bool cta_reduce_fits(int nsub, int vh, int d, int stage_bytes) {
+  return kCtaReduce && nsub > 1 && reduce_scratch_bytes(nsub, vh, d) <= stage_bytes;
+}
 constexpr int kPlanMagic = 0x62323030;  // "b200"
 constexpr int kHdrInts = 16;
 // header words: 0 total tiles, 1 tiles per CTA, 2 CTAs used, 3 bs, 4 tile tokens, 5 grid, 6 magic,
@@ -410,7 +415,10 @@ __device__ __forceinline__ void cursor_advance(Cursor& c, const DecodeArgs& a) {
   }
 }
 
-template <int D_, bool FP8_, int HPC_, int NW_, bool PAGED_ = false>
+// QT_ = N=8 tiles of q heads per kv head: 1 for group sizes <= 8, 2 for 9..16 (Llama-3.1-405B: 128 q / 8 kv heads).  The
+// QT warps of a kv head read the SAME K/V rows of the staged tile against their own 8 q heads, so a larger group costs
+// warps (fewer token sub-slices per tile), never a second pass over the KV bytes.
+template <int D_, bool FP8_, int HPC_, int NW_, bool PAGED_ = false, int QT_ = 1>
 struct DecodeCfg {
   static constexpr int D = D_;
   static constexpr bool FP8 = FP8_;
@@ -421,7 +429,9 @@ struct DecodeCfg {
   static constexpr int ELT = FP8 ? 1 : 2;
   static constexpr int SEG = D * ELT;  // bytes of one (token, head) K or V row
   static constexpr int CPS = SEG / 16; // 16-byte chunks per segment
-  static constexpr int NSUB = NW / HPC;  // token sub-slices (one warp each per head)
+  static constexpr int QT = QT_;
+  static constexpr int VH = HPC * QT;    // "virtual" heads per CTA: (kv head, q tile) pairs, one warp each per sub-slice
+  static constexpr int NSUB = NW / VH;   // token sub-slices (one warp each per virtual head)
   static constexpr int TN = 16 * NSUB;   // tokens per tile
   static constexpr int CPT = HPC * CPS;  // chunks per token (contiguous in the pool row)
   static constexpr int PASSES = TN * CPT / NT;
@@ -433,10 +443,14 @@ struct DecodeCfg {
   // paged: + kStages mbarriers behind the ring.  No alignment slack (the dynamic segment is declared 1024-aligned):
   // two CTAs of 98,368 B (+1 KiB each that the system reserves) stay inside the 196 KiB shared-memory carve-out
   static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + (PAGED ? 64 : 0);
+  // the token sub-slices of a tile are combined inside the CTA where the scratch fits a ring stage (everywhere but the
+  // fp8 two-q-tile variants): then ONE partial per (cta, request), else one per sub-slice
+  static constexpr bool REDUCE = cta_reduce_fits(NSUB, VH, D, STAGE_BYTES);
+  static constexpr int PARTS = REDUCE ? 1 : NSUB;
   static constexpr int NSLOT = (TN + 31) / 32;  // slot-id registers per lane
   static constexpr int KC = D / 16;             // MMA k-chunks (bf16) == 16-elt chunks (fp8)
   static constexpr int MT = D / 16;             // PV m-tiles
-  static_assert(NW % HPC == 0, "warps must tile the heads");
+  static_assert(NW % VH == 0 && NSUB >= 1, "warps must tile the (kv head, q tile) pairs");
   static_assert(NT % CPT == 0 && PASSES >= 1, "copy mapping");
   static_assert(CPS == 4 || CPS == 8 || CPS == 16, "segment size");
 };
@@ -622,8 +636,10 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
   // Measured slower at every distance -- C2 169 -> 187 us at 2 tiles, 295 us at 8 -- so it is gone.)
 
   // ---- consumer: warp -> (kv head, token sub-slice) ---------------------------
-  const int w_head = warp % HPC;
-  const int w_sub = warp / HPC;
+  const int w_vh = warp % C::VH;       // (kv head, q tile) pair of this warp
+  const int w_head = w_vh / C::QT;     // kv head inside the CTA's staged tile
+  const int q0 = (w_vh % C::QT) * 8;   // first q head (of the kv head's group) of this warp's N=8 tile
+  const int w_sub = warp / C::VH;
   const int kvh = h0 + w_head;
   const int gid = lane >> 2, cid = lane & 3;  // mma "groupID" / "threadID_in_group"
   const int G = a.g;
@@ -644,8 +660,8 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
   };
   // B fragments of Q^T: lane holds q-head n = gid (of this kv head's group)
   auto load_q = [&](int b) {
-    const bool live = gid < G;
-    const __nv_bfloat16* qp = a.q + static_cast<int64_t>(b) * a.q_st + static_cast<int64_t>(kvh * G + (live ? gid : 0)) * a.q_sh;
+    const bool live = q0 + gid < G;
+    const __nv_bfloat16* qp = a.q + static_cast<int64_t>(b) * a.q_st + static_cast<int64_t>(kvh * G + (live ? q0 + gid : 0)) * a.q_sh;
 #pragma unroll
     for (int kc = 0; kc < C::KC; ++kc) {
       if constexpr (!FP8) {
@@ -774,15 +790,14 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
   // hold the same (head, dim) fragment in the same lane, so the exchange is lane-local: no shuffles, log2(NSUB)
   // rounds, and the workspace and the merge kernel see ONE partial per (cta, request) instead of NSUB.
   auto flush = [&](int b, int free_stage) {
-    if constexpr (C::NSUB > 1 && kCtaReduce) {
+    if constexpr (C::REDUCE) {
       constexpr int kStateF = C::MT * 4 + 4;  // floats of softmax state per lane: o, m[2], l[2]
-      static_assert((C::NSUB / 2) * HPC * kStateF * 32 * 4 <= C::STAGE_BYTES, "reduction scratch must fit one ring stage");
       float* red = reinterpret_cast<float*>(smem + free_stage * C::STAGE_BYTES);
 #pragma unroll
       for (int half = C::NSUB / 2; half >= 1; half >>= 1) {
         __syncthreads();  // round 1: every warp is done reading the stage; later rounds: the previous round's reads
         if (w_sub >= half && w_sub < 2 * half) {
-          float* dst = red + (static_cast<size_t>((w_sub - half) * HPC + w_head) * kStateF) * 32 + lane;
+          float* dst = red + (static_cast<size_t>((w_sub - half) * C::VH + w_vh) * kStateF) * 32 + lane;
 #pragma unroll
           for (int mt = 0; mt < C::MT; ++mt)
 #pragma unroll
@@ -794,7 +809,7 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
         }
         __syncthreads();
         if (w_sub < half) {
-          const float* src = red + (static_cast<size_t>(w_sub * HPC + w_head) * kStateF) * 32 + lane;
+          const float* src = red + (static_cast<size_t>(w_sub * C::VH + w_vh) * kStateF) * 32 + lane;
           const float pm0 = src[(C::MT * 4 + 0) * 32], pm1 = src[(C::MT * 4 + 1) * 32];
           const float mn0 = fmaxf(m[0], pm0), mn1 = fmaxf(m[1], pm1);
           // a slice that saw no token has m = -inf (and l = 0, o = 0): weight 0, never exp2(-inf - -inf)
@@ -823,8 +838,8 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
       l1 += __shfl_xor_sync(0xffffffffu, l1, x);
     }
     const float inv0 = l0 > 0.f ? vs / l0 : 0.f, inv1 = l1 > 0.f ? vs / l1 : 0.f;
-    const int64_t slot = kCtaReduce ? static_cast<int64_t>(cta + b) : static_cast<int64_t>(cta + b) * C::NSUB + w_sub;
-    const int n0 = 2 * cid, n1 = 2 * cid + 1;  // q-head index inside the group
+    const int64_t slot = C::REDUCE ? static_cast<int64_t>(cta + b) : static_cast<int64_t>(cta + b) * C::NSUB + w_sub;
+    const int n0 = q0 + 2 * cid, n1 = n0 + 1;  // q-head index inside the group
     const int64_t pi0 = slot * a.hq + kvh * G + n0;
     const int64_t pi1 = pi0 + 1;
     if (gid == 0) {
@@ -1171,8 +1186,14 @@ __global__ void __launch_bounds__(32) naive_decode_kernel(const b200_decode_para
 // host side: config selection + launchers
 // ---------------------------------------------------------------------------
 struct KernelChoice {
-  int d, fp8, hpc, nw;
+  int d, fp8, hpc, nw, qt;
 };
+// partials per (cta, request) slot of the workspace: must mirror DecodeCfg::PARTS
+static int parts_per_slot(const KernelChoice& kc) {
+  const int vh = kc.hpc * kc.qt, nsub = kc.nw / vh, elt = kc.fp8 ? 1 : 2;
+  const int stage_bytes = 2 * kc.hpc * (16 * nsub) * kc.d * elt;
+  return cta_reduce_fits(nsub, vh, kc.d, stage_bytes) ? 1 : nsub;
+}
 
 static int pick_hpc(int hkv, int nw) {
   int hpc = 1;
@@ -1185,11 +1206,13 @@ static int choose(int hq, int hkv, int d, int dv, int kv_dtype, KernelChoice* kc
   if (d != dv) return B200_ERR_UNSUPPORTED;            // MLA-style split dims: out of scope
   if (d != 64 && d != 128) return B200_ERR_UNSUPPORTED;
   if (kv_dtype != B200_KV_BF16 && kv_dtype != B200_KV_FP8_E4M3) return B200_ERR_UNSUPPORTED;
-  if (hq / hkv > 8) return B200_ERR_UNSUPPORTED;       // one N=8 mma tile of q heads per kv head
+  // one N=8 mma tile of q heads per kv head, or two for group sizes 9..16 (built for head_dim 128)
+  if (hq / hkv > 16 || (hq / hkv > 8 && d != 128)) return B200_ERR_UNSUPPORTED;
   kc->d = d;
   kc->fp8 = kv_dtype == B200_KV_FP8_E4M3;
   kc->nw = (d == 128 && !kc->fp8) ? 4 : 8;  // keep a stage at 32 KiB
-  kc->hpc = pick_hpc(hkv, kc->nw);
+  kc->qt = hq / hkv > 8 ? 2 : 1;
+  kc->hpc = pick_hpc(hkv, kc->nw / kc->qt);
   return B200_OK;
 }
 
@@ -1350,6 +1373,17 @@ template <int D, bool FP8, bool PAGED>
 static int dispatch_hpc(const KernelChoice& kc, const DecodeArgs& a, const PagedMaps* m, int gx, int gy, cudaStream_t st, bool q,
                         int* occ) {
   constexpr int NW = (D == 128 && !FP8) ? 4 : 8;
+  if constexpr (D == 128) {
+    if (kc.qt == 2) {  // group sizes 9..16: two q tiles per kv head
+      switch (kc.hpc) {
+        case 1: return launch_decode_t<DecodeCfg<D, FP8, 1, NW, PAGED, 2>>(a, m, gx, gy, st, q, occ);
+        case 2: return launch_decode_t<DecodeCfg<D, FP8, 2, NW, PAGED, 2>>(a, m, gx, gy, st, q, occ);
+        case 4:
+          if constexpr (NW >= 8) return launch_decode_t<DecodeCfg<D, FP8, 4, NW, PAGED, 2>>(a, m, gx, gy, st, q, occ);
+      }
+      return B200_ERR_UNSUPPORTED;
+    }
+  }
   switch (kc.hpc) {
     case 1: return launch_decode_t<DecodeCfg<D, FP8, 1, NW, PAGED>>(a, m, gx, gy, st, q, occ);
     case 2: return launch_decode_t<DecodeCfg<D, FP8, 2, NW, PAGED>>(a, m, gx, gy, st, q, occ);
@@ -1392,7 +1426,9 @@ static int get_config(int max_bs, int hq, int hkv, int d, int dv, int kv_dtype, 
   const int elt = kc.fp8 ? 1 : 2;
   out->path = B200_PATH_MMA;
   out->heads_per_cta = kc.hpc;
-  out->sub_splits = kc.nw / kc.hpc;
+  out->sub_splits = kc.nw / (kc.hpc * kc.qt);
+  out->partials_per_slot = parts_per_slot(kc);
+  out->q_tiles = kc.qt;
   out->tile_tokens = 16 * out->sub_splits;
   const int gy = hkv / kc.hpc;
   // persistent grid: every resident CTA slot of the machine, shared by the head groups
@@ -1402,7 +1438,7 @@ static int get_config(int max_bs, int hq, int hkv, int d, int dv, int kv_dtype, 
   out->stages = kStages;
   out->smem_bytes = kStages * 2 * kc.hpc * out->tile_tokens * d * elt;
   out->num_sms = di.num_sms;
-  out->workspace_bytes = ws_layout(max_bs, gx, parts_per_slot(out->sub_splits), hq, dv).total;
+  out->workspace_bytes = ws_layout(max_bs, gx, out->partials_per_slot, hq, dv).total;
   return B200_OK;
 }
 
@@ -1431,7 +1467,7 @@ const char* b200_attn_error_string(int code) {
   switch (code) {
     case B200_OK: return "ok";
     case B200_ERR_INVALID: return "invalid argument (null pointer, bad size or misaligned stride)";
-    case B200_ERR_UNSUPPORTED: return "unsupported configuration (head_dim must be 64 or 128 with d == dv, group size <= 8, kv dtype bf16 or fp8-e4m3)";
+    case B200_ERR_UNSUPPORTED: return "unsupported configuration (head_dim must be 64 or 128 with d == dv, group size <= 8 -- <= 16 at head_dim 128 --, kv dtype bf16 or fp8-e4m3)";
     case B200_ERR_WORKSPACE: return "workspace too small for this configuration";
     case B200_ERR_NOT_PLANNED: return "workspace holds no plan for this batch (call b200_attn_plan with the same bs, shape and cascade flag first)";
     default:
@@ -1469,7 +1505,7 @@ int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs, co
   int rc = get_config(max_bs, hq, hkv, d, dv, kv_dtype, force_path, &cfg);
   if (rc) return rc;
   if (workspace_bytes < cfg.workspace_bytes) return B200_ERR_WORKSPACE;
-  const WsLayout L = ws_layout(max_bs, cfg.grid_ctas, parts_per_slot(cfg.sub_splits), hq, dv);
+  const WsLayout L = ws_layout(max_bs, cfg.grid_ctas, cfg.partials_per_slot, hq, dv);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int use_cascade = cascade && bs <= kMaxGroupBs && cascade_supported(bs, hq, hkv, d, dv, kv_dtype);
@@ -1531,7 +1567,7 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
     rec.cascade = p->cascade != 0; rec.max_bs = p->max_bs;
     if (!plan_matches(rec)) return B200_ERR_NOT_PLANNED;
   }
-  const WsLayout L = ws_layout(p->max_bs, cfg.grid_ctas, parts_per_slot(cfg.sub_splits), p->hq, p->dv);
+  const WsLayout L = ws_layout(p->max_bs, cfg.grid_ctas, cfg.partials_per_slot, p->hq, p->dv);
   uint8_t* ws = static_cast<uint8_t*>(p->workspace);
   DecodeArgs a;
   a.q = static_cast<const __nv_bfloat16*>(p->q);
@@ -1614,11 +1650,11 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
     return launch_pdl(merge_kernel<64>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
                       static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
                       static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
-                      parts_per_slot(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
+                      static_cast<int>(cfg.partials_per_slot), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
   return launch_pdl(merge_kernel<128>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
                     static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
                     static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
-                    parts_per_slot(cfg.sub_splits), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
+                    static_cast<int>(cfg.partials_per_slot), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
 }
 
 #ifdef B200_DEC_TRACE

@@ -44,6 +44,9 @@ SHAPES = [
     (7, 1, 64),     # g=7 (Qwen2-7B shard), odd group
     (4, 4, 128),    # MHA g=1
     (6, 2, 64),     # g=3
+    (16, 1, 128),   # g=16 (Llama-3.1-405B TP8 shard): two N=8 q tiles per kv head, HPC 1
+    (64, 4, 128),   # g=16, several kv heads per CTA
+    (12, 1, 128),   # g=12: second q tile half empty
 ]
 LENS = [[1], [15, 16, 17], [127, 128, 129, 1, 300], [513, 64, 2, 1000]]
 
@@ -231,9 +234,32 @@ def test_unsupported_configs_raise():
     runner = synth.make_model_runner(32, 8, 96, pool_tokens=64, max_reqs=4, context_len=64)
     with pytest.raises(_lib.B200AttnError):
         CudaB200AttnBackend(runner)
-    runner = synth.make_model_runner(32, 2, 64, pool_tokens=64, max_reqs=4, context_len=64)  # g = 16
+    runner = synth.make_model_runner(32, 2, 64, pool_tokens=64, max_reqs=4, context_len=64)  # g = 16 at head_dim 64
     with pytest.raises(_lib.B200AttnError):
         CudaB200AttnBackend(runner)
+    runner = synth.make_model_runner(64, 2, 128, pool_tokens=64, max_reqs=4, context_len=64)  # g = 32
+    with pytest.raises(_lib.B200AttnError):
+        CudaB200AttnBackend(runner)
+
+
+@pytest.mark.parametrize("kv", ["bf16", "fp8"])
+@pytest.mark.parametrize("hq,hkv", [(16, 1), (128, 8)])
+def test_decode_group_size_16_many_ctas_paged_and_graph(hq, hkv, kv):
+    """Llama-3.1-405B head layout (128 q / 8 kv heads; 16 / 1 at TP8): two q tiles per kv head share every staged K/V
+    tile.  Enough requests that CTAs cross request boundaries (flush, in-CTA sub-slice combination where it fits),
+    over a token-granular pool, over 128-token pages (TMA tiles) and with int32 indices."""
+    kv_dtype = torch.bfloat16 if kv == "bf16" else torch.float8_e4m3fn
+    tol = (G.BF16_ABS, G.BF16_REL) if kv == "bf16" else (G.FP8_ABS, G.FP8_REL)
+    lens = [int(x) for x in torch.randint(1, 1200, (40,), generator=torch.Generator().manual_seed(hq))]
+    c = G.random_decode_case(hq, hkv, 128, lens, seed=70 + hq, kv_dtype=kv_dtype)
+    got, backend = G.run_decode_case(c["q"], c["k_buf"], c["v_buf"], c["req_to_token"], c["req_pool_indices"], c["seq_lens"],
+                                     c["sm_scale"], 0.0, kv_dtype, c["k_scale"], c["v_scale"], idx_dtype=torch.int32)[:2]
+    assert backend.config.q_tiles == 2
+    G.assert_close(got, _oracle(c), *tol, what=f"g=16 {hq}/{hkv}/{kv}")
+    cp = G.random_decode_case(hq, hkv, 128, lens, seed=71 + hq, kv_dtype=kv_dtype, page_size=128)
+    gotp = G.run_decode_case(cp["q"], cp["k_buf"], cp["v_buf"], cp["req_to_token"], cp["req_pool_indices"], cp["seq_lens"],
+                             cp["sm_scale"], 0.0, kv_dtype, cp["k_scale"], cp["v_scale"], page_size=128)[0]
+    G.assert_close(gotp, _oracle(cp), *tol, what=f"g=16 paged {hq}/{hkv}/{kv}")
 
 
 @pytest.mark.parametrize("kv", ["bf16", "fp8"])

@@ -919,6 +919,14 @@ def measure_decode(args, rank, world, local_rank, dist, K, W, want_e2e=True, wan
                     capture((first + j) % L, min(per, m - j))
                     j += per
 
+        # the first replay of a CUDA graph also uploads it (~100 us): every graph the timed loop will use is replayed
+        # once here, outside the timed region (at K = 20, L = 16 the remainder graph would otherwise meet its first
+        # replay inside it)
+        replan()
+        for g_, _ in list(graphs.values()):
+            g_.replay()
+        torch.cuda.synchronize()
+
         def run_steps(n):
             for first, m in segments(n):
                 replan()
@@ -962,7 +970,11 @@ def measure_decode(args, rank, world, local_rank, dist, K, W, want_e2e=True, wan
     timed_launches = launches["n"]
     barrier()
     tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+    per_rank_us = None
     if dist is not None:
+        allt = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allt, tt)  # every rank's own device time: the job's time is the slowest rank's
+        per_rank_us = [float(x.item()) / K * 1e6 for x in allt]
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_max = float(tt.item())
 
@@ -1063,7 +1075,7 @@ def measure_decode(args, rank, world, local_rank, dist, K, W, want_e2e=True, wan
                K=K, W=max(W, 0), t_max=t_max, k_avg=k_avg, k_med=k_med, n_kernel=len(kt), e2e=e2e, parity=parity,
                comparators=comparators, clocks=sampler.summary(), algo_bytes=st["algo_bytes"],
                timed_launches=timed_launches, shared_len=shared_len, row_tiles=row_tiles, tma_mode=tma_mode,
-               tma_tiles=tma_tiles, total_tiles=int(hdr[0].item()) * (hkv // int(backend.config.heads_per_cta)),
+               per_rank_us=per_rank_us, tma_tiles=tma_tiles, total_tiles=int(hdr[0].item()) * (hkv // int(backend.config.heads_per_cta)),
                cascade_enabled=bool(backend.cascade), cascade_launched=cascade_launched, tp=tp)
     graphs.clear()
     last_outs.clear()
@@ -1119,6 +1131,7 @@ def decode_line(r, args, world):
         "roofline": decode_roofline(r, args, world),
         "e2e": r["e2e"], "parity_check": r["parity"], "comparators": r["comparators"],
         "gpu_launches": r["timed_launches"], "clocks": r["clocks"],
+        **({"step_us_per_rank": r["per_rank_us"]} if r.get("per_rank_us") else {}),
     }
 
 
@@ -1144,6 +1157,8 @@ def compact(line):
         out["parity_check"] = pc
     if line.get("comparators"):
         out["comparators"] = line["comparators"]
+    if "step_us_per_rank" in line:
+        out["step_us_per_rank"] = line["step_us_per_rank"]
     out["clocks"] = {k: (line.get("clocks") or {}).get(k) for k in ("sm_mhz", "reasons")}
     return out
 

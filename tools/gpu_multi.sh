@@ -35,4 +35,4 @@ for n in (1, 2, 4, 8):
         print(f"N={n} {name:44s} step {us:8.1f} us  kernel {kus if kus else 0:8.1f}  value {val:12.0f}  e2e {e2e if e2e else 0:12.0f}  efficiency {eff:.3f}")
     if "allreduce_after_o_proj_us" in d: print(f"N={n} all-reduce after o_proj: {d['allreduce_after_o_proj_us']:.1f} us")
 PY
-tail -3 $out/${tag}_n*.err | grep -v Warning | tail -12
+for f in $out/${tag}_n*.err; do grep -v -i "warning\|warn(" $f | tail -2; done

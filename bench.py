@@ -615,6 +615,13 @@ def measure_extend(args, rank, world, local_rank, dist, K, W, want_e2e=True, wan
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_max = float(tt.item())
 
+    backend.lib.b200_debug_extend_tma_tiles(1)  # debug counter: K / V tiles fetched by one TMA box copy each
+    step(0)
+    tma_tiles = int(backend.lib.b200_debug_extend_tma_tiles(1))
+    total_tiles = 2 * hkv * sum(((e + 256 // (hq // hkv) - 1) // (256 // (hq // hkv))) and
+                                sum((p_ + min(e, (qb + 1) * (256 // (hq // hkv))) + 127) // 128
+                                    for qb in range((e + 256 // (hq // hkv) - 1) // (256 // (hq // hkv))))
+                                for p_, e in zip(pre, ext))
     parity = None
     if want_parity and rank == 0:
         # the timed output of the last step against the CPU oracle, on sampled query rows of every request (the
@@ -668,7 +675,8 @@ def measure_extend(args, rank, world, local_rank, dist, K, W, want_e2e=True, wan
     ach = flops / (t_max / K) / 1e12
     return dict(
         w=w, K=K, W=W, t_max=t_max, T=T, flops=flops, ach=ach, peak=peak, burst=burst, e2e=e2e, parity=parity,
-        comparators=comparators, clocks=sampler.summary(), hq=hq, hkv=hkv, d=d, L=L,
+        comparators=comparators, clocks=sampler.summary(), hq=hq, hkv=hkv, d=d, L=L, tma_tiles=tma_tiles,
+        total_tiles=total_tiles,
         traffic=traffic_for(f"{w.name}/{args.index_mode}/n{world}"))
 
 
@@ -811,6 +819,8 @@ def extend_line(r, args, world):
                                   "region is K back-to-back launches of this kernel",
                      "peak_burst": burst, "frac_of_burst": ach / burst, "frac_of_nominal_2250": ach / 2250.0,
                      "note": "step time used (KV store + extend kernel); the store is <1% of the step"},
+        "runtime": {"kv_tiles_per_launch": r["total_tiles"], "kv_tiles_fetched_by_tma_per_launch": r["tma_tiles"],
+                    "note": "tcgen05 kernel: a K / V tile of 128 consecutive rows (new tokens; prefix runs) is one TMA box copy"},
         "cpu_baseline": None, "e2e": r["e2e"], "parity_check": r["parity"], "comparators": r["comparators"],
         "gpu_launches": K * 2, "clocks": r["clocks"],
     }
@@ -1231,7 +1241,10 @@ def main():
         suite = []
         plan = [("C2", {}), ("C3U", {})]  # at every N (kv heads sharded like the headline)
         if world == 1:
-            plan += [("C3", {}), ("C5", {"shard": 8}), ("C2", {"shard": 8}), ("C3B", {"shard": 8}), ("C4", {})]
+            # C4 in both slot orders SURVEY 8d asks for: random-permuted (worst case) and contiguous runs (what an
+            # unfragmented allocator hands out: prefix tiles then arrive by TMA like the new tokens do)
+            plan += [("C3", {}), ("C5", {"shard": 8}), ("C2", {"shard": 8}), ("C3B", {"shard": 8}), ("C4", {}),
+                     ("C4", {"index_mode": "contiguous"})]
         for name, over in plan:
             a2 = copy.copy(args)
             a2.workload = name
@@ -1242,7 +1255,8 @@ def main():
             try:
                 if wl.extend_len:
                     rr = measure_extend(a2, rank, world, local_rank, dist, 16, 3, want_e2e=False,
-                                        want_parity=not args.no_parity, want_comparators=want_cmp)
+                                        want_parity=not args.no_parity,
+                                        want_comparators=want_cmp and a2.index_mode == "random")
                     entry = compact(extend_line(rr, a2, world)) if rank == 0 else None
                 else:
                     if wl.hkv_total % (world * a2.shard):

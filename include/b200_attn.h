@@ -150,8 +150,11 @@ typedef struct b200_extend_params {
   float logit_cap;
   const float* k_scale;
   const float* v_scale;
-  int32_t force_path;           /* -1 auto, else B200_PATH_MMA / B200_PATH_TC (tests, bench) */
-  int32_t reserved;
+  int32_t force_path;           /* -1 auto, else B200_PATH_MMA / B200_PATH_TC / B200_PATH_TC2 (tests, bench) */
+  int32_t page_size;            /* hint as in b200_decode_params: >= 128 or B200_PAGE_AUTO lets the tcgen05 kernel fetch prefix
+                                 * tiles whose 128 slots are consecutive by TMA (checked per tile on device); 0 / 1: row gather.
+                                 * Tiles of 128 new tokens (rows of k_new / v_new) are fetched by TMA whatever the value. */
+  int64_t kv_pool_rows;         /* token rows of k_buf / v_buf (bounds of the pool's tensor maps); 0 = unknown, no prefix TMA */
 } b200_extend_params;
 
 int b200_attn_abi_version(void);
@@ -255,6 +258,8 @@ int b200_debug_last_tma_mode(void);
  * since the last call with reset != 0 (-1 on a CUDA error).  b200_debug_last_tma_mode() says the TMA-capable kernel
  * was launched; this says how often its TMA branch was actually taken. */
 int64_t b200_debug_tma_tiles(int32_t reset);
+/* The same for the tcgen05 extend kernel: K / V tiles (128 keys of one kv head) fetched by one TMA box copy each. */
+int64_t b200_debug_extend_tma_tiles(int32_t reset);
 
 /* Debug check of the paged-table contract (b200_decode_params.page_size): writes to *violations (device int32)
  * the number of positions t < seq_lens[i] with req_to_token[r_i, t] != page_start + t % page_size, page_start =

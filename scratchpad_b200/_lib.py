@@ -38,6 +38,7 @@ EXPORTS = (
     "b200_rope_kv_store",
     "b200_debug_last_tma_mode",
     "b200_debug_tma_tiles",
+    "b200_debug_extend_tma_tiles",
     "b200_debug_check_paged",
     "b200_debug_gather",
     "b200_debug_decode_naive",
@@ -95,7 +96,7 @@ class ExtendParams(C.Structure):
         ("kv_dtype", C.c_int32),
         ("sm_scale", C.c_float), ("logit_cap", C.c_float),
         ("k_scale", C.c_void_p), ("v_scale", C.c_void_p),
-        ("force_path", C.c_int32), ("reserved", C.c_int32),
+        ("force_path", C.c_int32), ("page_size", C.c_int32), ("kv_pool_rows", C.c_int64),
     ]
 
 
@@ -175,6 +176,8 @@ def load() -> C.CDLL:
         getattr(lib, name).restype = C.c_int
     lib.b200_debug_tma_tiles.restype = C.c_int64
     lib.b200_debug_tma_tiles.argtypes = [i32]
+    lib.b200_debug_extend_tma_tiles.restype = C.c_int64
+    lib.b200_debug_extend_tma_tiles.argtypes = [i32]
     _lib = lib
     return lib
 

@@ -363,7 +363,8 @@ class CudaB200AttnBackend(AttentionBackend):
             bs=forward_batch.batch_size, hq=hq, hkv=hkv, d=d, dv=dv,
             total_tokens=q3.shape[0], max_extend_len=int(max_extend_len), kv_dtype=self.kv_dtype,
             sm_scale=float(layer.scaling), logit_cap=self._logit_cap(layer),
-            k_scale=_ptr(ks), v_scale=_ptr(vs), force_path=self.force_path, reserved=0,
+            k_scale=_ptr(ks), v_scale=_ptr(vs), force_path=self.force_path,
+            page_size=self._page_hint(pool), kv_pool_rows=kb.shape[0],
         )
         rc = self.lib.b200_attn_extend(p, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "b200_attn_extend")

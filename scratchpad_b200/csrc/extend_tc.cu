@@ -40,6 +40,7 @@
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "tensor_map.cuh"
 
 namespace b200 {
 namespace tc {
@@ -125,6 +126,14 @@ struct Args {
   const float* k_scale;    // per kv head (fp8 pools), or null
   const float* v_scale;
   int bs;
+  int tma;  // extend, bf16 pools: bit 0 = tiles of 128 new tokens, bit 1 = prefix tiles whose 128 slots are consecutive: TMA
+};
+
+__device__ unsigned long long g_tc_tma_tiles;  // debug counter: K / V tiles the extend kernel fetched by TMA since the last reset
+
+// tensor maps of the launch (extend mode; zero-filled and unused otherwise): pool K / V, new-token K / V
+struct TcMaps {
+  CUtensorMap pool_k, pool_v, new_k, new_v;
 };
 
 constexpr int kModeExtend = 0;  // causal extend over [gathered prefix | new tokens], bf16 out
@@ -140,7 +149,7 @@ __device__ __forceinline__ uint32_t tile_off(int r, int cb, int c) {
 // narrowed bf16 -> f16 (exact for |q| >= 2^-14) and the MMAs run as f16 x f16; k_scale folds into the softmax
 // scale and v_scale into the epilogue, like the split-KV kernel does.
 template <int MODE, bool F16, int D>
-__global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
+__global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_constant__ Args a, const __grid_constant__ TcMaps tm) {
   static_assert(D == 128 || (D == 64 && !F16), "head_dim 64 over an fp8 pool stays on the mma.sync kernels");
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -350,6 +359,27 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     const uint32_t dst_thread = (ch >> 3) * kColBlockBytes + rr * 128 + (((ch & 7) ^ r7) << 4);
     const int64_t col_bytes = static_cast<int64_t>(kvh) * (D * 2) + ch * 16;
     const int total = 2 * nt;
+    // TMA where 128 keys are 128 consecutive rows (north_star: "TMA where pages are contiguous"): the new tokens of the
+    // chunk always are (rows of k_new / v_new), cached-prefix tiles are when the allocator handed the slots out as a
+    // run -- pages of >= 128 tokens, or an unfragmented token-granular pool -- which every producer warp checks for
+    // itself on the tile's slot ids (4 per lane, one vote: all warps reach the same verdict without talking).  Such a
+    // tile is ONE box copy for K and one for V, issued by one thread and completing on the slot's full barrier through
+    // its tx count; the 128 lagged thread arrivals stay as they are.  Everything else -- scattered slots, the tile
+    // that straddles prefix and new tokens, the ragged last tile -- takes the row gather below.
+    bool tile_by_tma = false;
+    int tile_row0 = 0, n_tma = 0;
+    // Page-table lookups run one tile ahead of the copies they feed (-DB200_TC_NO_SLOT_PREFETCH: looked up in place)
+#ifndef B200_TC_NO_SLOT_PREFETCH
+    int slot_nx[NQ];
+    auto fetch_slots = [&](int n_) {
+      const int j_ = n_ >> 1;
+      if (n_ < total && (j_ + 1) * kBN <= pre) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) slot_nx[q] = __ldg(row + j_ * kBN + rr + STEP * q);
+      }
+    };
+    fetch_slots(0);
+#endif
     for (int n = 0; n < total; ++n) {
       const int j = n >> 1, is_v = n & 1, s = n % kSlots;
       const uint8_t* pool = (is_v ? a.vbuf : a.kbuf) + col_bytes;
@@ -358,11 +388,41 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
       mbar_wait(bar_empty(s), ((n / kSlots) & 1) ^ 1);
       if (tid == kProdWarp0 * 32) TC_TRACE(0, n);
       const uint32_t dst0 = sbase + kSmemRing + s * kTileBytes + dst_thread;
-      if ((j + 1) * kBN <= pre) {
+#ifndef B200_TC_NO_SLOT_PREFETCH
+      int slot[NQ];  // this tile's slot ids (looked up one tile ago; meaningful for prefix tiles), then the next tile's
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) slot[q] = slot_nx[q];
+      fetch_slots(n + 1);
+#endif
+      if constexpr (MODE == kModeExtend) {
+        if (a.tma != 0 && !is_v) {  // decided on the K tile, reused for the V tile of the same keys
+          tile_by_tma = false;
+          if ((a.tma & 1) && j * kBN >= pre && (j + 1) * kBN <= kv_len) {
+            tile_by_tma = true;
+            tile_row0 = start + j * kBN - pre;
+          } else if ((a.tma & 2) && (j + 1) * kBN <= pre) {
+            const int32_t* rp = row + j * kBN + 4 * lane;
+            const int s0 = __ldg(rp), s1 = __ldg(rp + 1), s2 = __ldg(rp + 2), s3 = __ldg(rp + 3);
+            tile_row0 = __shfl_sync(0xffffffffu, s0, 0);
+            tile_by_tma = __all_sync(0xffffffffu, s1 == s0 + 1 && s2 == s0 + 2 && s3 == s0 + 3 && s0 == tile_row0 + 4 * lane);
+          }
+        }
+      }
+      if (MODE == kModeExtend && tile_by_tma) {
+        if (tid == kProdWarp0 * 32) {
+          const bool fresh_tile = j * kBN >= pre;
+          const CUtensorMap* map = fresh_tile ? (is_v ? &tm.new_v : &tm.new_k) : (is_v ? &tm.pool_v : &tm.pool_k);
+          mbar_expect_tx(bar_full(s), kBN * D * 2);
+          tma_load_4d(sbase + kSmemRing + s * kTileBytes, map, bar_full(s), 0, tile_row0, 0, kvh);
+          ++n_tma;
+        }
+      } else if ((j + 1) * kBN <= pre) {
         // tile of cached-prefix keys only: page-table lookup (L1-resident after the first touch) + one copy
+#ifdef B200_TC_NO_SLOT_PREFETCH
         int slot[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) slot[q] = __ldg(row + p0 + STEP * q);
+#endif
 #pragma unroll
         for (int q = 0; q < NQ; ++q) cp_async16(dst0 + q * (STEP * 128), kv_row_ptr(pool, slot[q], pool_st), 16);
       } else {
@@ -386,6 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
     cp_async_wait<0>();
     fence_proxy_async();
     for (int n = max(total - kLag, 0); n < total; ++n) mbar_arrive(bar_full(n % kSlots));
+    if (n_tma) atomicAdd(&g_tc_tma_tiles, static_cast<unsigned long long>(n_tma));
     }  // !F16
     TC_TILE_LOOP_END
   } else if (warp == kMmaWarp) {
@@ -889,6 +950,19 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const Args a) {
 
 }  // namespace tc
 
+// Test hook (synchronises): K / V tiles the tcgen05 extend kernel fetched by TMA on the current device since the last call
+// with reset != 0 (-1 on a CUDA error).
+extern "C" int64_t b200_debug_extend_tma_tiles(int32_t reset) {
+  unsigned long long n = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(&n, tc::g_tc_tma_tiles, sizeof(n)) != cudaSuccess) return -1;
+  if (reset) {
+    const unsigned long long zero = 0;
+    if (cudaMemcpyToSymbol(tc::g_tc_tma_tiles, &zero, sizeof(zero)) != cudaSuccess) return -1;
+  }
+  return static_cast<int64_t>(n);
+}
+
 #ifdef B200_TC_TRACE
 extern "C" int b200_debug_tc_trace_read(long long* host_dst) {
   return cudaMemcpyFromSymbol(host_dst, tc::g_trace, sizeof(tc::g_trace)) == cudaSuccess ? 0 : 1;
@@ -896,11 +970,11 @@ extern "C" int b200_debug_tc_trace_read(long long* host_dst) {
 #endif
 
 template <int MODE, bool F16, int D>
-static int launch_tc(const tc::Args& a, dim3 grid, cudaStream_t st) {
+static int launch_tc(const tc::Args& a, const tc::TcMaps& maps, dim3 grid, cudaStream_t st) {
   auto kern = tc::extend_tc_kernel<MODE, F16, D>;
   static PerDevice pd;  // per instantiation
   if (int rc = ensure_smem_attr(kern, tc::kSmemBytes, pd)) return rc;
-  return launch_pdl(kern, grid, dim3(tc::kThreads), tc::kSmemBytes, st, a);
+  return launch_pdl(kern, grid, dim3(tc::kThreads), tc::kSmemBytes, st, a, maps);
 }
 
 // Called by b200_attn_extend (extend.cu) for head_dim 128 (bf16 or fp8 pool) and 64 (bf16 pool).  Strides and pointers have been validated there.
@@ -940,8 +1014,26 @@ int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
   a.logit_cap = p->logit_cap;
   const int nqb = (p->max_extend_len + a.bm_t - 1) / a.bm_t;
   const dim3 grid(nqb, p->hkv, p->bs);
-  if (p->d == 64) return fp8 ? B200_ERR_UNSUPPORTED : launch_tc<tc::kModeExtend, false, 64>(a, grid, st);
-  return fp8 ? launch_tc<tc::kModeExtend, true, 128>(a, grid, st) : launch_tc<tc::kModeExtend, false, 128>(a, grid, st);
+  // TMA for tiles of 128 consecutive rows (bf16 pools; fp8 pools widen their rows on chip and keep the row gather):
+  // the new tokens' K / V are described per call (the activations move), the pool's maps are cached per buffer.  A map
+  // the driver refuses only switches the feature off.
+  tc::TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  static const bool no_tma = getenv("B200_EXTEND_NO_TMA") != nullptr;  // measurement switch
+  if (!fp8 && !no_tma) {
+    if (p->total_tokens >= tc::kBN &&
+        encode_pool_map(&maps.new_k, p->k_new, p->kn_stride_t * 2, p->total_tokens, p->hkv, p->d, false, tc::kBN, 1) == B200_OK &&
+        encode_pool_map(&maps.new_v, p->v_new, p->vn_stride_t * 2, p->total_tokens, p->hkv, p->dv, false, tc::kBN, 1) == B200_OK)
+      a.tma |= 1;
+    // prefix tiles: a paged pool with pages of >= 128 tokens, or a token-granular pool whose allocator hands out runs
+    // (page_size B200_PAGE_AUTO); every tile's slot ids are checked on device before they are trusted
+    if ((p->page_size >= tc::kBN || p->page_size == B200_PAGE_AUTO) && p->kv_pool_rows >= tc::kBN &&
+        cached_pool_map(&maps.pool_k, p->k_buf, a.k_st_bytes, p->kv_pool_rows, p->hkv, p->d, false, tc::kBN, 1) == B200_OK &&
+        cached_pool_map(&maps.pool_v, p->v_buf, a.v_st_bytes, p->kv_pool_rows, p->hkv, p->dv, false, tc::kBN, 1) == B200_OK)
+      a.tma |= 2;
+  }
+  if (p->d == 64) return fp8 ? B200_ERR_UNSUPPORTED : launch_tc<tc::kModeExtend, false, 64>(a, maps, grid, st);
+  return fp8 ? launch_tc<tc::kModeExtend, true, 128>(a, maps, grid, st) : launch_tc<tc::kModeExtend, false, 128>(a, maps, grid, st);
 }
 
 // Shared-prefix ("cascade") leg of b200_attn_decode (decode.cu): the decode queries of the whole batch against the
@@ -976,8 +1068,10 @@ int launch_shared_prefix_tc(const b200_decode_params* p, const CasTables& t, flo
   a.v_scale = p->v_scale;
   a.bs = p->bs;
   const dim3 grid(p->hkv, nsplit, (p->bs + a.bm_t - 1) / a.bm_t);  // z = row-tile lanes; CTAs loop over further tiles
-  if (p->d == 64) return launch_tc<tc::kModeShared, false, 64>(a, grid, st);
-  return fp8 ? launch_tc<tc::kModeShared, true, 128>(a, grid, st) : launch_tc<tc::kModeShared, false, 128>(a, grid, st);
+  tc::TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (p->d == 64) return launch_tc<tc::kModeShared, false, 64>(a, maps, grid, st);
+  return fp8 ? launch_tc<tc::kModeShared, true, 128>(a, maps, grid, st) : launch_tc<tc::kModeShared, false, 128>(a, maps, grid, st);
 }
 
 }  // namespace b200

@@ -163,3 +163,33 @@ def test_extend_tcgen05_head_dim_64(hq, hkv, d, pre, ext):
     with pytest.raises(_lib.B200AttnError):  # head_dim 64 over an fp8 pool has no tcgen05 variant
         c8 = G.random_extend_case(hq, hkv, d, pre, ext, seed=1, kv_dtype=torch.float8_e4m3fn)
         G.run_extend_case(c8, force_path=_lib.PATH_TC)
+
+
+def test_extend_tcgen05_tma_tiles_new_tokens_and_consecutive_prefix():
+    """The tcgen05 extend kernel fetches a K / V tile by ONE TMA box copy when its 128 keys are 128 consecutive rows:
+    tiles of new tokens always (rows of k_new / v_new), cached-prefix tiles when the slots are a run (unfragmented
+    token-granular allocator, or pages of >= 128 tokens) -- checked per tile on device.  Same oracle; the debug counter
+    proves which path ran."""
+    from scratchpad_b200 import _lib
+    lib = _lib.load()
+    hq, hkv, d = 8, 2, 128
+    pre, ext = [640, 130], [300, 520]
+
+    def run(c):
+        lib.b200_debug_extend_tma_tiles(1)
+        got = G.run_extend_case(c, force_path=_lib.PATH_TC)[0]
+        n = lib.b200_debug_extend_tma_tiles(1)
+        G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, "tc extend with TMA tiles")
+        return n
+
+    n_random = run(G.random_extend_case(hq, hkv, d, pre, ext, seed=31))                       # new-token tiles only
+    n_contig = run(G.random_extend_case(hq, hkv, d, pre, ext, seed=32, mode="contiguous"))    # + prefix runs
+    n_paged = run(G.random_extend_case(hq, hkv, d, pre, ext, seed=33, page_size=128))         # + 128-token pages
+    assert n_random > 0, "tiles of new tokens must arrive by TMA"
+    assert n_contig > n_random and n_paged > n_random, (n_random, n_contig, n_paged)
+    # fp8 pools widen their rows on chip: row gather only
+    lib.b200_debug_extend_tma_tiles(1)
+    c8 = G.random_extend_case(hq, hkv, d, pre, ext, seed=34, kv_dtype=torch.float8_e4m3fn, mode="contiguous")
+    got = G.run_extend_case(c8, force_path=_lib.PATH_TC)[0]
+    G.assert_close(got, _oracle(c8), G.FP8_ABS, G.FP8_REL, "tc extend fp8")
+    assert lib.b200_debug_extend_tma_tiles(1) == 0

@@ -26,7 +26,11 @@ cap c2 'decode_(mma|paged)' 6 --workload C2 --layers 4
 cap c3u 'decode_(mma|paged)' 6 --workload C3U --layers 4
 cap c2_tp8 'decode_(mma|paged)' 6 --workload C2 --shard 8 --layers 4
 cap c5_tp8 'decode_(mma|paged)' 6 --workload C5 --shard 8 --layers 4
+cap c3b_tp2 'decode_(mma|paged)' 6 --shard 2 --layers 4
+cap c3b_tp4 'decode_(mma|paged)' 6 --shard 4 --layers 4
+cap c3b_tp8 'decode_(mma|paged)' 6 --shard 8 --layers 4
 cap c4 'extend_tc' 2 --workload C4 --layers 2
+cap c4_contig 'extend_tc' 2 --workload C4 --layers 2 --index-mode contiguous
 cap c4_pair 'extend_tc2' 2 --workload C4 --layers 2 --force-path tc2
 python tools/ncu_summary.py --launches $out/${tag}_launches_c3b.csv > $out/${tag}_launches_c3b.txt 2>&1
 ls -la $out/ | head -40

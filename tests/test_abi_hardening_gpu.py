@@ -127,3 +127,25 @@ def test_two_devices_in_one_process():
                                    e["req_pool_indices"], e["seq_lens"], e["extend_seq_lens"], e["extend_start_loc"],
                                    e["sm_scale"], 0.0)
                 G.assert_close(got, ref, G.BF16_ABS, G.BF16_REL, f"extend path {path} on cuda:{dev}")
+
+
+def test_workspace_cannot_grow_under_captured_graphs():
+    """graphs captured earlier hold the workspace's address and a layout that depends on max_bs; a larger
+    batch after capture must be refused, not served from a re-allocated workspace."""
+    c, backend, layer, fb, q = _setup([40, 3, 200])
+    small = backend.max_bs
+    backend.init_cuda_graph_state(small)
+    backend.init_forward_metadata_capture_cuda_graph(3, 3, fb.req_pool_indices, fb.seq_lens, None, ForwardMode.DECODE, None)
+    ws = backend.workspace.data_ptr()
+    big = ForwardBatch(forward_mode=ForwardMode.DECODE, batch_size=small + 1,
+                       req_pool_indices=torch.zeros(small + 1, dtype=torch.int64, device="cuda"),
+                       seq_lens=torch.ones(small + 1, dtype=torch.int64, device="cuda"),
+                       out_cache_loc=torch.zeros(small + 1, dtype=torch.int64, device="cuda"), seq_lens_sum=small + 1,
+                       req_to_token_pool=fb.req_to_token_pool, token_to_kv_pool=fb.token_to_kv_pool, attn_backend=backend)
+    with pytest.raises(RuntimeError, match="after CUDA-graph capture"):
+        backend.init_forward_metadata(big)
+    assert backend.workspace.data_ptr() == ws and backend.max_bs == small
+    # the captured batch size still works
+    backend.init_forward_metadata(fb)
+    got = layer(q, None, None, fb, save_kv_cache=False).view(3, 8, 128).cpu()
+    G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, "after the refused growth")

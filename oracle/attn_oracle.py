@@ -27,11 +27,15 @@ Parity pin: the reference has no golden vectors for this path (SURVEY.md
 section 8c).  The oracle is pinned against the reference's *own* in-tree
 kernels executed in this container under ``TRITON_INTERPRET=1``
 (``oracle/gen_golden.py`` -> ``tests/golden/*.npz``; checked by
-``tests/test_oracle_golden.py``).  The fp8-e4m3 KV variant does not exist in
-the reference (its e5m2 path is broken); its
-semantics here follow ``MHATokenToKVPool.set_kv_buffer`` and are pinned only
-through the bf16 path plus quantise/dequantise identities -- "parity unpinned"
-for fp8 beyond that.
+``tests/test_oracle_golden.py``).  The fp8-e4m3 KV variant has no working
+Triton path in the reference (its e5m2 path is broken, SURVEY.md section 0
+fact 4); its semantics here follow ``MHATokenToKVPool.set_kv_buffer`` and the
+scales the reference's FlashInfer backend passes
+(flashinfer_backend.py:387-388,457-458,475-482), and are pinned on the GPU box
+against that backend itself -- the unmodified ``FlashInferAttnBackend`` from
+``baseline/_ref`` over the installed FlashInfer, on the same quantised pool
+bytes (``tests/test_comparators_gpu.py``: oracle, reference and CUDA path
+agree pairwise within the fp8 tolerance).
 
 All math is fp32 (the tolerance in BASELINE.json is stated against an fp32
 reference).  ``decode_torch_native`` / ``extend_torch_native`` are the

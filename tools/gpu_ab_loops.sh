@@ -13,7 +13,7 @@ if [ $rc -eq 0 ]; then
   done
   python - <<'PY'
 import json, glob
-for f in sorted(glob.glob("gpurun_out/r2e_c4*.json")):
+for f in sorted(glob.glob("gpurun_out/${tag}_c4*.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         print(f.split("/")[-1], f"{d['value']:.0f} TFLOP/s  {d['ms_per_step']*1e3:.0f} us  parity {d['parity_check']}")

@@ -1,7 +1,9 @@
 #!/usr/bin/env bash
 # A/B of library builds on ONE box: B200_ATTN_LIB selects the build (scratchpad_b200/_lib.py), bench.py is the same.
 #   gpurun --timeout 900 -- 'bash tools/gpu_ab_lib.sh TAG'
-# Variants (built here by `B200_OUT=... B200_EXTRA_FLAGS=... bash scratchpad_b200/csrc/build.sh`):
+# Variants (built here, no GPU needed, by
+#   B200_OUT=$PWD/_ab/lib_noreduce_oneloop.so B200_OBJDIR=$PWD/_ab/o1 B200_EXTRA_FLAGS="-DB200_NO_CTA_REDUCE -DB200_ONE_LOOP" bash scratchpad_b200/csrc/build.sh
+#   B200_OUT=$PWD/_ab/lib_reduce_oneloop.so B200_OBJDIR=$PWD/_ab/o2 B200_EXTRA_FLAGS="-DB200_ONE_LOOP" bash scratchpad_b200/csrc/build.sh ):
 #   A = _ab/lib_noreduce_oneloop.so  (round-1 behaviour: one partial per sub-slice, one two-producer loop)
 #   B = _ab/lib_reduce_oneloop.so    (in-CTA sub-slice reduction only)
 #   C = the in-tree library          (reduction + two loop bodies)

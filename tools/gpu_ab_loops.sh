@@ -1,5 +1,9 @@
 #!/usr/bin/env bash
-# Round-2 iteration: (1) the CTA-pair extend kernel: smallest test first, bounded; (2) decode loop-structure A/B
+# decode loop-structure A/B on one box (and the CTA-pair extend kernel's first bounded run).
+# Build the variants first (here, no GPU needed):
+#   B200_OUT=$PWD/_ab/lib_A.so B200_OBJDIR=$PWD/_ab/o1 B200_EXTRA_FLAGS="-DB200_NO_CTA_REDUCE -DB200_ONE_LOOP -DB200_FLAT_LOOP" bash scratchpad_b200/csrc/build.sh
+#   B200_OUT=$PWD/_ab/lib_C.so B200_OBJDIR=$PWD/_ab/o2 B200_EXTRA_FLAGS="-DB200_FLAT_LOOP" bash scratchpad_b200/csrc/build.sh
+#   B200_OUT=$PWD/_ab/lib_E.so B200_OBJDIR=$PWD/_ab/o3 B200_EXTRA_FLAGS="-DB200_NO_CTA_REDUCE" bash scratchpad_b200/csrc/build.sh
 tag="${1:-r2e}"; out=$PWD/gpurun_out; mkdir -p $out
 echo "== pair kernel: one small case" 
 timeout -s KILL 180 python -m pytest "tests/test_extend_gpu.py::test_extend_tcgen05_path_vs_oracle" -x -q -m gpu -k "bf16" > $out/${tag}_pair_small.log 2>&1

@@ -16,8 +16,8 @@ the engine's graph runner captures a whole forward pass
 
 Headline workload = the shape BASELINE.json's ``north_star`` sets its target on:
 Llama-3.1-8B decode, batch 256, 4k context, bf16 KV, page size 1, random-permuted
-slot ids (C3B).  The other BASELINE configs ride along in ``suite`` (C2 and the
-fp8 control C3U at every N; the shared-prefix C3, the 70B TP8 shard C5 and the
+slot ids (C3B).  The other BASELINE configs ride along in ``suite`` (C2, the
+shared-prefix C3 and its fp8 control C3U at every N; the 70B TP8 shard C5 and the
 extend chunk C4 at N=1).  At N GPUs the kv heads are sharded N ways (the engine's
 tensor-parallel layout); every rank serves the same batch with Hkv/N heads, no
 collective on the path.
@@ -1246,11 +1246,13 @@ def main():
     # --- suite: the other BASELINE configs, compact ------------------------------------------------
     if want_suite:
         suite = []
-        plan = [("C2", {}), ("C3U", {})]  # at every N (kv heads sharded like the headline)
+        # at every N (kv heads sharded like the headline): C2, and BASELINE configs[2] -- the shared-prefix decode C3 with
+        # its unshared control C3U
+        plan = [("C2", {}), ("C3U", {}), ("C3", {})]
         if world == 1:
             # C4 in both slot orders SURVEY 8d asks for: random-permuted (worst case) and contiguous runs (what an
             # unfragmented allocator hands out: prefix tiles then arrive by TMA like the new tokens do)
-            plan += [("C3", {}), ("C5", {"shard": 8}), ("C2", {"shard": 8}), ("C3B", {"shard": 8}), ("C4", {}),
+            plan += [("C5", {"shard": 8}), ("C2", {"shard": 8}), ("C3B", {"shard": 8}), ("C4", {}),
                      ("C4", {"index_mode": "contiguous"})]
         for name, over in plan:
             a2 = copy.copy(args)

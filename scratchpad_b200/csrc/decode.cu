@@ -1050,16 +1050,6 @@ __global__ void __launch_bounds__(256, 4) merge_kernel(const int* __restrict__ h
   if (lane < ncas) mx = fmaxf(mx, __ldcg(cas_lse + lane * cas_st + cas_i));
 #pragma unroll
   for (int x = 16; x > 0; x >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, x));
-  auto fold = [&](float w, const float* src) {
-    den += w;
-    if constexpr (VPL == 4) {
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(src));
-      acc[0] += w * v.x; acc[1] += w * v.y; acc[2] += w * v.z; acc[3] += w * v.w;
-    } else {
-      const float2 v = __ldcg(reinterpret_cast<const float2*>(src));
-      acc[0] += w * v.x; acc[1] += w * v.y;
-    }
-  };
   if (mx > -INFINITY) {
     for (int base = 0; base < n; base += 32) {
       const int i = base + lane;
@@ -1096,8 +1086,34 @@ __global__ void __launch_bounds__(256, 4) merge_kernel(const int* __restrict__ h
       }
     }
     if (ncas > 0) {
+      // the shared-prefix leg's partials, four loads in flight at a time (one dependent L2 round trip per partial was
+      // 4-8 of them in a row at the end of every warp)
       const float w_lane = lane < ncas ? ex2(__ldcg(cas_lse + lane * cas_st + cas_i) - mx) : 0.f;
-      for (int j = 0; j < ncas; ++j) fold(__shfl_sync(0xffffffffu, w_lane, j), cas_o + (j * cas_st + cas_i) * DV + lane * VPL);
+      for (int j0 = 0; j0 < ncas; j0 += 4) {
+        float vb4[4][VPL];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (j0 + u < ncas) {
+            const float* src = cas_o + ((j0 + u) * cas_st + cas_i) * DV + lane * VPL;
+            if constexpr (VPL == 4) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(src));
+              vb4[u][0] = v.x; vb4[u][1] = v.y; vb4[u][2] = v.z; vb4[u][3] = v.w;
+            } else {
+              const float2 v = __ldcg(reinterpret_cast<const float2*>(src));
+              vb4[u][0] = v.x; vb4[u][1] = v.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (j0 + u < ncas) {
+            const float w = __shfl_sync(0xffffffffu, w_lane, j0 + u);
+            den += w;
+#pragma unroll
+            for (int e = 0; e < VPL; ++e) acc[e] += w * vb4[u][e];
+          }
+        }
+      }
     }
   }
   const float r = den > 0.f ? 1.f / den : 0.f;  // seq_len == 0 -> zeros

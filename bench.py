@@ -858,7 +858,7 @@ def measure_decode(args, rank, world, local_rank, dist, K, W, want_e2e=True, wan
 
     launches = {"n": 0}
     # the cascade leg is launched (and exits at once when nothing is shared) wherever it is supported
-    cascade_launched = (bool(backend.cascade) and (d == 128 or (d == 64 and w.kv_dtype == torch.bfloat16))
+    cascade_launched = (bool(backend.cascade) and d in (64, 128)
                         and B * (hq // hkv) >= 64 and B <= 1024 and 256 % (hq // hkv) == 0)
     # kv_store (or rope_kv_store), [extend_tc<shared>], decode_mma, merge; + the separate rotary kernel
     KERNELS_PER_LAYER_CALL = 3 + int(cascade_launched) + int(args.rope == "separate")

@@ -60,6 +60,9 @@ WORKLOADS = {
     "C4S": Workload("C4S", 32, 8, 64, 8, torch.bfloat16,
                     "Llama-3.2-1B chunked extend: 8x2k new tokens on 8k cached prefix, causal, bf16",
                     extend_len=2048, prefix_len=8192, layers_total=16),
+    "C4SF": Workload("C4SF", 32, 8, 64, 8, torch.float8_e4m3fn,
+                     "Llama-3.2-1B chunked extend: 8x2k new tokens on 8k cached prefix, causal, FP8-e4m3 KV pool",
+                     extend_len=2048, prefix_len=8192, layers_total=16),
     "C4F": Workload("C4F", 32, 8, 128, 8, torch.float8_e4m3fn,
                     "Llama-3.1-8B chunked extend: 8x2k new tokens on 8k cached prefix, causal, FP8-e4m3 KV pool",
                     extend_len=2048, prefix_len=8192, layers_total=32),

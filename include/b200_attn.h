@@ -49,8 +49,7 @@ extern "C" {
 #define B200_IDX_I64 1
 /* compute path (b200_attn_config.path) */
 #define B200_PATH_MMA 0  /* GQA-packed register-level tensor-core path (mma.sync m16n8k16): decode, generic extend */
-#define B200_PATH_TC 1   /* extend only: tcgen05 + TMEM path, one CTA per 256-row tile (head_dim 128, bf16 or fp8 pool; head_dim 64,
-                          * bf16 pool) */
+#define B200_PATH_TC 1   /* extend only: tcgen05 + TMEM path, one CTA per 256-row tile (head_dim 128 or 64, bf16 or fp8 pool) */
 #define B200_PATH_TC2 2  /* extend only: tcgen05 cta_group::2 path, CTA pairs (head_dim 128 over a bf16 pool).  Opt-in: correct
                           * and tested, measured slower than B200_PATH_TC */
 
@@ -177,7 +176,7 @@ int b200_attn_get_config(int32_t max_bs, int32_t hq, int32_t hkv, int32_t d, int
  * tokens and the group has >= 64 query rows per kv head.  b200_attn_decode then computes that prefix once per kv
  * head as a dense tcgen05 contraction over all queries of the group and only the per-request suffixes through the
  * split-KV kernel; the LSE merge combines both.  Detection is on device (no host sync, CUDA-graph safe); head_dim
- * 128, or 64 with a bf16 pool, and bs <= 1024; otherwise the flag is ignored.
+ * 128 or 64 and bs <= 1024; otherwise the flag is ignored.
  * req_to_token may be NULL when cascade == 0. */
 int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs,
                    const void* req_pool_indices, const void* seq_lens, int32_t idx_dtype,

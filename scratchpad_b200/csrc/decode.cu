@@ -1433,7 +1433,7 @@ static int cas_max_tiles(int bs, int g) {
 
 // cascade is honoured only where the dense leg exists and is worth launching
 static bool cascade_supported(int bs, int hq, int hkv, int d, int dv, int kv_dtype) {
-  const bool shape_ok = d == dv && (d == 128 || (d == 64 && kv_dtype == B200_KV_BF16));
+  const bool shape_ok = d == dv && (d == 128 || d == 64);
   return shape_ok && hkv > 0 && 256 % (hq / hkv) == 0 && bs * (hq / hkv) >= kMinCasRows;
 }
 

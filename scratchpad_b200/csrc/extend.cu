@@ -401,10 +401,10 @@ extern "C" int b200_attn_extend(const b200_extend_params* p, b200_stream_t strea
       p->o_stride_h % 2 || mis16(p->q) || mis16(p->k_new) || mis16(p->v_new) || mis16(p->k_buf) || mis16(p->v_buf) ||
       (reinterpret_cast<uintptr_t>(p->o) & 3))
     return B200_ERR_INVALID;
-  // tcgen05/TMEM path: head_dim 128 (bf16 or fp8-e4m3 pool) or 64 (bf16 pool), 16-byte aligned output rows; auto-selected once the
+  // tcgen05/TMEM path: head_dim 128 or 64 (bf16 or fp8-e4m3 pool), 16-byte aligned output rows; auto-selected once the
   // longest extend fills at least half of its 256-row CTA tile (short MIXED-mode rows stay on mma.sync)
   // (k_new / v_new heads contiguous inside a token row, as in the fused qkv GEMM output)
-  const bool tc_ok = (p->d == 128 || (p->d == 64 && !fp8)) && p->o_stride_t % 8 == 0 && p->o_stride_h % 8 == 0 && !mis16(p->o) && g <= 128 &&
+  const bool tc_ok = (p->d == 128 || p->d == 64) && p->o_stride_t % 8 == 0 && p->o_stride_h % 8 == 0 && !mis16(p->o) && g <= 128 &&
                      p->kn_stride_h == p->d && p->vn_stride_h == p->dv;
   const bool pair_ok = tc_ok && p->d == 128 && !fp8;
   if (p->force_path == B200_PATH_TC && !tc_ok) return B200_ERR_UNSUPPORTED;

@@ -9,7 +9,7 @@
 //                     k_new/v_new[start_i : start_i+t+1].
 //   MODE kModeShared  the decode queries of a whole batch against the prefix all its requests share.
 //   F16               the pool is fp8-e4m3: rows are widened to f16 on chip and the MMAs run f16 x f16.
-//   D                 head_dim 128, or 64 (bf16 pools).
+//   D                 head_dim 128 or 64.
 //
 // One CTA per SM, 16 warps in 4 warpgroups, warp-specialised:
 //   warps 0-3 / 4-7 : softmax warpgroups for Q tile 0 / 1 (thread = one query row = one TMEM lane);
@@ -150,7 +150,7 @@ __device__ __forceinline__ uint32_t tile_off(int r, int cb, int c) {
 // scale and v_scale into the epilogue, like the split-KV kernel does.
 template <int MODE, bool F16, int D>
 __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_constant__ Args a, const __grid_constant__ TcMaps tm) {
-  static_assert(D == 128 || (D == 64 && !F16), "head_dim 64 over an fp8 pool stays on the mma.sync kernels");
+  static_assert(D == 128 || D == 64, "head_dim 128 or 64");
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) TC_TRACE(16, 0);
@@ -263,12 +263,17 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_con
       //  New tokens (extend mode; bf16, never read from the pool) are copied straight to their final place in
       //  phase A and converted in place in phase B: bf16 -> x 1/scale -> f16, so that the per-head scale folds
       //  into the softmax scale (K) and the epilogue (V) for pool rows and new rows alike.
-      // lane & 7 = 16-byte chunk of the 128-byte raw row = f16 chunks 2c, 2c+1; rows 16q + 4pw + lane/8
-      // (constant row & 7 per thread).
-      const int pw = warp - kProdWarp0, c8 = lane & 7, rr = 4 * pw + (lane >> 3), rr7 = rr & 7;
-      const int64_t col8 = static_cast<int64_t>(kvh) * kD + c8 * 16;
+      // A raw row is D bytes = CPRR 16-byte chunks, so a warp instruction covers 32 / CPRR rows and a thread owns raw
+      // chunk c8 (= f16 chunks 2c, 2c+1) of rows rr + ROWSTEP q, q < NQ (ROWSTEP is a multiple of 8: constant row & 7
+      // per thread).  head_dim 128: 8 chunks, rows 16q + 4pw + lane/8, the f16 tile fills the slot and the raw rows
+      // alias its second element block (see phase B); head_dim 64: 4 chunks, rows 32q + 8pw + lane/4, the f16 tile is
+      // the slot's lower 16 KiB and the raw rows ([128 x 64 B]) sit above it, no aliasing.
+      constexpr int CPRR = D / 16, ROWSTEP = 4 * (32 / CPRR), NQ = kBN / ROWSTEP;
+      constexpr uint32_t kRawStep = ROWSTEP * D, kOutStep = ROWSTEP * 128;  // bytes between a thread's rows: raw / f16
+      const int pw = warp - kProdWarp0, c8 = lane % CPRR, rr = (32 / CPRR) * pw + lane / CPRR, rr7 = rr & 7;
+      const int64_t col8 = static_cast<int64_t>(kvh) * D + c8 * 16;
       const uint32_t ring = sbase + kSmemRing;
-      const uint32_t raw_thread = kColBlockBytes + rr * 128 + c8 * 16;
+      const uint32_t raw_thread = kColBlockBytes + rr * D + c8 * 16;
       const uint32_t out_thread = (c8 >> 2) * kColBlockBytes + rr * 128;
       const uint32_t o0 = (((2 * c8) & 7) ^ rr7) << 4, o1 = (((2 * c8 + 1) & 7) ^ rr7) << 4;
       const float inv_ks = a.k_scale ? 1.f / __ldg(a.k_scale + kvh) : 1.f;
@@ -278,16 +283,16 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_con
         const int p_base = (n >> 1) * kBN + rr;
         const float inv = (n & 1) ? inv_vs : inv_ks;
 #pragma unroll
-        for (int q0 = 0; q0 < 8; q0 += 4) {  // 4 rows at a time: this warpgroup runs on 64 registers
+        for (int q0 = 0; q0 < NQ; q0 += 4) {  // 4 rows at a time: this warpgroup runs on 64 registers
           uint32_t raw[4][4];
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            if (MODE == kModeShared || p_base + 16 * (q0 + q) < pre) ld_shared_v4(slot_base + raw_thread + (q0 + q) * 2048, raw[q]);
+            if (MODE == kModeShared || p_base + ROWSTEP * (q0 + q) < pre) ld_shared_v4(slot_base + raw_thread + (q0 + q) * kRawStep, raw[q]);
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint32_t dst = slot_base + out_thread + (q0 + q) * 2048;
-            if (MODE == kModeShared || p_base + 16 * (q0 + q) < pre) {
+            const uint32_t dst = slot_base + out_thread + (q0 + q) * kOutStep;
+            if (MODE == kModeShared || p_base + ROWSTEP * (q0 + q) < pre) {
               uint32_t h[8];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -320,24 +325,24 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_con
         mbar_wait(bar_empty(s), ((n / kSlots) & 1) ^ 1);
         const uint32_t slot_base = ring + s * kTileBytes;
         if (MODE == kModeShared || (j + 1) * kBN <= pre) {
-          int slot[8];
+          int slot[NQ];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) slot[q] = __ldg(row + j * kBN + 16 * q + rr);
+          for (int q = 0; q < NQ; ++q) slot[q] = __ldg(row + j * kBN + ROWSTEP * q + rr);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) cp_async16(slot_base + raw_thread + q * 2048, kv_row_ptr(pool8, slot[q], pool_st), 16);
+          for (int q = 0; q < NQ; ++q) cp_async16(slot_base + raw_thread + q * kRawStep, kv_row_ptr(pool8, slot[q], pool_st), 16);
         } else {
-          const uint8_t* fresh = reinterpret_cast<const uint8_t*>(is_v ? a.v_new : a.k_new) + static_cast<int64_t>(kvh) * (kD * 2) + c8 * 32;
+          const uint8_t* fresh = reinterpret_cast<const uint8_t*>(is_v ? a.v_new : a.k_new) + static_cast<int64_t>(kvh) * (D * 2) + c8 * 32;
           const int64_t f_st = (is_v ? a.vn_st : a.kn_st) * 2;
 #pragma unroll 2
-          for (int q = 0; q < 8; ++q) {
-            const int p = j * kBN + 16 * q + rr, pc = min(p, kv_len - 1);
+          for (int q = 0; q < NQ; ++q) {
+            const int p = j * kBN + ROWSTEP * q + rr, pc = min(p, kv_len - 1);
             if (pc < pre) {
-              cp_async16(slot_base + raw_thread + q * 2048, kv_row_ptr(pool8, __ldg(row + pc), pool_st), 16);
+              cp_async16(slot_base + raw_thread + q * kRawStep, kv_row_ptr(pool8, __ldg(row + pc), pool_st), 16);
             } else {
               const uint8_t* src = fresh + static_cast<int64_t>(start + pc - pre) * f_st;
               const int nb = p < kv_len ? 16 : 0;  // keys past the end: zeros (masked by the softmax anyway)
-              cp_async16(slot_base + out_thread + q * 2048 + o0, src, nb);
-              cp_async16(slot_base + out_thread + q * 2048 + o1, src + 16, nb);
+              cp_async16(slot_base + out_thread + q * kOutStep + o0, src, nb);
+              cp_async16(slot_base + out_thread + q * kOutStep + o1, src + 16, nb);
             }
           }
         }
@@ -977,7 +982,7 @@ static int launch_tc(const tc::Args& a, const tc::TcMaps& maps, dim3 grid, cudaS
   return launch_pdl(kern, grid, dim3(tc::kThreads), tc::kSmemBytes, st, a, maps);
 }
 
-// Called by b200_attn_extend (extend.cu) for head_dim 128 (bf16 or fp8 pool) and 64 (bf16 pool).  Strides and pointers have been validated there.
+// Called by b200_attn_extend (extend.cu) for head_dim 128 and 64 (bf16 or fp8 pool).  Strides and pointers have been validated there.
 int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
   const bool fp8 = p->kv_dtype == B200_KV_FP8_E4M3;
   tc::Args a{};
@@ -1032,7 +1037,7 @@ int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
         cached_pool_map(&maps.pool_v, p->v_buf, a.v_st_bytes, p->kv_pool_rows, p->hkv, p->dv, false, tc::kBN, 1) == B200_OK)
       a.tma |= 2;
   }
-  if (p->d == 64) return fp8 ? B200_ERR_UNSUPPORTED : launch_tc<tc::kModeExtend, false, 64>(a, maps, grid, st);
+  if (p->d == 64) return fp8 ? launch_tc<tc::kModeExtend, true, 64>(a, maps, grid, st) : launch_tc<tc::kModeExtend, false, 64>(a, maps, grid, st);
   return fp8 ? launch_tc<tc::kModeExtend, true, 128>(a, maps, grid, st) : launch_tc<tc::kModeExtend, false, 128>(a, maps, grid, st);
 }
 
@@ -1044,7 +1049,7 @@ int launch_shared_prefix_tc(const b200_decode_params* p, const CasTables& t, flo
                             cudaStream_t st) {
   const int g = p->hq / p->hkv;
   const bool fp8 = p->kv_dtype == B200_KV_FP8_E4M3;
-  if (p->d != p->dv || tc::kRows % g != 0 || !(p->d == 128 || (p->d == 64 && !fp8))) return B200_ERR_UNSUPPORTED;
+  if (p->d != p->dv || tc::kRows % g != 0 || !(p->d == 128 || p->d == 64)) return B200_ERR_UNSUPPORTED;
   tc::Args a{};
   a.q = static_cast<const __nv_bfloat16*>(p->q);
   a.q_st = p->q_stride_t;
@@ -1070,7 +1075,7 @@ int launch_shared_prefix_tc(const b200_decode_params* p, const CasTables& t, flo
   const dim3 grid(p->hkv, nsplit, (p->bs + a.bm_t - 1) / a.bm_t);  // z = row-tile lanes; CTAs loop over further tiles
   tc::TcMaps maps;
   memset(&maps, 0, sizeof(maps));
-  if (p->d == 64) return launch_tc<tc::kModeShared, false, 64>(a, maps, grid, st);
+  if (p->d == 64) return fp8 ? launch_tc<tc::kModeShared, true, 64>(a, maps, grid, st) : launch_tc<tc::kModeShared, false, 64>(a, maps, grid, st);
   return fp8 ? launch_tc<tc::kModeShared, true, 128>(a, maps, grid, st) : launch_tc<tc::kModeShared, false, 128>(a, maps, grid, st);
 }
 

@@ -401,7 +401,7 @@ def test_decode_cascade_under_cuda_graph_with_padded_rows():
 
 
 def test_decode_cascade_head_dim_64():
-    """Llama-3.2-1B shapes (head_dim 64, bf16 pool) through the shared-prefix leg; fp8 pools of that width stay off."""
+    """Llama-3.2-1B shapes (head_dim 64) through the shared-prefix leg, bf16 and (round 2) fp8-e4m3 pools."""
     lens = [1100 + 9 * i for i in range(20)]
     c = G.random_decode_case(32, 8, 64, lens, seed=17, shared_prefix=1090)
     got, backend = _run_full(c, cascade=True)[:2]
@@ -409,8 +409,10 @@ def test_decode_cascade_head_dim_64():
     G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, what="cascade d64")
     c = G.random_decode_case(32, 8, 64, lens, seed=17, shared_prefix=1090, kv_dtype=torch.float8_e4m3fn)
     got, backend = _run_full(c, cascade=True)[:2]
-    assert _shared_len(backend) == 0
-    G.assert_close(got, _oracle(c), G.FP8_ABS, G.FP8_REL, what="d64 fp8 stays on split-KV")
+    assert _shared_len(backend) == 1024
+    G.assert_close(got, _oracle(c), G.FP8_ABS, G.FP8_REL, what="cascade d64 fp8")
+    off = _run_full(c, cascade=False)[0]
+    G.assert_close(got, off, G.FP8_ABS, G.FP8_REL, what="cascade d64 fp8 vs split-KV only")
 
 
 def _multi_group_case(hq, hkv, d, groups, seed, kv_dtype=torch.bfloat16):

@@ -160,9 +160,12 @@ def test_extend_tcgen05_head_dim_64(hq, hkv, d, pre, ext):
     c = G.random_extend_case(hq, hkv, d, pre, ext, seed=hq * 13 + hkv + len(pre))
     got = G.run_extend_case(c, force_path=_lib.PATH_TC)[0]
     G.assert_close(got, _oracle(c), G.BF16_ABS, G.BF16_REL, what=f"tc d64 {hq}/{hkv}/{pre}/{ext}")
-    with pytest.raises(_lib.B200AttnError):  # head_dim 64 over an fp8 pool has no tcgen05 variant
-        c8 = G.random_extend_case(hq, hkv, d, pre, ext, seed=1, kv_dtype=torch.float8_e4m3fn)
-        G.run_extend_case(c8, force_path=_lib.PATH_TC)
+    # head_dim 64 over an fp8-e4m3 pool (round 2): raw 64-byte rows widened to f16 on chip, per-head and per-tensor scales
+    for per_head in (True, False):
+        c8 = G.random_extend_case(hq, hkv, d, pre, ext, seed=1, kv_dtype=torch.float8_e4m3fn, per_head=per_head)
+        got8 = G.run_extend_case(c8, force_path=_lib.PATH_TC)[0]
+        G.assert_close(got8, _oracle(c8), G.FP8_ABS, G.FP8_REL, what=f"tc d64 fp8 {hq}/{hkv}/{pre}/{ext}")
+        G.assert_close(got8, G.run_extend_case(c8, force_path=_lib.PATH_MMA)[0], G.FP8_ABS, G.FP8_REL, what="tc d64 fp8 vs mma.sync")
 
 
 def test_extend_tcgen05_tma_tiles_new_tokens_and_consecutive_prefix():

@@ -55,8 +55,7 @@ def test_fuzz_extend_both_kernel_families(seed):
     want = O.extend_ref(c["q"], c["k_new"], c["v_new"], c["k_buf"], c["v_buf"], c["req_to_token"], c["req_pool_indices"],
                         c["seq_lens"], c["extend_seq_lens"], c["extend_start_loc"], c["sm_scale"], 0.0, c.get("kv_dtype"),
                         c.get("k_scale"), c.get("v_scale"))
-    tc_ok = d == 128 or not fp8  # head_dim 64 over an fp8 pool has no tcgen05 variant
-    for path in ([_lib.PATH_MMA] + ([_lib.PATH_TC] if tc_ok else []) + ([_lib.PATH_TC2] if d == 128 and not fp8 else [])):
+    for path in ([_lib.PATH_MMA, _lib.PATH_TC] + ([_lib.PATH_TC2] if d == 128 and not fp8 else [])):
         got = G.run_extend_case(c, force_path=path, save_kv_cache=rng.random() < 0.5)[0]
         G.assert_close(got, want, *tol, what=f"fuzz extend seed {seed} path {path}: {hq}/{hkv}/{d} fp8={fp8} pre={pre} ext={ext}")
 

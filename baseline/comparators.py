@@ -26,7 +26,7 @@ from . import ref_loader
 
 
 def _ref_runner(hq_total: int, hkv_total: int, head_dim: int, tp_size: int, context_len: int, kv_dtype: torch.dtype,
-                device, r2t_pool, kv_pool, max_reqs: int):
+                device, r2t_pool, kv_pool, max_reqs: int, model_dtype: torch.dtype = torch.bfloat16):
     """What FlashInferAttnBackend.__init__ reads from ModelRunner (flashinfer_backend.py:62-74,107)."""
     model_config = SimpleNamespace(
         num_attention_heads=hq_total, head_dim=head_dim, context_len=context_len,
@@ -34,10 +34,10 @@ def _ref_runner(hq_total: int, hkv_total: int, head_dim: int, tp_size: int, cont
         hf_config=SimpleNamespace(architectures=["LlamaForCausalLM"]),
     )
     server_args = SimpleNamespace(
-        kv_cache_dtype="auto" if kv_dtype == torch.bfloat16 else "fp8_e4m3", enable_dp_attention=False,
+        kv_cache_dtype="auto" if kv_dtype == model_dtype else "fp8_e4m3", enable_dp_attention=False,
         triton_attention_num_kv_splits=8, attention_backend="flashinfer",
     )
-    return SimpleNamespace(model_config=model_config, tp_size=tp_size, device=device, dtype=torch.bfloat16,
+    return SimpleNamespace(model_config=model_config, tp_size=tp_size, device=device, dtype=model_dtype,
                            kv_cache_dtype=kv_dtype, server_args=server_args, req_to_token_pool=r2t_pool,
                            token_to_kv_pool=kv_pool, sliding_window_size=None)
 
@@ -47,8 +47,9 @@ class RefState:
 
     def __init__(self, *, req_to_token: torch.Tensor, k_buffers, v_buffers, kv_dtype: torch.dtype, hq: int, hkv: int,
                  head_dim: int, k_scale: Optional[float] = None, v_scale: Optional[float] = None,
-                 logit_cap: float = 0.0, sm_scale: Optional[float] = None):
+                 logit_cap: float = 0.0, sm_scale: Optional[float] = None, model_dtype: torch.dtype = torch.bfloat16):
         pool_mod = ref_loader.load("memory.pool")
+        self.model_dtype = model_dtype  # ModelRunner.dtype: bf16, or fp16 (model_runner.py:366-367 makes it the pool's too)
         self.fi_mod = None
         dev = req_to_token.device
         self.device = dev
@@ -75,7 +76,7 @@ class RefState:
 
     def runner(self, context_len: int):
         return _ref_runner(self.hq, self.hkv, self.d, 1, context_len, self.kv_dtype, str(self.device), self.r2t_pool,
-                           self.kv_pool, self.r2t_pool.size)
+                           self.kv_pool, self.r2t_pool.size, self.model_dtype)
 
     def decode_batch(self, req_pool_indices, seq_lens, out_cache_loc, backend):
         F = self.fwd_mod

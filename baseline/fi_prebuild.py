@@ -35,6 +35,12 @@ def main() -> int:
             for kv in (bf16, fp8):
                 jobs.append(("prefill", get_batch_prefill_module,
                              ("fa2", bf16, kv, bf16, i32, hd, hd, none, False, cap, False)))
+    # fp16 model dtype (fp16 or fp8 pool), no soft cap: the fp16 comparator cases of tests/test_fp16_gpu.py
+    f16 = torch.float16
+    for hd in (64, 128):
+        jobs.append(("decode", get_batch_decode_module, (f16, f16, f16, i32, hd, hd, none, False, False)))
+        for kv in (f16, fp8):
+            jobs.append(("prefill", get_batch_prefill_module, ("fa2", f16, kv, f16, i32, hd, hd, none, False, False, False)))
     jobs.append(("cascade", get_cascade_module, ()))
     t0 = time.time()
     for name, fn, args in jobs:

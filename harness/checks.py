@@ -17,10 +17,10 @@ from scratchpad_b200 import _lib
 def naive_decode(q3: torch.Tensor, kb: torch.Tensor, vb: torch.Tensor, req_to_token: torch.Tensor,
                  req_pool_indices: torch.Tensor, seq_lens: torch.Tensor, sm_scale: float, logit_cap: float,
                  kv_code: int, k_scale: Optional[torch.Tensor], v_scale: Optional[torch.Tensor]) -> torch.Tensor:
-    """q3 [B, Hq, D] bf16 (any token / head stride); returns o [B, Hq, Dv] bf16."""
+    """q3 [B, Hq, D] bf16 or fp16 (any token / head stride); returns o [B, Hq, Dv] in q3's dtype."""
     b, hq, d = q3.shape
     hkv, dv = kb.shape[1], vb.shape[2]
-    o = torch.empty((b, hq, dv), dtype=torch.bfloat16, device=q3.device)
+    o = torch.empty((b, hq, dv), dtype=q3.dtype, device=q3.device)
     if req_pool_indices.dtype != seq_lens.dtype:
         seq_lens = seq_lens.to(req_pool_indices.dtype)
     p = _lib.DecodeParams(
@@ -30,7 +30,8 @@ def naive_decode(q3: torch.Tensor, kb: torch.Tensor, vb: torch.Tensor, req_to_to
         req_to_token=req_to_token.data_ptr(), req_to_token_stride=req_to_token.stride(0),
         bs=b, hq=hq, hkv=hkv, d=d, dv=dv, kv_dtype=kv_code, sm_scale=float(sm_scale), logit_cap=float(logit_cap),
         k_scale=None if k_scale is None else k_scale.data_ptr(), v_scale=None if v_scale is None else v_scale.data_ptr(),
-        workspace=None, workspace_bytes=0, max_bs=b, force_path=-1)
+        workspace=None, workspace_bytes=0, max_bs=b, force_path=-1,
+        act_dtype=_lib.ACT_F16 if q3.dtype == torch.float16 else _lib.ACT_BF16)
     code = _lib.IDX_I64 if req_pool_indices.dtype == torch.int64 else _lib.IDX_I32
     rc = _lib.load().b200_debug_decode_naive(p, req_pool_indices.data_ptr(), seq_lens.data_ptr(), code,
                                              torch.cuda.current_stream().cuda_stream)

@@ -91,8 +91,11 @@ def workload_seq_lens(w: Workload, gen: torch.Generator) -> List[int]:
 def make_model_runner(hq_total: int, hkv_total: int, head_dim: int, tp_size: int = 1, layer_num: int = 1,
                       pool_tokens: int = 4096, max_reqs: int = 64, context_len: int = 4096,
                       kv_dtype: torch.dtype = torch.bfloat16, device: str = "cuda", fused_kv: bool = False,
-                      page_size: int = 1):
-    """The attributes AttentionBackend.__init__ may read over freshly allocated pools."""
+                      page_size: int = 1, dtype: torch.dtype = None):
+    """The attributes AttentionBackend.__init__ may read over freshly allocated pools.  ``dtype`` = the
+    model dtype (default: the pool's when that is a 16-bit type -- kv_cache_dtype "auto" -- else bfloat16)."""
+    if dtype is None:
+        dtype = kv_dtype if kv_dtype in (torch.bfloat16, torch.float16) else torch.bfloat16
     hkv_local = max(1, hkv_total // tp_size)  # ModelConfig.get_num_kv_heads (model_config.py:159-166)
     model_config = SimpleNamespace(
         num_attention_heads=hq_total, head_dim=head_dim, context_len=context_len,
@@ -101,8 +104,8 @@ def make_model_runner(hq_total: int, hkv_total: int, head_dim: int, tp_size: int
     r2t = ReqToTokenPool(max_reqs + 1, context_len + 4, device)
     kv = MHATokenToKVPool(pool_tokens, page_size, kv_dtype, hkv_local, head_dim, layer_num, device, fused_kv=fused_kv)
     return SimpleNamespace(
-        model_config=model_config, tp_size=tp_size, device=device, dtype=torch.bfloat16,
-        kv_cache_dtype="auto" if kv_dtype == torch.bfloat16 else "fp8_e4m3",
+        model_config=model_config, tp_size=tp_size, device=device, dtype=dtype,
+        kv_cache_dtype="auto" if kv_dtype == dtype else "fp8_e4m3",
         server_args=SimpleNamespace(enable_dp_attention=False, attention_backend="cuda_b200"),
         req_to_token_pool=r2t, token_to_kv_pool=kv, sliding_window_size=None,
     )

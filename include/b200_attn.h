@@ -15,9 +15,9 @@
  *   req_to_token  int32 [rows, cols] row-major, row stride given in elements
  *                 (scratchpad/memory/pool.py:16-22)
  *   k_buf/v_buf   [P+1, Hkv, D] contiguous in the last two dims, token stride
- *                 given in elements; bf16, or fp8-e4m3 stored as bytes
+ *                 given in elements; bf16 / fp16 (the model dtype), or fp8-e4m3 stored as bytes
  *                 (pool.py:298-317,373-390); slot 0 is the padding slot
- *   q / o         bf16 [T, Hq, D] with last dim contiguous, token and head
+ *   q / o         bf16 or fp16 (act_dtype) [T, Hq, D] with last dim contiguous, token and head
  *                 strides in elements (q may be a column slice of the fused
  *                 qkv GEMM output, scratchpad/nn/models/llama/llama.py:149-152)
  *   req_pool_indices, seq_lens  int32 or int64 (eager batches are int64,
@@ -37,11 +37,18 @@
 extern "C" {
 #endif
 
-#define B200_ATTN_ABI_VERSION 9
+#define B200_ATTN_ABI_VERSION 10
 
 /* kv_dtype */
 #define B200_KV_BF16 0
 #define B200_KV_FP8_E4M3 1
+#define B200_KV_F16 2
+/* act_dtype: the model dtype -- q, the new tokens' k / v and o (model_runner.dtype; `o` is "same dtype as q",
+ * triton_backend.py:171-176).  Pools that go with it: bf16 activations over a bf16 or fp8-e4m3 pool, fp16 activations
+ * over an fp16 or fp8-e4m3 pool (kv_cache_dtype "auto" = the model dtype, model_runner.py:366-367; fp32 checkpoints
+ * are served in fp16 by default, config/utils.py:41-43); any other pairing returns B200_ERR_UNSUPPORTED. */
+#define B200_ACT_BF16 0
+#define B200_ACT_F16 1
 /* b200_decode_params.page_size */
 #define B200_PAGE_AUTO (-1)
 /* idx_dtype */
@@ -83,12 +90,12 @@ typedef struct b200_attn_config {
  * from triton_backend.py:183-195 and the FlashInfer decode wrapper call,
  * flashinfer_backend.py:475-482). */
 typedef struct b200_decode_params {
-  const void* q;            /* bf16 [bs, hq, d] */
+  const void* q;            /* act_dtype [bs, hq, d] */
   int64_t q_stride_t, q_stride_h;
-  const void* k_buf;        /* [P+1, hkv, d]  bf16 or fp8 bytes */
+  const void* k_buf;        /* [P+1, hkv, d]  bf16 / fp16 or fp8 bytes */
   const void* v_buf;        /* [P+1, hkv, dv] */
   int64_t k_stride_t, v_stride_t; /* token stride in elements */
-  void* o;                  /* bf16 [bs, hq, dv] */
+  void* o;                  /* act_dtype [bs, hq, dv] */
   int64_t o_stride_t, o_stride_h;
   const int32_t* req_to_token;
   int64_t req_to_token_stride;
@@ -117,6 +124,8 @@ typedef struct b200_decode_params {
                              * B200_PAGE_AUTO: token-granular pool, TMA for every tile whose slots happen to be
                              * consecutive (an unfragmented allocator hands out runs, memory/pool.py:240-253). */
   int64_t kv_pool_rows;     /* paged only: token rows of k_buf / v_buf (bounds of the tensor maps) */
+  int32_t act_dtype;        /* B200_ACT_*: dtype of q and o (0 = bf16) */
+  int32_t reserved0;
 } b200_decode_params;
 
 /* One layer's extend / chunked-prefill attention over prefix-cached chunks
@@ -124,15 +133,15 @@ typedef struct b200_decode_params {
  * query row t of request i attends to the pool slots req_to_token[r, :pre_i]
  * (non-causal) and to k_new/v_new[start_i : start_i + t + 1] (causal). */
 typedef struct b200_extend_params {
-  const void* q;            /* bf16 [T, hq, d] */
+  const void* q;            /* act_dtype [T, hq, d] */
   int64_t q_stride_t, q_stride_h;
-  const void* k_new;        /* bf16 [T, hkv, d]  (model dtype, unquantised) */
-  const void* v_new;        /* bf16 [T, hkv, dv] */
+  const void* k_new;        /* act_dtype [T, hkv, d]  (model dtype, unquantised) */
+  const void* v_new;        /* act_dtype [T, hkv, dv] */
   int64_t kn_stride_t, kn_stride_h, vn_stride_t, vn_stride_h;
   const void* k_buf;
   const void* v_buf;
   int64_t k_stride_t, v_stride_t;
-  void* o;                  /* bf16 [T, hq, dv] */
+  void* o;                  /* act_dtype [T, hq, dv] */
   int64_t o_stride_t, o_stride_h;
   const int32_t* req_to_token;
   int64_t req_to_token_stride;
@@ -154,6 +163,8 @@ typedef struct b200_extend_params {
                                  * tiles whose 128 slots are consecutive by TMA (checked per tile on device); 0 / 1: row gather.
                                  * Tiles of 128 new tokens (rows of k_new / v_new) are fetched by TMA whatever the value. */
   int64_t kv_pool_rows;         /* token rows of k_buf / v_buf (bounds of the pool's tensor maps); 0 = unknown, no prefix TMA */
+  int32_t act_dtype;            /* B200_ACT_*: dtype of q, k_new, v_new and o (0 = bf16) */
+  int32_t reserved0;
 } b200_extend_params;
 
 int b200_attn_abi_version(void);
@@ -188,21 +199,23 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream);
 int b200_attn_extend(const b200_extend_params* p, b200_stream_t stream);
 
 /* KV write: k_buf[loc[t]] = quant(k[t]) (replaces MHATokenToKVPool.set_kv_buffer's
- * two index_put_ launches + div_/cast, pool.py:392-424).  k/v are bf16
+ * two index_put_ launches + div_/cast, pool.py:392-424).  k/v are act_dtype (bf16 or fp16)
  * [T, hkv, d] with strides in elements; loc int32/int64 [T]; for fp8 the value
- * stored is e4m3(bf16(x / scale[h])) and k/v are NOT modified in place. */
+ * stored is e4m3(act(x / scale[h])) -- the division rounded to the model dtype first, as the reference's
+ * in-place div_ does -- and k/v are NOT modified in place. */
 int b200_kv_store(void* k_buf, void* v_buf, int64_t k_stride_t, int64_t v_stride_t,
                   const void* loc, int32_t loc_dtype, const void* k, const void* v,
                   int64_t k_src_stride_t, int64_t k_src_stride_h, int64_t v_src_stride_t,
                   int64_t v_src_stride_h, int32_t num_tokens, int32_t hkv, int32_t d, int32_t dv,
-                  int32_t kv_dtype, const float* k_scale, const float* v_scale, b200_stream_t stream);
+                  int32_t kv_dtype, int32_t act_dtype, const float* k_scale, const float* v_scale,
+                  b200_stream_t stream);
 
 /* Rotary position embedding fused with the KV write: one launch replaces the model's
  * `q, k = self.rotary_emb(positions, q, k)` (scratchpad/nn/models/llama/llama.py:149-152 ->
  * RotaryEmbedding.forward_cuda, scratchpad/nn/layers/rotary_embedding.py:131-164, an in-place kernel on q and k)
  * and MHATokenToKVPool.set_kv_buffer (memory/pool.py:392-424, two index_put_ + div_/cast).
  * Arithmetic is RotaryEmbedding.forward_native's (rotary_embedding.py:24-49,101-129) in the model dtype: every
- * product and every sum is rounded to bf16, so results are bit-identical to the reference's:
+ * product and every sum is rounded to bf16 (fp16 when act_dtype says so), so results are bit-identical to the reference's:
  *   o1 = bf16(bf16(x1*cos) - bf16(x2*sin)),  o2 = bf16(bf16(x2*cos) + bf16(x1*sin)),
  * (x1, x2) = (x[i], x[i + rotary_dim/2]) for neox style, (x[2i], x[2i+1]) for GPT-J style; elements
  * >= rotary_dim pass through.  cos/sin come from the module's cos_sin_cache[positions[t]] = [cos | sin]
@@ -211,16 +224,17 @@ int b200_kv_store(void* k_buf, void* v_buf, int64_t k_stride_t, int64_t v_stride
  * in place only when write_back_k != 0 (the extend kernels read the new tokens' K from the k argument;
  * decode reads it from the pool).  v is stored as b200_kv_store does. */
 typedef struct b200_rope_store_params {
-  void* q;                  /* bf16 [T, hq, d], rotated in place; NULL = no q */
+  void* q;                  /* act_dtype [T, hq, d], rotated in place; NULL = no q */
   int64_t q_stride_t, q_stride_h;
-  void* k;                  /* bf16 [T, hkv, d] */
+  void* k;                  /* act_dtype [T, hkv, d] */
   int64_t k_src_stride_t, k_src_stride_h;
-  const void* v;            /* bf16 [T, hkv, dv] */
+  const void* v;            /* act_dtype [T, hkv, dv] */
   int64_t v_src_stride_t, v_src_stride_h;
   const void* positions;    /* [T] int32 / int64 (pos_dtype = B200_IDX_*) */
   const void* cos_sin_cache; /* [max_position, rotary_dim] = [cos(rotary_dim/2) | sin(rotary_dim/2)] */
   int64_t cache_stride;     /* row stride in elements */
-  int32_t cache_dtype;      /* B200_CACHE_BF16 / B200_CACHE_F32 (f32 is rounded to bf16 first: cos.to(x.dtype)) */
+  int32_t cache_dtype;      /* B200_CACHE_BF16 / B200_CACHE_F16 (must be the model dtype) / B200_CACHE_F32 (rounded to the
+                             * model dtype first: cos.to(x.dtype)) */
   int32_t pos_dtype;
   int32_t rotary_dim;       /* multiple of 16, <= d */
   int32_t is_neox;
@@ -234,10 +248,11 @@ typedef struct b200_rope_store_params {
   const float* k_scale;
   const float* v_scale;
   int32_t write_back_k;
-  int32_t reserved;
+  int32_t act_dtype;        /* B200_ACT_*: dtype of q, k and v (0 = bf16) */
 } b200_rope_store_params;
 #define B200_CACHE_BF16 0
 #define B200_CACHE_F32 1
+#define B200_CACHE_F16 2
 
 int b200_rope_kv_store(const b200_rope_store_params* p, b200_stream_t stream);
 

@@ -48,7 +48,7 @@ def bits(x: torch.Tensor) -> np.ndarray:
 LLAMA3_SCALING = {"rope_type": "llama3", "factor": 32.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
                   "original_max_position_embeddings": 8192}
 
-# name: (head_size, rotary_dim, max_position, base, is_neox, rope_scaling, hq, hkv, tokens)
+# name: (head_size, rotary_dim, max_position, base, is_neox, rope_scaling, hq, hkv, tokens); "ropeh_*" = fp16 model dtype
 CASES = {
     "rope_llama1b_neox": (64, 64, 2048, 500000.0, True, LLAMA3_SCALING, 32, 8, 24),
     "rope_llama8b_neox": (128, 128, 2048, 500000.0, True, LLAMA3_SCALING, 8, 2, 17),
@@ -56,6 +56,10 @@ CASES = {
     "rope_gptj": (64, 64, 2048, 10000.0, False, None, 4, 2, 11),
     "rope_partial_neox": (128, 64, 2048, 10000.0, True, None, 4, 2, 7),
     "rope_partial_gptj": (64, 32, 2048, 10000.0, False, None, 2, 2, 5),
+    "ropeh_llama8b_neox": (128, 128, 2048, 500000.0, True, LLAMA3_SCALING, 8, 2, 17),
+    "ropeh_llama1b_neox": (64, 64, 2048, 500000.0, True, LLAMA3_SCALING, 32, 8, 24),
+    "ropeh_gptj": (64, 64, 2048, 10000.0, False, None, 4, 2, 11),
+    "ropeh_partial_neox": (128, 64, 2048, 10000.0, True, None, 4, 2, 7),
 }
 
 
@@ -64,15 +68,16 @@ def main():
     ref = load_reference_rope()
     for i, (name, (hs, rd, maxpos, base, neox, scaling, hq, hkv, t)) in enumerate(CASES.items()):
         gen = torch.Generator().manual_seed(3000 + i)
+        dtype = torch.float16 if name.startswith("ropeh_") else torch.bfloat16
         mod = ref.get_rope(hs, rotary_dim=rd, max_position=maxpos, base=base, is_neox_style=neox,
-                           rope_scaling=scaling, dtype=torch.bfloat16)
+                           rope_scaling=scaling, dtype=dtype)
         positions = torch.randint(0, maxpos, (t,), generator=gen, dtype=torch.int64)
         positions[0], positions[-1] = 0, maxpos - 1
-        q = torch.randn((t, hq * hs), generator=gen).to(torch.bfloat16)
-        k = (torch.randn((t, hkv * hs), generator=gen) * 3).to(torch.bfloat16)
+        q = torch.randn((t, hq * hs), generator=gen).to(dtype)
+        k = (torch.randn((t, hkv * hs), generator=gen) * 3).to(dtype)
         q_out, k_out = mod.forward_native(positions, q.clone(), k.clone())
         np.savez_compressed(
-            os.path.join(OUT_DIR, name + ".npz"), kind="rope", head_size=hs, rotary_dim=rd, max_position=maxpos,
+            os.path.join(OUT_DIR, name + ".npz"), kind="rope", dtype="f16" if dtype == torch.float16 else "bf16", head_size=hs, rotary_dim=rd, max_position=maxpos,
             base=np.float64(base), is_neox=int(neox), llama3=int(scaling is not None), hq=hq, hkv=hkv,
             positions=positions.numpy(), q=bits(q), k=bits(k), cos_sin_cache=bits(mod.cos_sin_cache),
             q_out=bits(q_out), k_out=bits(k_out),

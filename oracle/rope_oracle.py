@@ -30,9 +30,9 @@ import math
 import torch
 
 
-def _bf16r(x: torch.Tensor) -> torch.Tensor:
-    """fp32 -> nearest-even bf16 -> fp32."""
-    return x.to(torch.bfloat16).to(torch.float32)
+def _round_to(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """fp32 -> nearest-even model dtype (bf16 or fp16) -> fp32."""
+    return x.to(dtype).to(torch.float32)
 
 
 def inv_freq_ref(rotary_dim: int, base: float) -> torch.Tensor:
@@ -62,22 +62,24 @@ def cos_sin_cache_ref(inv_freq: torch.Tensor, max_position: int, dtype=torch.bfl
 
 def rope_ref(positions: torch.Tensor, x: torch.Tensor, cos_sin_cache: torch.Tensor, rotary_dim: int,
              is_neox: bool) -> torch.Tensor:
-    """x: bf16 [T, H, D] -> rotated bf16 [T, H, D] (forward_native's arithmetic, explicit roundings)."""
+    """x: bf16 or fp16 [T, H, D] -> rotated [T, H, D] in the same dtype (forward_native's arithmetic, explicit
+    roundings to x.dtype: torch evaluates 16-bit elementwise ops in fp32 and rounds each result once)."""
     t, h, d = x.shape
+    rnd = lambda y: _round_to(y, x.dtype)
     cs = cos_sin_cache.index_select(0, positions.long().flatten())
     half = rotary_dim // 2
-    cos = _bf16r(cs[:, :half].float())[:, None, :]  # .to(x.dtype)
-    sin = _bf16r(cs[:, half:rotary_dim].float())[:, None, :]
+    cos = rnd(cs[:, :half].float())[:, None, :]  # .to(x.dtype)
+    sin = rnd(cs[:, half:rotary_dim].float())[:, None, :]
     xf = x.float()
     rot, rest = xf[..., :rotary_dim], xf[..., rotary_dim:]
     if is_neox:
         x1, x2 = rot[..., :half], rot[..., half:]
     else:
         x1, x2 = rot[..., 0::2], rot[..., 1::2]
-    o1 = _bf16r(_bf16r(x1 * cos) - _bf16r(x2 * sin))
-    o2 = _bf16r(_bf16r(x2 * cos) + _bf16r(x1 * sin))
+    o1 = rnd(rnd(x1 * cos) - rnd(x2 * sin))
+    o2 = rnd(rnd(x2 * cos) + rnd(x1 * sin))
     if is_neox:
         out = torch.cat((o1, o2), dim=-1)
     else:
         out = torch.stack((o1, o2), dim=-1).flatten(-2)
-    return torch.cat((out, rest), dim=-1).to(torch.bfloat16)
+    return torch.cat((out, rest), dim=-1).to(x.dtype)

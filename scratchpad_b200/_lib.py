@@ -16,12 +16,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200_ATTN_LIB") or os.path.join(_HERE, "csrc", "libb200attn.so")
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
-KV_BF16, KV_FP8_E4M3 = 0, 1
+KV_BF16, KV_FP8_E4M3, KV_F16 = 0, 1, 2
+ACT_BF16, ACT_F16 = 0, 1
 IDX_I32, IDX_I64 = 0, 1
 PATH_AUTO, PATH_MMA, PATH_TC, PATH_TC2 = -1, 0, 1, 2
-CACHE_BF16, CACHE_F32 = 0, 1
+CACHE_BF16, CACHE_F32, CACHE_F16 = 0, 1, 2
 PAGE_AUTO = -1
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_NOT_PLANNED = 0, 1, 2, 3, 4
@@ -76,6 +77,7 @@ class DecodeParams(C.Structure):
         ("max_bs", C.c_int32), ("force_path", C.c_int32),
         ("ev_kernel_begin", C.c_void_p), ("ev_kernel_end", C.c_void_p),
         ("cascade", C.c_int32), ("page_size", C.c_int32), ("kv_pool_rows", C.c_int64),
+        ("act_dtype", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -97,6 +99,7 @@ class ExtendParams(C.Structure):
         ("sm_scale", C.c_float), ("logit_cap", C.c_float),
         ("k_scale", C.c_void_p), ("v_scale", C.c_void_p),
         ("force_path", C.c_int32), ("page_size", C.c_int32), ("kv_pool_rows", C.c_int64),
+        ("act_dtype", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -112,7 +115,7 @@ class RopeStoreParams(C.Structure):
         ("num_tokens", C.c_int32), ("hq", C.c_int32), ("hkv", C.c_int32), ("d", C.c_int32), ("dv", C.c_int32),
         ("kv_dtype", C.c_int32),
         ("k_scale", C.c_void_p), ("v_scale", C.c_void_p),
-        ("write_back_k", C.c_int32), ("reserved", C.c_int32),
+        ("write_back_k", C.c_int32), ("act_dtype", C.c_int32),
     ]
 
 
@@ -167,7 +170,7 @@ def load() -> C.CDLL:
     lib.b200_attn_plan.argtypes = [vp, u64, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, i32, vp]
     lib.b200_attn_decode.argtypes = [C.POINTER(DecodeParams), vp]
     lib.b200_attn_extend.argtypes = [C.POINTER(ExtendParams), vp]
-    lib.b200_kv_store.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp, i64, i64, i64, i64, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.b200_kv_store.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp, i64, i64, i64, i64, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.b200_rope_kv_store.argtypes = [C.POINTER(RopeStoreParams), vp]
     lib.b200_debug_check_paged.argtypes = [vp, i64, vp, vp, i32, i32, i32, vp, vp]
     lib.b200_debug_gather.argtypes = [vp, i64, i32, vp, i64, vp, vp, i32, vp, i32, vp, vp]

@@ -27,7 +27,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from .pool import kv_dtype_code, kv_store
+from .pool import act_dtype_code, check_dtype_pair, kv_dtype_code, kv_store
 
 
 class AttentionBackend(ABC):
@@ -132,8 +132,10 @@ class CudaB200AttnBackend(AttentionBackend):
         self.tma_contiguous_runs = bool(tma_contiguous_runs)
         if getattr(model_runner, "sliding_window_size", None) not in (None, -1):
             raise NotImplementedError("cuda_b200 backend: sliding-window attention is not supported")
-        if model_runner.dtype != torch.bfloat16:
-            raise NotImplementedError("cuda_b200 backend: model dtype must be bfloat16")
+        # the model dtype: bf16, or fp16 (what the engine serves fp16 and, by default, fp32 checkpoints in,
+        # config/utils.py:41-43); a 16-bit pool has the model dtype (kv_cache_dtype "auto", model_runner.py:366-367)
+        self.act_dtype = act_dtype_code(model_runner.dtype)
+        check_dtype_pair(self.kv_dtype, self.act_dtype)
         self._graph_state_frozen = False
         self.cuda_graph_max_seq_len = cfg.context_len
         self._check_pages = os.environ.get("B200_CHECK_PAGES", "0") == "1"
@@ -240,7 +242,7 @@ class CudaB200AttnBackend(AttentionBackend):
         pool = pool if pool is not None else self.token_to_kv_pool
         if hasattr(pool, "get_kv_scales"):
             return pool.get_kv_scales(layer.layer_id)
-        if self.kv_dtype == _lib.KV_BF16:
+        if self.kv_dtype != _lib.KV_FP8_E4M3:
             return None, None
         # a pool without scale metadata (the reference's class): per-tensor floats carried by the layer, the way
         # the reference's FlashInfer backend reads them (flashinfer_backend.py:387-388,457-458)
@@ -271,6 +273,13 @@ class CudaB200AttnBackend(AttentionBackend):
     def _logit_cap(self, layer) -> float:
         cap = getattr(layer, "logit_cap", 0.0)
         return float(cap) if cap else 0.0
+
+    def _act_code(self, *tensors) -> int:
+        """The kernels read q / k / v as the model dtype the backend was built for; anything else would be misread."""
+        for t in tensors:
+            if act_dtype_code(t.dtype) != self.act_dtype:
+                raise TypeError(f"cuda_b200 backend: built for model dtype code {self.act_dtype}, got a {t.dtype} tensor")
+        return self.act_dtype
 
     def _check_layer(self, layer) -> None:
         if getattr(layer, "is_cross_attention", False):
@@ -317,7 +326,7 @@ class CudaB200AttnBackend(AttentionBackend):
             k_scale=_ptr(ks), v_scale=_ptr(vs),
             workspace=self.workspace.data_ptr(), workspace_bytes=self.workspace.numel(),
             max_bs=self.max_bs, force_path=self.force_path, cascade=self.cascade,
-            page_size=self._page_hint(pool), kv_pool_rows=kb.shape[0],
+            page_size=self._page_hint(pool), kv_pool_rows=kb.shape[0], act_dtype=self._act_code(q),
         )
         if self.profile_events is not None:
             p.ev_kernel_begin, p.ev_kernel_end = self.profile_events
@@ -364,7 +373,7 @@ class CudaB200AttnBackend(AttentionBackend):
             total_tokens=q3.shape[0], max_extend_len=int(max_extend_len), kv_dtype=self.kv_dtype,
             sm_scale=float(layer.scaling), logit_cap=self._logit_cap(layer),
             k_scale=_ptr(ks), v_scale=_ptr(vs), force_path=self.force_path,
-            page_size=self._page_hint(pool), kv_pool_rows=kb.shape[0],
+            page_size=self._page_hint(pool), kv_pool_rows=kb.shape[0], act_dtype=self._act_code(q3, k3, v3),
         )
         rc = self.lib.b200_attn_extend(p, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "b200_attn_extend")

@@ -36,6 +36,15 @@ struct CasTables {
   int max_tiles;
 };
 
+// ---- dtype pairing ------------------------------------------------------------
+// The pool holds the model dtype (kv_cache_dtype "auto", model_runner.py:366-367) or fp8-e4m3: bf16 activations go
+// with a bf16 or fp8 pool, fp16 activations with an fp16 or fp8 pool.
+static inline bool dtype_pair_ok(int kv_dtype, int act_dtype) {
+  if (act_dtype == B200_ACT_BF16) return kv_dtype == B200_KV_BF16 || kv_dtype == B200_KV_FP8_E4M3;
+  if (act_dtype == B200_ACT_F16) return kv_dtype == B200_KV_F16 || kv_dtype == B200_KV_FP8_E4M3;
+  return false;
+}
+
 // ---- index helpers ---------------------------------------------------------
 __device__ __forceinline__ int64_t load_idx(const void* p, int idx64, int i) {
   return idx64 ? static_cast<const int64_t*>(p)[i] : static_cast<int64_t>(static_cast<const int32_t*>(p)[i]);
@@ -203,21 +212,37 @@ __device__ __forceinline__ float e4m3_to_float(uint8_t b) {
   return __half2float(*reinterpret_cast<__half*>(&h));
 }
 
-// bf16 activation -> pool byte: e4m3_rn(bf16_rn(x / scale)), the double rounding of the reference's bf16 div_
-// followed by .to(fp8) (memory/pool.py:404-412); overflow becomes NaN exactly as torch's cast does (no saturation)
-__device__ __forceinline__ uint8_t quant_e4m3(uint16_t bf16_bits, float scale) {
-  const float x = bf16_bits_to_float(bf16_bits);
-  const float y = __bfloat162float(__float2bfloat16_rn(__fdiv_rn(x, scale)));
+__device__ __forceinline__ float f16_bits_to_float(uint16_t b) { return __half2float(__ushort_as_half(b)); }
+// 16-bit activation (HALF: fp16, else bf16) <-> float; round_act = the value rounded to the model dtype
+template <bool HALF>
+__device__ __forceinline__ float act_bits_to_float(uint16_t b) {
+  if constexpr (HALF) return f16_bits_to_float(b);
+  else return bf16_bits_to_float(b);
+}
+template <bool HALF>
+__device__ __forceinline__ float round_act(float x) {
+  if constexpr (HALF) return __half2float(__float2half_rn(x));
+  else return __bfloat162float(__float2bfloat16_rn(x));
+}
+
+// activation -> pool byte: e4m3_rn(act_rn(x / scale)), the double rounding of the reference's in-place div_ on the
+// model-dtype tensor followed by .to(fp8) (memory/pool.py:404-412); overflow becomes NaN exactly as torch's cast does
+// (no saturation)
+template <bool HALF>
+__device__ __forceinline__ uint8_t quant_e4m3(uint16_t act_bits, float scale) {
+  const float x = act_bits_to_float<HALF>(act_bits);
+  const float y = round_act<HALF>(__fdiv_rn(x, scale));
   return static_cast<uint8_t>(__nv_cvt_float_to_fp8(y, __NV_NOSAT, __NV_E4M3));
 }
-// 8 bf16 (one uint4) -> 8 e4m3 bytes
+// 8 activations (one uint4) -> 8 e4m3 bytes
+template <bool HALF>
 __device__ __forceinline__ uint2 quant_e4m3x8(uint4 x, float scale) {
   const uint32_t w[4] = {x.x, x.y, x.z, x.w};
   uint32_t out[2] = {0u, 0u};
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const uint16_t bits = static_cast<uint16_t>(j & 1 ? w[j >> 1] >> 16 : w[j >> 1] & 0xffffu);
-    out[j >> 2] |= static_cast<uint32_t>(quant_e4m3(bits, scale)) << (8 * (j & 3));
+    out[j >> 2] |= static_cast<uint32_t>(quant_e4m3<HALF>(bits, scale)) << (8 * (j & 3));
   }
   return make_uint2(out[0], out[1]);
 }

@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* 
 // decode kernel
 // ---------------------------------------------------------------------------
 struct DecodeArgs {
-  const __nv_bfloat16* q;
+  const uint16_t* q;  // bf16 or fp16 bits (act_dtype)
   int64_t q_st, q_sh;
   const uint8_t* kbuf;
   const uint8_t* vbuf;
@@ -419,10 +419,14 @@ __device__ __forceinline__ void cursor_advance(Cursor& c, const DecodeArgs& a) {
 // QT_ = N=8 tiles of q heads per kv head: 1 for group sizes <= 8, 2 for 9..16 (Llama-3.1-405B: 128 q / 8 kv heads).  The
 // QT warps of a kv head read the SAME K/V rows of the staged tile against their own 8 q heads, so a larger group costs
 // warps (fewer token sub-slices per tile), never a second pass over the KV bytes.
-template <int D_, bool FP8_, int HPC_, int NW_, bool PAGED_ = false, int QT_ = 1>
+// HALF_ = the model dtype (q, and the pool unless it is fp8) is fp16 instead of bf16: a 16-bit pool runs the same kernel
+// with f16 MMAs and P rounded to f16; an fp8 pool (widened to f16 either way) takes q as it is instead of narrowing it.
+template <int D_, bool FP8_, int HPC_, int NW_, bool PAGED_ = false, int QT_ = 1, bool HALF_ = false>
 struct DecodeCfg {
   static constexpr int D = D_;
   static constexpr bool FP8 = FP8_;
+  static constexpr bool HALF = HALF_;
+  static constexpr bool F16MATH = FP8_ || HALF_;  // MMA operand type: f16 (fp8 pools are widened to f16), else bf16
   static constexpr bool PAGED = PAGED_;  // page_size >= 16: whole tiles arrive by TMA box copies (one per page)
   static constexpr int HPC = HPC_;     // kv heads per CTA
   static constexpr int NW = NW_;       // warps per CTA
@@ -662,7 +666,7 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
   // B fragments of Q^T: lane holds q-head n = gid (of this kv head's group)
   auto load_q = [&](int b) {
     const bool live = q0 + gid < G;
-    const __nv_bfloat16* qp = a.q + static_cast<int64_t>(b) * a.q_st + static_cast<int64_t>(kvh * G + (live ? q0 + gid : 0)) * a.q_sh;
+    const uint16_t* qp = a.q + static_cast<int64_t>(b) * a.q_st + static_cast<int64_t>(kvh * G + (live ? q0 + gid : 0)) * a.q_sh;
 #pragma unroll
     for (int kc = 0; kc < C::KC; ++kc) {
       if constexpr (!FP8) {
@@ -678,10 +682,15 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
       } else {
         // 16-element chunk kc: slots (2c,2c+1) <-> d = 16kc+4c+{0,1}; (2c+8,2c+9) <-> d = 16kc+4c+{2,3}
         const uint2 raw = live ? __ldg(reinterpret_cast<const uint2*>(qp + kc * 16 + cid * 4)) : make_uint2(0u, 0u);
-        const __nv_bfloat162 x01 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-        const __nv_bfloat162 x23 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-        qf[kc][0] = pack_f16x2(__low2float(x01), __high2float(x01));
-        qf[kc][1] = pack_f16x2(__low2float(x23), __high2float(x23));
+        if constexpr (C::HALF) {  // fp16 activations: already the MMA's operand type (through a shuffle, as above:
+          qf[kc][0] = __shfl_sync(0xffffffffu, raw.x, lane);  // the loop's HMMAs must not read an LDG result directly)
+          qf[kc][1] = __shfl_sync(0xffffffffu, raw.y, lane);
+        } else {
+          const __nv_bfloat162 x01 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+          const __nv_bfloat162 x23 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+          qf[kc][0] = pack_f16x2(__low2float(x01), __high2float(x01));
+          qf[kc][1] = pack_f16x2(__low2float(x23), __high2float(x23));
+        }
       }
     }
   };
@@ -699,7 +708,7 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
       for (int kc = 0; kc < C::KC; ++kc) {
         uint32_t af[4];
         ldmatrix_x4(af, sk + tile_chunk_off<CPS, TN>(w_head, wtok + lrow, 2 * kc + lhi));
-        mma_16816<false>(s, af, qf[kc][0], qf[kc][1]);
+        mma_16816<C::F16MATH>(s, af, qf[kc][0], qf[kc][1]);
       }
     } else {
 #pragma unroll
@@ -750,8 +759,8 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
       o[i][3] *= al1;
     }
     // P^T (tokens x heads, accumulator layout) -> B fragment (k = tokens, n = heads)
-    const uint32_t pb0 = movmatrix_trans(pack2<FP8>(p0, p1));
-    const uint32_t pb1 = movmatrix_trans(pack2<FP8>(p2, p3));
+    const uint32_t pb0 = movmatrix_trans(pack2<C::F16MATH>(p0, p1));
+    const uint32_t pb1 = movmatrix_trans(pack2<C::F16MATH>(p2, p3));
     const int vtok = (lane & 7) + ((lane >> 4) << 3);  // ldmatrix.trans row (token)
     const int vhalf = (lane >> 3) & 1;
     if constexpr (!FP8) {
@@ -759,7 +768,7 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
       for (int mt = 0; mt < C::MT; ++mt) {
         uint32_t af[4];  // V^T tile: rows d = 16mt + {gid, gid+8}, cols tokens
         ldmatrix_x4_trans(af, sv + tile_chunk_off<CPS, TN>(w_head, wtok + vtok, 2 * mt + vhalf));
-        mma_16816<false>(o[mt], af, pb0, pb1);
+        mma_16816<C::F16MATH>(o[mt], af, pb0, pb1);
       }
     } else {
 #pragma unroll
@@ -1011,7 +1020,7 @@ __global__ void __launch_bounds__(C::NT, 2) decode_paged_kernel(const __grid_con
 template <int DV>
 __global__ void __launch_bounds__(256, 4) merge_kernel(const int* __restrict__ hdr, const int* __restrict__ tile_off,
                                                     const float* __restrict__ part_o,
-                                                    const float* __restrict__ part_lse, __nv_bfloat16* __restrict__ o,
+                                                    const float* __restrict__ part_lse, uint16_t* __restrict__ o, int o_half,
                                                     int64_t o_st, int64_t o_sh, int bs, int hq, int nsub,
                                                     const float* __restrict__ cas_o, const float* __restrict__ cas_lse,
                                                     int cas_splits, const int* __restrict__ shared32) {
@@ -1024,15 +1033,15 @@ __global__ void __launch_bounds__(256, 4) merge_kernel(const int* __restrict__ h
   const int b = pair / hq, h = pair % hq;
   const int tpc = __ldg(hdr + 1);
   if (__ldg(hdr + 6) != kPlanMagic || __ldg(hdr + 3) != bs) {  // no plan for this batch in the workspace: poison o
-    __nv_bfloat16* bad = o + static_cast<int64_t>(b) * o_st + static_cast<int64_t>(h) * o_sh + lane * (DV / 32);
+    uint16_t* bad = o + static_cast<int64_t>(b) * o_st + static_cast<int64_t>(h) * o_sh + lane * (DV / 32);
 #pragma unroll
-    for (int j = 0; j < DV / 32; ++j) bad[j] = __ushort_as_bfloat16(0x7fc0);
+    for (int j = 0; j < DV / 32; ++j) bad[j] = o_half ? 0x7e00 : 0x7fc0;  // quiet NaN in fp16 / bf16
     return;
   }
   const int t0 = __ldg(tile_off + b), t1 = __ldg(tile_off + b + 1);
   // partials of the shared-prefix leg (one per KV split), present when the plan found a shared prefix
   const int ncas = (cas_splits > 0 && __ldg(shared32 + b) > 0) ? cas_splits : 0;
-  __nv_bfloat16* op = o + static_cast<int64_t>(b) * o_st + static_cast<int64_t>(h) * o_sh + lane * VPL;
+  uint16_t* op = o + static_cast<int64_t>(b) * o_st + static_cast<int64_t>(h) * o_sh + lane * VPL;
   float acc[VPL];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) acc[j] = 0.f;
@@ -1117,10 +1126,11 @@ __global__ void __launch_bounds__(256, 4) merge_kernel(const int* __restrict__ h
     }
   }
   const float r = den > 0.f ? 1.f / den : 0.f;  // seq_len == 0 -> zeros
+  auto pack_o = [&](float lo, float hi) { return o_half ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); };
   if constexpr (VPL == 4) {
-    *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16x2(acc[0] * r, acc[1] * r), pack_bf16x2(acc[2] * r, acc[3] * r));
+    *reinterpret_cast<uint2*>(op) = make_uint2(pack_o(acc[0] * r, acc[1] * r), pack_o(acc[2] * r, acc[3] * r));
   } else {
-    *reinterpret_cast<uint32_t*>(op) = pack_bf16x2(acc[0] * r, acc[1] * r);
+    *reinterpret_cast<uint32_t*>(op) = pack_o(acc[0] * r, acc[1] * r);
   }
 }
 
@@ -1165,10 +1175,11 @@ __global__ void __launch_bounds__(32) naive_decode_kernel(const b200_decode_para
   const int g = p.hq / p.hkv, kvh = h / g;
   const int64_t n = load_idx(seq, idx64, b);
   const int32_t* row = p.req_to_token + load_idx(req, idx64, b) * p.req_to_token_stride;
-  const bool fp8 = p.kv_dtype == B200_KV_FP8_E4M3;
+  const bool fp8 = p.kv_dtype == B200_KV_FP8_E4M3, kv_half = p.kv_dtype == B200_KV_F16, act_half = p.act_dtype == B200_ACT_F16;
   const int elt = fp8 ? 1 : 2;
   const float ks = p.k_scale ? p.k_scale[kvh] : 1.f, vs = p.v_scale ? p.v_scale[kvh] : 1.f;
-  const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(p.q) + b * p.q_stride_t + h * p.q_stride_h;
+  const uint16_t* q = static_cast<const uint16_t*>(p.q) + b * p.q_stride_t + h * p.q_stride_h;
+  auto ld16 = [](const uint16_t* x, int i, bool half) { return half ? f16_bits_to_float(x[i]) : bf16_bits_to_float(x[i]); };
   float acc[8];  // dv <= 256
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -1179,8 +1190,8 @@ __global__ void __launch_bounds__(32) naive_decode_kernel(const b200_decode_para
     const uint8_t* vr = kv_row_ptr(static_cast<const uint8_t*>(p.v_buf), slot, p.v_stride_t * elt) + kvh * p.dv * elt;
     float s = 0.f;
     for (int i = lane; i < p.d; i += 32) {
-      const float kx = fp8 ? e4m3_to_float(kr[i]) * ks : bf16_bits_to_float(reinterpret_cast<const uint16_t*>(kr)[i]);
-      s += __bfloat162float(q[i]) * kx;
+      const float kx = fp8 ? e4m3_to_float(kr[i]) * ks : ld16(reinterpret_cast<const uint16_t*>(kr), i, kv_half);
+      s += ld16(q, i, act_half) * kx;
     }
 #pragma unroll
     for (int x = 16; x > 0; x >>= 1) s += __shfl_xor_sync(0xffffffffu, s, x);
@@ -1190,20 +1201,23 @@ __global__ void __launch_bounds__(32) naive_decode_kernel(const b200_decode_para
     const float al = expf(m - mn), pr = expf(s - mn);
     l = l * al + pr;
     for (int i = lane, j = 0; i < p.dv; i += 32, ++j) {
-      const float vx = fp8 ? e4m3_to_float(vr[i]) * vs : bf16_bits_to_float(reinterpret_cast<const uint16_t*>(vr)[i]);
+      const float vx = fp8 ? e4m3_to_float(vr[i]) * vs : ld16(reinterpret_cast<const uint16_t*>(vr), i, kv_half);
       acc[j] = acc[j] * al + pr * vx;
     }
     m = mn;
   }
-  __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.o) + b * p.o_stride_t + h * p.o_stride_h;
-  for (int i = lane, j = 0; i < p.dv; i += 32, ++j) op[i] = __float2bfloat16(l > 0.f ? acc[j] / l : 0.f);
+  uint16_t* op = static_cast<uint16_t*>(p.o) + b * p.o_stride_t + h * p.o_stride_h;
+  for (int i = lane, j = 0; i < p.dv; i += 32, ++j) {
+    const float x = l > 0.f ? acc[j] / l : 0.f;
+    op[i] = act_half ? __half_as_ushort(__float2half_rn(x)) : __bfloat16_as_ushort(__float2bfloat16_rn(x));
+  }
 }
 
 // ---------------------------------------------------------------------------
 // host side: config selection + launchers
 // ---------------------------------------------------------------------------
 struct KernelChoice {
-  int d, fp8, hpc, nw, qt;
+  int d, fp8, hpc, nw, qt, half;  // half: fp16 activations (and pool, unless it is fp8)
 };
 // partials per (cta, request) slot of the workspace: must mirror DecodeCfg::PARTS
 static int parts_per_slot(const KernelChoice& kc) {
@@ -1222,11 +1236,12 @@ static int choose(int hq, int hkv, int d, int dv, int kv_dtype, KernelChoice* kc
   if (hq <= 0 || hkv <= 0 || hq % hkv != 0) return B200_ERR_INVALID;
   if (d != dv) return B200_ERR_UNSUPPORTED;            // MLA-style split dims: out of scope
   if (d != 64 && d != 128) return B200_ERR_UNSUPPORTED;
-  if (kv_dtype != B200_KV_BF16 && kv_dtype != B200_KV_FP8_E4M3) return B200_ERR_UNSUPPORTED;
+  if (kv_dtype != B200_KV_BF16 && kv_dtype != B200_KV_FP8_E4M3 && kv_dtype != B200_KV_F16) return B200_ERR_UNSUPPORTED;
   // one N=8 mma tile of q heads per kv head, or two for group sizes 9..16 (built for head_dim 128)
   if (hq / hkv > 16 || (hq / hkv > 8 && d != 128)) return B200_ERR_UNSUPPORTED;
   kc->d = d;
   kc->fp8 = kv_dtype == B200_KV_FP8_E4M3;
+  kc->half = kv_dtype == B200_KV_F16;
   kc->nw = (d == 128 && !kc->fp8) ? 4 : 8;  // keep a stage at 32 KiB
   kc->qt = hq / hkv > 8 ? 2 : 1;
   kc->hpc = pick_hpc(hkv, kc->nw / kc->qt);
@@ -1311,27 +1326,27 @@ static int launch_decode_t(const DecodeArgs& a, const PagedMaps* maps, int grid_
   }
 }
 
-template <int D, bool FP8, bool PAGED>
+template <int D, bool FP8, bool PAGED, bool HALF = false>
 static int dispatch_hpc(const KernelChoice& kc, const DecodeArgs& a, const PagedMaps* m, int gx, int gy, cudaStream_t st, bool q,
                         int* occ) {
   constexpr int NW = (D == 128 && !FP8) ? 4 : 8;
   if constexpr (D == 128) {
     if (kc.qt == 2) {  // group sizes 9..16: two q tiles per kv head
       switch (kc.hpc) {
-        case 1: return launch_decode_t<DecodeCfg<D, FP8, 1, NW, PAGED, 2>>(a, m, gx, gy, st, q, occ);
-        case 2: return launch_decode_t<DecodeCfg<D, FP8, 2, NW, PAGED, 2>>(a, m, gx, gy, st, q, occ);
+        case 1: return launch_decode_t<DecodeCfg<D, FP8, 1, NW, PAGED, 2, HALF>>(a, m, gx, gy, st, q, occ);
+        case 2: return launch_decode_t<DecodeCfg<D, FP8, 2, NW, PAGED, 2, HALF>>(a, m, gx, gy, st, q, occ);
         case 4:
-          if constexpr (NW >= 8) return launch_decode_t<DecodeCfg<D, FP8, 4, NW, PAGED, 2>>(a, m, gx, gy, st, q, occ);
+          if constexpr (NW >= 8) return launch_decode_t<DecodeCfg<D, FP8, 4, NW, PAGED, 2, HALF>>(a, m, gx, gy, st, q, occ);
       }
       return B200_ERR_UNSUPPORTED;
     }
   }
   switch (kc.hpc) {
-    case 1: return launch_decode_t<DecodeCfg<D, FP8, 1, NW, PAGED>>(a, m, gx, gy, st, q, occ);
-    case 2: return launch_decode_t<DecodeCfg<D, FP8, 2, NW, PAGED>>(a, m, gx, gy, st, q, occ);
-    case 4: return launch_decode_t<DecodeCfg<D, FP8, 4, NW, PAGED>>(a, m, gx, gy, st, q, occ);
+    case 1: return launch_decode_t<DecodeCfg<D, FP8, 1, NW, PAGED, 1, HALF>>(a, m, gx, gy, st, q, occ);
+    case 2: return launch_decode_t<DecodeCfg<D, FP8, 2, NW, PAGED, 1, HALF>>(a, m, gx, gy, st, q, occ);
+    case 4: return launch_decode_t<DecodeCfg<D, FP8, 4, NW, PAGED, 1, HALF>>(a, m, gx, gy, st, q, occ);
     case 8:
-      if constexpr (NW >= 8) return launch_decode_t<DecodeCfg<D, FP8, 8, NW, PAGED>>(a, m, gx, gy, st, q, occ);
+      if constexpr (NW >= 8) return launch_decode_t<DecodeCfg<D, FP8, 8, NW, PAGED, 1, HALF>>(a, m, gx, gy, st, q, occ);
   }
   return B200_ERR_UNSUPPORTED;
 }
@@ -1339,6 +1354,11 @@ static int dispatch_hpc(const KernelChoice& kc, const DecodeArgs& a, const Paged
 template <bool PAGED>
 static int dispatch_p(const KernelChoice& kc, const DecodeArgs& a, const PagedMaps* m, int gx, int gy, cudaStream_t st, bool q,
                       int* occ) {
+  if (kc.half) {
+    if (kc.d == 64)
+      return kc.fp8 ? dispatch_hpc<64, true, PAGED, true>(kc, a, m, gx, gy, st, q, occ) : dispatch_hpc<64, false, PAGED, true>(kc, a, m, gx, gy, st, q, occ);
+    return kc.fp8 ? dispatch_hpc<128, true, PAGED, true>(kc, a, m, gx, gy, st, q, occ) : dispatch_hpc<128, false, PAGED, true>(kc, a, m, gx, gy, st, q, occ);
+  }
   if (kc.d == 64)
     return kc.fp8 ? dispatch_hpc<64, true, PAGED>(kc, a, m, gx, gy, st, q, occ) : dispatch_hpc<64, false, PAGED>(kc, a, m, gx, gy, st, q, occ);
   return kc.fp8 ? dispatch_hpc<128, true, PAGED>(kc, a, m, gx, gy, st, q, occ) : dispatch_hpc<128, false, PAGED>(kc, a, m, gx, gy, st, q, occ);
@@ -1409,7 +1429,7 @@ const char* b200_attn_error_string(int code) {
   switch (code) {
     case B200_OK: return "ok";
     case B200_ERR_INVALID: return "invalid argument (null pointer, bad size or misaligned stride)";
-    case B200_ERR_UNSUPPORTED: return "unsupported configuration (head_dim must be 64 or 128 with d == dv, group size <= 8 -- <= 16 at head_dim 128 --, kv dtype bf16 or fp8-e4m3)";
+    case B200_ERR_UNSUPPORTED: return "unsupported configuration (head_dim must be 64 or 128 with d == dv, group size <= 8 -- <= 16 at head_dim 128 --, bf16 activations over a bf16 or fp8-e4m3 pool or fp16 activations over an fp16 or fp8-e4m3 pool)";
     case B200_ERR_WORKSPACE: return "workspace too small for this configuration";
     case B200_ERR_NOT_PLANNED: return "workspace holds no plan for this batch (call b200_attn_plan with the same bs, shape and cascade flag first)";
     default:
@@ -1489,9 +1509,11 @@ int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs, co
 int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
   if (!p || !p->q || !p->k_buf || !p->v_buf || !p->o || !p->req_to_token || !p->workspace) return B200_ERR_INVALID;
   if (p->bs <= 0 || p->bs > p->max_bs) return B200_ERR_INVALID;
+  if (!dtype_pair_ok(p->kv_dtype, p->act_dtype)) return B200_ERR_UNSUPPORTED;
   KernelChoice kc;
   int rc = choose(p->hq, p->hkv, p->d, p->dv, p->kv_dtype, &kc);
   if (rc) return rc;
+  kc.half = p->act_dtype == B200_ACT_F16;  // fp8 pools: the q dtype picks the kernel (same shape, same launch configuration)
   const int elt = kc.fp8 ? 1 : 2;
   // 16-byte vector access on pool rows, 8-byte on q
   if ((p->k_stride_t * elt) % 16 || (p->v_stride_t * elt) % 16 || p->q_stride_t % 4 || p->q_stride_h % 4 ||
@@ -1512,7 +1534,7 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
   const WsLayout L = ws_layout(p->max_bs, cfg.grid_ctas, cfg.partials_per_slot, p->hq, p->dv);
   uint8_t* ws = static_cast<uint8_t*>(p->workspace);
   DecodeArgs a;
-  a.q = static_cast<const __nv_bfloat16*>(p->q);
+  a.q = static_cast<const uint16_t*>(p->q);
   a.q_st = p->q_stride_t;
   a.q_sh = p->q_stride_h;
   a.kbuf = static_cast<const uint8_t*>(p->k_buf);
@@ -1586,15 +1608,16 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
   rc = dispatch(kc, a, mp, cfg.grid_ctas, p->hkv / kc.hpc, st, false, nullptr);
   if (rc) return rc;
   if (p->ev_kernel_end) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(p->ev_kernel_end), st));
-  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p->o);
+  uint16_t* o = static_cast<uint16_t*>(p->o);
+  const int o_half = p->act_dtype == B200_ACT_F16;
   const dim3 mgrid((p->bs * p->hq + 7) / 8);
   if (p->dv == 64)
     return launch_pdl(merge_kernel<64>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
-                      static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
+                      static_cast<const float*>(a.part_lse), o, o_half, static_cast<int64_t>(p->o_stride_t),
                       static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
                       static_cast<int>(cfg.partials_per_slot), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
   return launch_pdl(merge_kernel<128>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
-                    static_cast<const float*>(a.part_lse), o, static_cast<int64_t>(p->o_stride_t),
+                    static_cast<const float*>(a.part_lse), o, o_half, static_cast<int64_t>(p->o_stride_t),
                     static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
                     static_cast<int>(cfg.partials_per_slot), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
 }

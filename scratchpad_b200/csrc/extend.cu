@@ -31,15 +31,15 @@ constexpr int kExtNW = 8;
 constexpr int kExtNT = kExtNW * 32;
 
 struct ExtendArgs {
-  const __nv_bfloat16* q;
+  const uint16_t* q;  // bf16 or fp16 bits (act_dtype), like k_new / v_new / o
   int64_t q_st, q_sh;
-  const __nv_bfloat16* k_new;
-  const __nv_bfloat16* v_new;
+  const uint16_t* k_new;
+  const uint16_t* v_new;
   int64_t kn_st, kn_sh, vn_st, vn_sh;
   const uint8_t* kbuf;
   const uint8_t* vbuf;
   int64_t k_st_bytes, v_st_bytes;
-  __nv_bfloat16* o;
+  uint16_t* o;
   int64_t o_st, o_sh;
   const int32_t* r2t;
   int64_t r2t_stride;
@@ -54,11 +54,13 @@ struct ExtendArgs {
   const float* v_scale;
 };
 
-template <int D_, bool FP8_>
+// HALF_: the model dtype (q, new tokens, o, and a 16-bit pool) is fp16 instead of bf16
+template <int D_, bool FP8_, bool HALF_ = false>
 struct ExtCfg {
   static constexpr int D = D_;
   static constexpr bool FP8 = FP8_;
-  static constexpr int SEG = D * 2;        // bytes of one smem row (always bf16 in smem)
+  static constexpr bool HALF = HALF_;
+  static constexpr int SEG = D * 2;        // bytes of one smem row (always the model dtype in smem)
   static constexpr int CPS = SEG / 16;     // 16-byte chunks per smem row
   static constexpr int KC = D / 16;        // k-steps of Q.K^T
   static constexpr int TILE_BYTES = kExtBN * SEG;
@@ -72,7 +74,8 @@ struct ExtCfg {
   static_assert(PASSES >= 1 && (kExtBN * CPS) % kExtNT == 0, "copy mapping");
 };
 
-// 16 e4m3 bytes -> 16 bf16 (x scale), as two 16-byte chunks
+// 16 e4m3 bytes -> 16 model-dtype values (x scale), as two 16-byte chunks
+template <bool HALF>
 __device__ __forceinline__ void dequant16(const uint4& raw, float scale, uint4& lo, uint4& hi) {
   const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
   uint32_t out[8];
@@ -82,8 +85,8 @@ __device__ __forceinline__ void dequant16(const uint4& raw, float scale, uint4& 
     const uint32_t h23 = e4m3x2_to_f16x2(static_cast<uint16_t>(w[i] >> 16));
     const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
     const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
-    out[2 * i] = pack_bf16x2(f01.x * scale, f01.y * scale);
-    out[2 * i + 1] = pack_bf16x2(f23.x * scale, f23.y * scale);
+    out[2 * i] = pack2<HALF>(f01.x * scale, f01.y * scale);
+    out[2 * i + 1] = pack2<HALF>(f23.x * scale, f23.y * scale);
   }
   lo = make_uint4(out[0], out[1], out[2], out[3]);
   hi = make_uint4(out[4], out[5], out[6], out[7]);
@@ -93,7 +96,7 @@ template <class C>
 __global__ void __launch_bounds__(kExtNT, 1) extend_mma_kernel(const ExtendArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int D = C::D, SEG = C::SEG, CPS = C::CPS, BN = kExtBN;
-  constexpr bool FP8 = C::FP8;
+  constexpr bool FP8 = C::FP8, HALF = C::HALF;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, cid = lane & 3;
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(kExtNT, 1) extend_mma_kernel(const ExtendArgs 
     const int r = idx / CPS, ch = idx % CPS;
     const bool live = r < live_rows;
     const int t = t0 + (live ? r / G : 0), h = kvh * G + (live ? r % G : 0);
-    const __nv_bfloat16* src = a.q + static_cast<int64_t>(start + t) * a.q_st + static_cast<int64_t>(h) * a.q_sh + ch * 8;
+    const uint16_t* src = a.q + static_cast<int64_t>(start + t) * a.q_st + static_cast<int64_t>(h) * a.q_sh + ch * 8;
     cp_async16(smem_base + (r * CPS + swz_chunk<CPS>(ch, r)) * 16, src, live ? 16 : 0);
   }
   cp_async_commit();
@@ -203,10 +206,10 @@ __global__ void __launch_bounds__(kExtNT, 1) extend_mma_kernel(const ExtendArgs 
         const int p = t * BN + kr;
         if (kr < BN && p < pre) {
           uint4 lo, hi;
-          dequant16(stg_k[i], ks, lo, hi);
+          dequant16<HALF>(stg_k[i], ks, lo, hi);
           *reinterpret_cast<uint4*>(sk + (kr * CPS + swz_chunk<CPS>(2 * ch, kr)) * 16) = lo;
           *reinterpret_cast<uint4*>(sk + (kr * CPS + swz_chunk<CPS>(2 * ch + 1, kr)) * 16) = hi;
-          dequant16(stg_v[i], vs, lo, hi);
+          dequant16<HALF>(stg_v[i], vs, lo, hi);
           *reinterpret_cast<uint4*>(sv + (kr * CPS + swz_chunk<CPS>(2 * ch, kr)) * 16) = lo;
           *reinterpret_cast<uint4*>(sv + (kr * CPS + swz_chunk<CPS>(2 * ch + 1, kr)) * 16) = hi;
         }
@@ -242,8 +245,8 @@ __global__ void __launch_bounds__(kExtNT, 1) extend_mma_kernel(const ExtendArgs 
           uint32_t bf[4];
           const int kr = np * 16 + krow;
           ldmatrix_x4(bf, sk + (kr * CPS + swz_chunk<CPS>(2 * kc + kch, kr)) * 16);
-          mma_16816<false>(s[2 * np], qf[kc], bf[0], bf[1]);
-          mma_16816<false>(s[2 * np + 1], qf[kc], bf[2], bf[3]);
+          mma_16816<HALF>(s[2 * np], qf[kc], bf[0], bf[1]);
+          mma_16816<HALF>(s[2 * np + 1], qf[kc], bf[2], bf[3]);
         }
       }
     }
@@ -308,17 +311,17 @@ __global__ void __launch_bounds__(kExtNT, 1) extend_mma_kernel(const ExtendArgs 
 #pragma unroll
       for (int ksx = 0; ksx < BN / 16; ++ksx) {
         uint32_t pa[4];
-        pa[0] = pack_bf16x2(s[2 * ksx][0], s[2 * ksx][1]);
-        pa[1] = pack_bf16x2(s[2 * ksx][2], s[2 * ksx][3]);
-        pa[2] = pack_bf16x2(s[2 * ksx + 1][0], s[2 * ksx + 1][1]);
-        pa[3] = pack_bf16x2(s[2 * ksx + 1][2], s[2 * ksx + 1][3]);
+        pa[0] = pack2<HALF>(s[2 * ksx][0], s[2 * ksx][1]);
+        pa[1] = pack2<HALF>(s[2 * ksx][2], s[2 * ksx][3]);
+        pa[2] = pack2<HALF>(s[2 * ksx + 1][0], s[2 * ksx + 1][1]);
+        pa[3] = pack2<HALF>(s[2 * ksx + 1][2], s[2 * ksx + 1][3]);
         const int kr = ksx * 16 + vrow;
 #pragma unroll
         for (int dp = 0; dp < D / 16; ++dp) {
           uint32_t bf[4];
           ldmatrix_x4_trans(bf, sv + (kr * CPS + swz_chunk<CPS>(2 * dp + vch, kr)) * 16);
-          mma_16816<false>(o[2 * dp], pa, bf[0], bf[1]);
-          mma_16816<false>(o[2 * dp + 1], pa, bf[2], bf[3]);
+          mma_16816<HALF>(o[2 * dp], pa, bf[0], bf[1]);
+          mma_16816<HALF>(o[2 * dp + 1], pa, bf[2], bf[3]);
         }
       }
     }
@@ -357,14 +360,14 @@ __global__ void __launch_bounds__(kExtNT, 1) extend_mma_kernel(const ExtendArgs 
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
   if (r0 < live_rows) {
-    __nv_bfloat16* op = a.o + static_cast<int64_t>(start + t0 + r0 / G) * a.o_st + static_cast<int64_t>(kvh * G + r0 % G) * a.o_sh + 2 * cid;
+    uint16_t* op = a.o + static_cast<int64_t>(start + t0 + r0 / G) * a.o_st + static_cast<int64_t>(kvh * G + r0 % G) * a.o_sh + 2 * cid;
 #pragma unroll
-    for (int i = 0; i < D / 8; ++i) *reinterpret_cast<uint32_t*>(op + i * 8) = pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0);
+    for (int i = 0; i < D / 8; ++i) *reinterpret_cast<uint32_t*>(op + i * 8) = pack2<HALF>(o[i][0] * inv0, o[i][1] * inv0);
   }
   if (r1 < live_rows) {
-    __nv_bfloat16* op = a.o + static_cast<int64_t>(start + t0 + r1 / G) * a.o_st + static_cast<int64_t>(kvh * G + r1 % G) * a.o_sh + 2 * cid;
+    uint16_t* op = a.o + static_cast<int64_t>(start + t0 + r1 / G) * a.o_st + static_cast<int64_t>(kvh * G + r1 % G) * a.o_sh + 2 * cid;
 #pragma unroll
-    for (int i = 0; i < D / 8; ++i) *reinterpret_cast<uint32_t*>(op + i * 8) = pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1);
+    for (int i = 0; i < D / 8; ++i) *reinterpret_cast<uint32_t*>(op + i * 8) = pack2<HALF>(o[i][2] * inv1, o[i][3] * inv1);
   }
 }
 
@@ -392,8 +395,8 @@ extern "C" int b200_attn_extend(const b200_extend_params* p, b200_stream_t strea
   if (p->d != p->dv || (p->d != 64 && p->d != 128)) return B200_ERR_UNSUPPORTED;
   const int g = p->hq / p->hkv;
   if (g > kExtRows) return B200_ERR_UNSUPPORTED;
-  const bool fp8 = p->kv_dtype == B200_KV_FP8_E4M3;
-  if (!fp8 && p->kv_dtype != B200_KV_BF16) return B200_ERR_UNSUPPORTED;
+  const bool fp8 = p->kv_dtype == B200_KV_FP8_E4M3, half = p->act_dtype == B200_ACT_F16;
+  if (!dtype_pair_ok(p->kv_dtype, p->act_dtype)) return B200_ERR_UNSUPPORTED;
   const int elt = fp8 ? 1 : 2;
   auto mis16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) != 0; };
   if ((p->k_stride_t * elt) % 16 || (p->v_stride_t * elt) % 16 || p->q_stride_t % 8 || p->q_stride_h % 8 ||
@@ -406,7 +409,7 @@ extern "C" int b200_attn_extend(const b200_extend_params* p, b200_stream_t strea
   // (k_new / v_new heads contiguous inside a token row, as in the fused qkv GEMM output)
   const bool tc_ok = (p->d == 128 || p->d == 64) && p->o_stride_t % 8 == 0 && p->o_stride_h % 8 == 0 && !mis16(p->o) && g <= 128 &&
                      p->kn_stride_h == p->d && p->vn_stride_h == p->dv;
-  const bool pair_ok = tc_ok && p->d == 128 && !fp8;
+  const bool pair_ok = tc_ok && p->d == 128 && !fp8 && !half;
   if (p->force_path == B200_PATH_TC && !tc_ok) return B200_ERR_UNSUPPORTED;
   if (p->force_path == B200_PATH_TC2 && !pair_ok) return B200_ERR_UNSUPPORTED;
   if (tc_ok && (p->force_path == B200_PATH_TC || p->force_path == B200_PATH_TC2 ||
@@ -419,11 +422,11 @@ extern "C" int b200_attn_extend(const b200_extend_params* p, b200_stream_t strea
     return pair ? launch_extend_tc2(p, static_cast<cudaStream_t>(stream)) : launch_extend_tc(p, static_cast<cudaStream_t>(stream));
   }
   ExtendArgs a;
-  a.q = static_cast<const __nv_bfloat16*>(p->q);
+  a.q = static_cast<const uint16_t*>(p->q);
   a.q_st = p->q_stride_t;
   a.q_sh = p->q_stride_h;
-  a.k_new = static_cast<const __nv_bfloat16*>(p->k_new);
-  a.v_new = static_cast<const __nv_bfloat16*>(p->v_new);
+  a.k_new = static_cast<const uint16_t*>(p->k_new);
+  a.v_new = static_cast<const uint16_t*>(p->v_new);
   a.kn_st = p->kn_stride_t;
   a.kn_sh = p->kn_stride_h;
   a.vn_st = p->vn_stride_t;
@@ -432,7 +435,7 @@ extern "C" int b200_attn_extend(const b200_extend_params* p, b200_stream_t strea
   a.vbuf = static_cast<const uint8_t*>(p->v_buf);
   a.k_st_bytes = p->k_stride_t * elt;
   a.v_st_bytes = p->v_stride_t * elt;
-  a.o = static_cast<__nv_bfloat16*>(p->o);
+  a.o = static_cast<uint16_t*>(p->o);
   a.o_st = p->o_stride_t;
   a.o_sh = p->o_stride_h;
   a.r2t = p->req_to_token;
@@ -453,6 +456,10 @@ extern "C" int b200_attn_extend(const b200_extend_params* p, b200_stream_t strea
   const int nqb = (p->max_extend_len + a.bm_t - 1) / a.bm_t;
   const dim3 grid(nqb, p->hkv, p->bs);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (half) {
+    if (p->d == 64) return fp8 ? launch_extend_t<ExtCfg<64, true, true>>(a, grid, st) : launch_extend_t<ExtCfg<64, false, true>>(a, grid, st);
+    return fp8 ? launch_extend_t<ExtCfg<128, true, true>>(a, grid, st) : launch_extend_t<ExtCfg<128, false, true>>(a, grid, st);
+  }
   if (p->d == 64) return fp8 ? launch_extend_t<ExtCfg<64, true>>(a, grid, st) : launch_extend_t<ExtCfg<64, false>>(a, grid, st);
   return fp8 ? launch_extend_t<ExtCfg<128, true>>(a, grid, st) : launch_extend_t<ExtCfg<128, false>>(a, grid, st);
 }

@@ -1,7 +1,7 @@
 // Extend / chunked-prefill attention, and the shared-prefix leg of decode, on the 5th-generation tensor cores
 // (tcgen05 + TMEM), sm_100a.
 //
-// extend_tc_kernel<MODE, F16, D>:
+// extend_tc_kernel<MODE, F16, D, HALF>:
 //   MODE kModeExtend  the Blackwell-native path of b200_attn_extend (BASELINE.json config 4: Llama-3.1-8B, 8 x 2048
 //                     new tokens on an 8192-token cached prefix).  Same semantics as extend.cu / the reference's
 //                     extend_attention_fwd (scratchpad/nn/attention/triton_attn/extend_attention.py:53-226): query
@@ -10,6 +10,8 @@
 //   MODE kModeShared  the decode queries of a whole batch against the prefix all its requests share.
 //   F16               the pool is fp8-e4m3: rows are widened to f16 on chip and the MMAs run f16 x f16.
 //   D                 head_dim 128 or 64.
+//   HALF              the model dtype (q, new tokens, o, a 16-bit pool) is fp16 instead of bf16: the MMAs run f16 x f16
+//                     on the bytes as they are; over an fp8 pool q needs no narrowing and the new tokens are scaled in f16.
 //
 // One CTA per SM, 16 warps in 4 warpgroups, warp-specialised:
 //   warps 0-3 / 4-7 : softmax warpgroups for Q tile 0 / 1 (thread = one query row = one TMEM lane);
@@ -100,15 +102,15 @@ __device__ long long g_trace[kTraceEvents][kTraceLen];
 #endif
 
 struct Args {
-  const __nv_bfloat16* q;
+  const uint16_t* q;  // bf16 or fp16 bits (the model dtype), like k_new / v_new / o
   int64_t q_st, q_sh;
-  const __nv_bfloat16* k_new;
-  const __nv_bfloat16* v_new;
+  const uint16_t* k_new;
+  const uint16_t* v_new;
   int64_t kn_st, kn_sh, vn_st, vn_sh;
   const uint8_t* kbuf;
   const uint8_t* vbuf;
   int64_t k_st_bytes, v_st_bytes;
-  __nv_bfloat16* o;
+  uint16_t* o;
   int64_t o_st, o_sh;
   const int32_t* r2t;
   int64_t r2t_stride;
@@ -148,9 +150,10 @@ __device__ __forceinline__ uint32_t tile_off(int r, int cb, int c) {
 // KV split); F16 = the pool is fp8-e4m3: K/V are widened to f16 on their way into shared memory (exact), Q is
 // narrowed bf16 -> f16 (exact for |q| >= 2^-14) and the MMAs run as f16 x f16; k_scale folds into the softmax
 // scale and v_scale into the epilogue, like the split-KV kernel does.
-template <int MODE, bool F16, int D>
+template <int MODE, bool F16, int D, bool HALF>
 __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_constant__ Args a, const __grid_constant__ TcMaps tm) {
   static_assert(D == 128 || D == 64, "head_dim 128 or 64");
+  constexpr bool MATH16 = F16 || HALF;  // MMA operand type f16 (else bf16)
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) TC_TRACE(16, 0);
@@ -307,8 +310,14 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_con
                 uint32_t w[4];
                 ld_shared_v4(dst + (half ? o1 : o0), w);
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  w[e] = pack_f16x2(__uint_as_float(w[e] << 16) * inv, __uint_as_float(w[e] & 0xffff0000u) * inv);
+                for (int e = 0; e < 4; ++e) {
+                  if constexpr (HALF) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                    w[e] = pack_f16x2(f.x * inv, f.y * inv);
+                  } else {
+                    w[e] = pack_f16x2(__uint_as_float(w[e] << 16) * inv, __uint_as_float(w[e] & 0xffff0000u) * inv);
+                  }
+                }
                 st_shared_v4(dst + (half ? o1 : o0), w[0], w[1], w[2], w[3]);
               }
             }
@@ -486,8 +495,8 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_con
     // no R2UR in front of each UTCHMMA); only the tcgen05.mma / tcgen05.commit themselves are issued by lane 0.
     const bool leader = lane == 0;
     {
-      constexpr uint32_t idesc_qk = instr_desc(kTileRows, kBN, false, F16);
-      constexpr uint32_t idesc_pv = instr_desc(kTileRows, D, true, F16);
+      constexpr uint32_t idesc_qk = instr_desc(kTileRows, kBN, false, MATH16);
+      constexpr uint32_t idesc_pv = instr_desc(kTileRows, D, true, MATH16);
       const uint32_t q_base = sbase + kSmemQ;
       const uint32_t ring = sbase + kSmemRing;
       auto issue_qk = [&](int i, uint32_t k_base) {  // S_i = Q_i . K^T
@@ -608,20 +617,20 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_con
         }
       }
     }
-    auto q_chunk = [&](int it_q, const __nv_bfloat16*& src, uint32_t& dst, bool& live) {
+    auto q_chunk = [&](int it_q, const uint16_t*& src, uint32_t& dst, bool& live) {
       const int R = r_base + RSTEP * it_q;
       live = R < live_rows;
       src = a.q + static_cast<int64_t>(q_rowidx[it_q]) * a.q_st + static_cast<int64_t>(kvh * G + q_head[it_q]) * a.q_sh + ch * 8;
       dst = q_dst0 + ((RSTEP * it_q) >> 7) * kTileBytes + (r_base + ((RSTEP * it_q) & 127)) * 128;
     };
-    if constexpr (F16) {
+    if constexpr (F16 && !HALF) {
       // bf16 -> f16 on the way in: all of the thread's loads are issued before the first one is converted
       // (one memory round trip; one load per iteration was 10 us of the shared-prefix leg's 40)
       uint4 x[kQIters];
       uint32_t dsts[kQIters];
 #pragma unroll
       for (int it_q = 0; it_q < kQIters; ++it_q) {
-        const __nv_bfloat16* src;
+        const uint16_t* src;
         bool live;
         q_chunk(it_q, src, dsts[it_q], live);
         x[it_q] = live ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0u, 0u, 0u, 0u);
@@ -639,7 +648,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_con
     } else {
 #pragma unroll
       for (int it_q = 0; it_q < kQIters; ++it_q) {
-        const __nv_bfloat16* src;
+        const uint16_t* src;
         uint32_t dst;
         bool live;
         q_chunk(it_q, src, dst, live);
@@ -719,7 +728,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_con
             unpack_f32x2(y, y0, y1);
             const float p0 = ex2(y0), p1 = ex2(y1);
             l2 = add_f32x2(l2, pack_f32x2(p0, p1));
-            pk[k >> 1] = pack2<F16>(p0, p1);
+            pk[k >> 1] = pack2<MATH16>(p0, p1);
           }
           tc_st16(s_addr + c4 * 16, pk);
         }
@@ -753,7 +762,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_con
               unpack_f32x2(y, y0, y1);
               const float p0 = ex2(y0), p1 = ex2(y1);
               l2 = add_f32x2(l2, pack_f32x2(p0, p1));
-              pk[k >> 1] = pack2<F16>(p0, p1);
+              pk[k >> 1] = pack2<MATH16>(p0, p1);
             }
             tc_st16(s_addr + c4 * 16, pk);
           }
@@ -771,7 +780,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_con
             unpack_f32x2(y, y0, y1);
             const float p0 = ex2(y0), p1 = ex2(y1);
             l2 = add_f32x2(l2, pack_f32x2(p0, p1));
-            pk[k >> 1] = pack2<F16>(p0, p1);
+            pk[k >> 1] = pack2<MATH16>(p0, p1);
           }
           tc_st16(s_addr + c4 * 16, pk);
         }
@@ -848,7 +857,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_con
                 p1 = ex2(y1);
               }
               l2 = add_f32x2(l2, pack_f32x2(p0, p1));
-              pk[k >> 1] = pack2<F16>(p0, p1);
+              pk[k >> 1] = pack2<MATH16>(p0, p1);
             }
             tc_st16(s_addr + c4 * 16, pk);
             if (c4 == 1) {  // keys 0..63 of P are in TMEM: release them to the MMA warp
@@ -881,7 +890,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_con
             if (c4 * 32 + k > climit) p0 = 0.f;
             if (c4 * 32 + k + 1 > climit) p1 = 0.f;
             l += p0 + p1;
-            pk[k >> 1] = pack2<F16>(p0, p1);
+            pk[k >> 1] = pack2<MATH16>(p0, p1);
           }
           tc_st16(s_addr + c4 * 16, pk);
           if (c4 == 1) {
@@ -905,7 +914,7 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_con
     const bool live = R < live_rows;
     if constexpr (MODE == kModeExtend) {
       const float inv = l > 0.f ? ((F16 && a.v_scale) ? __ldg(a.v_scale + kvh) : 1.f) / l : 0.f;
-      __nv_bfloat16* op = a.o + static_cast<int64_t>(start + t0 + (live ? R / G : 0)) * a.o_st +
+      uint16_t* op = a.o + static_cast<int64_t>(start + t0 + (live ? R / G : 0)) * a.o_st +
                           static_cast<int64_t>(kvh * G + (live ? R % G : 0)) * a.o_sh;
 #pragma unroll 1
       for (int c4 = 0; c4 < D / 32; ++c4) {
@@ -916,10 +925,10 @@ __global__ void __launch_bounds__(kThreads, 1) extend_tc_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < 32; k += 8) {
             uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(w[k]) * inv, __uint_as_float(w[k + 1]) * inv);
-            u.y = pack_bf16x2(__uint_as_float(w[k + 2]) * inv, __uint_as_float(w[k + 3]) * inv);
-            u.z = pack_bf16x2(__uint_as_float(w[k + 4]) * inv, __uint_as_float(w[k + 5]) * inv);
-            u.w = pack_bf16x2(__uint_as_float(w[k + 6]) * inv, __uint_as_float(w[k + 7]) * inv);
+            u.x = pack2<HALF>(__uint_as_float(w[k]) * inv, __uint_as_float(w[k + 1]) * inv);
+            u.y = pack2<HALF>(__uint_as_float(w[k + 2]) * inv, __uint_as_float(w[k + 3]) * inv);
+            u.z = pack2<HALF>(__uint_as_float(w[k + 4]) * inv, __uint_as_float(w[k + 5]) * inv);
+            u.w = pack2<HALF>(__uint_as_float(w[k + 6]) * inv, __uint_as_float(w[k + 7]) * inv);
             *reinterpret_cast<uint4*>(op + c4 * 32 + k) = u;
           }
         }
@@ -974,23 +983,36 @@ extern "C" int b200_debug_tc_trace_read(long long* host_dst) {
 }
 #endif
 
-template <int MODE, bool F16, int D>
+template <int MODE>
+static int dispatch_tc(bool fp8, int d, bool half, const tc::Args& a, const tc::TcMaps& maps, dim3 grid, cudaStream_t st);
+
+template <int MODE, bool F16, int D, bool HALF>
 static int launch_tc(const tc::Args& a, const tc::TcMaps& maps, dim3 grid, cudaStream_t st) {
-  auto kern = tc::extend_tc_kernel<MODE, F16, D>;
+  auto kern = tc::extend_tc_kernel<MODE, F16, D, HALF>;
   static PerDevice pd;  // per instantiation
   if (int rc = ensure_smem_attr(kern, tc::kSmemBytes, pd)) return rc;
   return launch_pdl(kern, grid, dim3(tc::kThreads), tc::kSmemBytes, st, a, maps);
+}
+
+template <int MODE>
+static int dispatch_tc(bool fp8, int d, bool half, const tc::Args& a, const tc::TcMaps& maps, dim3 grid, cudaStream_t st) {
+  if (half) {
+    if (d == 64) return fp8 ? launch_tc<MODE, true, 64, true>(a, maps, grid, st) : launch_tc<MODE, false, 64, true>(a, maps, grid, st);
+    return fp8 ? launch_tc<MODE, true, 128, true>(a, maps, grid, st) : launch_tc<MODE, false, 128, true>(a, maps, grid, st);
+  }
+  if (d == 64) return fp8 ? launch_tc<MODE, true, 64, false>(a, maps, grid, st) : launch_tc<MODE, false, 64, false>(a, maps, grid, st);
+  return fp8 ? launch_tc<MODE, true, 128, false>(a, maps, grid, st) : launch_tc<MODE, false, 128, false>(a, maps, grid, st);
 }
 
 // Called by b200_attn_extend (extend.cu) for head_dim 128 and 64 (bf16 or fp8 pool).  Strides and pointers have been validated there.
 int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
   const bool fp8 = p->kv_dtype == B200_KV_FP8_E4M3;
   tc::Args a{};
-  a.q = static_cast<const __nv_bfloat16*>(p->q);
+  a.q = static_cast<const uint16_t*>(p->q);
   a.q_st = p->q_stride_t;
   a.q_sh = p->q_stride_h;
-  a.k_new = static_cast<const __nv_bfloat16*>(p->k_new);
-  a.v_new = static_cast<const __nv_bfloat16*>(p->v_new);
+  a.k_new = static_cast<const uint16_t*>(p->k_new);
+  a.v_new = static_cast<const uint16_t*>(p->v_new);
   a.kn_st = p->kn_stride_t;
   a.kn_sh = p->kn_stride_h;
   a.vn_st = p->vn_stride_t;
@@ -1001,7 +1023,7 @@ int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
   a.v_st_bytes = p->v_stride_t * (fp8 ? 1 : 2);
   a.k_scale = p->k_scale;
   a.v_scale = p->v_scale;
-  a.o = static_cast<__nv_bfloat16*>(p->o);
+  a.o = static_cast<uint16_t*>(p->o);
   a.o_st = p->o_stride_t;
   a.o_sh = p->o_stride_h;
   a.r2t = p->req_to_token;
@@ -1037,8 +1059,7 @@ int launch_extend_tc(const b200_extend_params* p, cudaStream_t st) {
         cached_pool_map(&maps.pool_v, p->v_buf, a.v_st_bytes, p->kv_pool_rows, p->hkv, p->dv, false, tc::kBN, 1) == B200_OK)
       a.tma |= 2;
   }
-  if (p->d == 64) return fp8 ? launch_tc<tc::kModeExtend, true, 64>(a, maps, grid, st) : launch_tc<tc::kModeExtend, false, 64>(a, maps, grid, st);
-  return fp8 ? launch_tc<tc::kModeExtend, true, 128>(a, maps, grid, st) : launch_tc<tc::kModeExtend, false, 128>(a, maps, grid, st);
+  return dispatch_tc<tc::kModeExtend>(fp8, p->d, p->act_dtype == B200_ACT_F16, a, maps, grid, st);
 }
 
 // Shared-prefix ("cascade") leg of b200_attn_decode (decode.cu): the decode queries of the whole batch against the
@@ -1051,7 +1072,7 @@ int launch_shared_prefix_tc(const b200_decode_params* p, const CasTables& t, flo
   const bool fp8 = p->kv_dtype == B200_KV_FP8_E4M3;
   if (p->d != p->dv || tc::kRows % g != 0 || !(p->d == 128 || p->d == 64)) return B200_ERR_UNSUPPORTED;
   tc::Args a{};
-  a.q = static_cast<const __nv_bfloat16*>(p->q);
+  a.q = static_cast<const uint16_t*>(p->q);
   a.q_st = p->q_stride_t;
   a.q_sh = p->q_stride_h;
   a.kbuf = static_cast<const uint8_t*>(p->k_buf);
@@ -1075,8 +1096,7 @@ int launch_shared_prefix_tc(const b200_decode_params* p, const CasTables& t, flo
   const dim3 grid(p->hkv, nsplit, (p->bs + a.bm_t - 1) / a.bm_t);  // z = row-tile lanes; CTAs loop over further tiles
   tc::TcMaps maps;
   memset(&maps, 0, sizeof(maps));
-  if (p->d == 64) return fp8 ? launch_tc<tc::kModeShared, true, 64>(a, maps, grid, st) : launch_tc<tc::kModeShared, false, 64>(a, maps, grid, st);
-  return fp8 ? launch_tc<tc::kModeShared, true, 128>(a, maps, grid, st) : launch_tc<tc::kModeShared, false, 128>(a, maps, grid, st);
+  return dispatch_tc<tc::kModeShared>(fp8, p->d, p->act_dtype == B200_ACT_F16, a, maps, grid, st);
 }
 
 }  // namespace b200

@@ -249,21 +249,44 @@ class MHATokenToKVPool:
 def kv_dtype_code(dtype: torch.dtype) -> int:
     if dtype == torch.bfloat16:
         return _lib.KV_BF16
+    if dtype == torch.float16:
+        return _lib.KV_F16
     if dtype == torch.float8_e4m3fn:
         return _lib.KV_FP8_E4M3
     raise NotImplementedError(f"kv cache dtype {dtype} is not supported by the cuda_b200 backend")
+
+
+def act_dtype_code(dtype: torch.dtype) -> int:
+    """The model dtype (q, the new tokens' k / v, o): bf16, or fp16 -- what the engine picks for fp16 and, by
+    default, fp32 checkpoints (config/utils.py:41-43)."""
+    if dtype == torch.bfloat16:
+        return _lib.ACT_BF16
+    if dtype == torch.float16:
+        return _lib.ACT_F16
+    raise NotImplementedError(f"model dtype {dtype} is not supported by the cuda_b200 backend (bfloat16 or float16)")
+
+
+def check_dtype_pair(kv_code: int, act_code: int) -> None:
+    """bf16 activations go with a bf16 or fp8-e4m3 pool, fp16 activations with an fp16 or fp8-e4m3 pool
+    (kv_cache_dtype "auto" = the model dtype, model_runner.py:366-367)."""
+    ok = {_lib.ACT_BF16: (_lib.KV_BF16, _lib.KV_FP8_E4M3), _lib.ACT_F16: (_lib.KV_F16, _lib.KV_FP8_E4M3)}[act_code]
+    if kv_code not in ok:
+        raise NotImplementedError("cuda_b200 backend: a 16-bit KV pool must have the model dtype "
+                                  f"(kv dtype code {kv_code}, activation dtype code {act_code})")
 
 
 def kv_store(kb: torch.Tensor, vb: torch.Tensor, loc: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor,
              kv_code: int, k_scale: Optional[torch.Tensor], v_scale: Optional[torch.Tensor]) -> None:
     """``kb[loc] = quant(cache_k); vb[loc] = quant(cache_v)`` -- one ``b200_kv_store`` launch on the current stream.
     ``kb``/``vb``: one layer's ``[P+page, Hkv, D]`` pool buffers (bf16, or uint8 / fp8 storage); ``cache_k``/``cache_v``
-    bf16 ``[T, Hkv, D]`` (or ``[T, Hkv*D]``), possibly column slices of the qkv GEMM output; scales: device fp32
+    bf16 / fp16 ``[T, Hkv, D]`` (or ``[T, Hkv*D]``), possibly column slices of the qkv GEMM output; scales: device fp32
     ``[Hkv]`` or None.  The caller's k/v are not modified (the reference divides them in place, pool.py:404-412)."""
     if not cache_k.is_cuda:
         raise RuntimeError("cuda_b200 kv_store needs CUDA tensors (no CPU fallback)")
-    if cache_k.dtype != torch.bfloat16 or cache_v.dtype != torch.bfloat16:
-        raise NotImplementedError("the cuda_b200 backend stores from bf16 activations")
+    if cache_k.dtype != cache_v.dtype:
+        raise TypeError(f"k and v must have one dtype, got {cache_k.dtype} and {cache_v.dtype}")
+    act_code = act_dtype_code(cache_k.dtype)
+    check_dtype_pair(kv_code, act_code)
     if loc.dtype not in (torch.int64, torch.int32) or not loc.is_contiguous():
         raise TypeError(f"out_cache_loc must be a contiguous int64/int32 tensor, got {loc.dtype}")
     hkv, d, dv = kb.shape[1], kb.shape[2], vb.shape[2]
@@ -278,7 +301,7 @@ def kv_store(kb: torch.Tensor, vb: torch.Tensor, loc: torch.Tensor, cache_k: tor
         kb.data_ptr(), vb.data_ptr(), kb.stride(0), vb.stride(0),
         loc.data_ptr(), loc_code, cache_k.data_ptr(), cache_v.data_ptr(),
         cache_k.stride(0), cache_k.stride(1), cache_v.stride(0), cache_v.stride(1),
-        cache_k.shape[0], hkv, d, dv, kv_code,
+        cache_k.shape[0], hkv, d, dv, kv_code, act_code,
         k_scale.data_ptr() if k_scale is not None else None, v_scale.data_ptr() if v_scale is not None else None,
         torch.cuda.current_stream().cuda_stream,
     )

@@ -24,7 +24,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .pool import kv_dtype_code
+from .pool import act_dtype_code, check_dtype_pair, kv_dtype_code
 
 
 class RotaryEmbedding(nn.Module):
@@ -54,17 +54,18 @@ class RotaryEmbedding(nn.Module):
     def _launch(self, positions, q, k, v=None, pool=None, layer_id=None, loc=None, write_back_k=True, scales=None) -> None:
         if not k.is_cuda:
             raise RuntimeError("cuda_b200 rotary embedding needs CUDA tensors (no CPU fallback)")
-        if k.dtype != torch.bfloat16 or (q is not None and q.dtype != torch.bfloat16):
-            raise NotImplementedError("cuda_b200 rotary embedding: q/k must be bfloat16")
+        if q is not None and q.dtype != k.dtype:
+            raise TypeError(f"q and k must have one dtype, got {q.dtype} and {k.dtype}")
+        act_code = act_dtype_code(k.dtype)  # bf16 or fp16: the arithmetic is rounded to this dtype
         cache = self.cos_sin_cache
         if cache.device != k.device:
             self.cos_sin_cache = cache = cache.to(k.device)
-        if cache.dtype == torch.bfloat16:
-            cache_code = _lib.CACHE_BF16
-        elif cache.dtype == torch.float32:
+        if cache.dtype == torch.float32:
             cache_code = _lib.CACHE_F32
-        else:
-            raise NotImplementedError(f"cos_sin_cache dtype {cache.dtype}")
+        elif cache.dtype == k.dtype:
+            cache_code = _lib.CACHE_F16 if k.dtype == torch.float16 else _lib.CACHE_BF16
+        else:  # the module builds its cache in the model dtype (reference rotary_embedding.py:90-99)
+            raise NotImplementedError(f"cos_sin_cache dtype {cache.dtype} with {k.dtype} activations")
         hs = self.head_size
         positions = positions.flatten()
         if positions.dtype not in (torch.int64, torch.int32):
@@ -82,7 +83,7 @@ class RotaryEmbedding(nn.Module):
             cache_dtype=cache_code, pos_dtype=_lib.IDX_I64 if positions.dtype == torch.int64 else _lib.IDX_I32,
             rotary_dim=self.rotary_dim, is_neox=int(self.is_neox_style),
             num_tokens=t, hq=q3.shape[1] if q3 is not None else 0, hkv=k3.shape[1], d=hs, dv=hs,
-            kv_dtype=_lib.KV_BF16, write_back_k=int(write_back_k),
+            kv_dtype=_lib.KV_BF16, write_back_k=int(write_back_k), act_dtype=act_code,
         )
         if pool is not None:
             kb, vb = pool.k_buffer[layer_id], pool.v_buffer[layer_id]
@@ -103,6 +104,7 @@ class RotaryEmbedding(nn.Module):
             p.loc_dtype = {torch.int64: _lib.IDX_I64, torch.int32: _lib.IDX_I32}[loc.dtype]
             p.dv = v3.shape[2]
             p.kv_dtype = kv_dtype_code(pool.dtype)
+            check_dtype_pair(p.kv_dtype, act_code)
             p.k_scale = ks.data_ptr() if ks is not None else None
             p.v_scale = vs.data_ptr() if vs is not None else None
         rc = _lib.load().b200_rope_kv_store(p, torch.cuda.current_stream().cuda_stream)

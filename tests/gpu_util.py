@@ -6,6 +6,7 @@ from scratchpad_b200 import CudaB200AttnBackend
 from harness import ForwardBatch, ForwardMode, compute_extend_start_loc, synth
 
 BF16_ABS, BF16_REL = 2e-2, 1e-2   # BASELINE.json north_star tolerance, bf16 KV
+F16_ABS, F16_REL = 1e-2, 5e-3     # fp16 model dtype over an fp16 pool: 3 more mantissa bits than bf16, tighter bound
 FP8_ABS, FP8_REL = 5e-2, 5e-2     # fp8-e4m3 KV
 
 
@@ -26,12 +27,12 @@ def assert_close(got, ref, abs_tol, rel_tol, what=""):
 FUSED_KV = False  # tests flip this to run every helper over the fused [P+1, 2, Hkv, D] pool layout
 
 
-def make_runner_from_case(k_buf, v_buf, r2t, kv_dtype, k_scale=None, v_scale=None, tp_hq=None, page_size=1):
-    """Pools on the GPU holding exactly the CPU case's bytes."""
+def make_runner_from_case(k_buf, v_buf, r2t, kv_dtype, k_scale=None, v_scale=None, tp_hq=None, page_size=1, dtype=None):
+    """Pools on the GPU holding exactly the CPU case's bytes.  ``dtype``: the model dtype (see make_model_runner)."""
     p1, hkv, d = k_buf.shape
     runner = synth.make_model_runner(tp_hq, hkv, d, tp_size=1, layer_num=1, pool_tokens=p1 - page_size,
                                      max_reqs=r2t.shape[0] - 1, context_len=r2t.shape[1] - 4, kv_dtype=kv_dtype,
-                                     fused_kv=FUSED_KV, page_size=page_size)
+                                     fused_kv=FUSED_KV, page_size=page_size, dtype=dtype)
     pool = runner.token_to_kv_pool
     pool.k_buffer[0].copy_(k_buf.view(pool.store_dtype))
     pool.v_buffer[0].copy_(v_buf.view(pool.store_dtype))
@@ -45,7 +46,8 @@ def run_decode_case(q, k_buf, v_buf, r2t, rpi, sl, sm_scale, logit_cap=0.0, kv_d
                     k_scale=None, v_scale=None, idx_dtype=torch.int64, q_slice_of_qkv=False, force_path=-1,
                     cascade=None, page_size=1, tma_contiguous_runs=None):
     b, hq, d = q.shape
-    runner = make_runner_from_case(k_buf, v_buf, r2t, kv_dtype, k_scale, v_scale, tp_hq=hq, page_size=page_size)
+    runner = make_runner_from_case(k_buf, v_buf, r2t, kv_dtype, k_scale, v_scale, tp_hq=hq, page_size=page_size,
+                                   dtype=q.dtype)
     backend = CudaB200AttnBackend(runner, force_path=force_path, cascade=cascade, tma_contiguous_runs=tma_contiguous_runs)
     layer = synth.make_layer(runner, 0, logit_cap)
     layer.scaling = sm_scale
@@ -56,7 +58,7 @@ def run_decode_case(q, k_buf, v_buf, r2t, rpi, sl, sm_scale, logit_cap=0.0, kv_d
                       attn_backend=backend)
     hkv = k_buf.shape[1]
     if q_slice_of_qkv:  # q as a column slice of the fused qkv GEMM output (llama.py:149-152)
-        qkv = torch.zeros((b, (hq + 2 * hkv) * d), dtype=torch.bfloat16, device="cuda")
+        qkv = torch.zeros((b, (hq + 2 * hkv) * d), dtype=q.dtype, device="cuda")
         qkv[:, : hq * d] = q.reshape(b, hq * d).cuda()
         qd = qkv[:, : hq * d]
     else:
@@ -68,9 +70,12 @@ def run_decode_case(q, k_buf, v_buf, r2t, rpi, sl, sm_scale, logit_cap=0.0, kv_d
 
 
 def random_decode_case(hq, hkv, d, seq_lens, seed, kv_dtype=torch.bfloat16, shared_prefix=0, per_head=True,
-                       extra_rows=3, mode="random", page_size=1):
-    """CPU tensors for one decode case (bf16-valued; fp8 pools quantised with amax/448 scales).
+                       extra_rows=3, mode="random", page_size=1, act_dtype=None):
+    """CPU tensors for one decode case (values in the model dtype ``act_dtype`` -- default: the pool's when 16-bit, else
+    bf16; fp8 pools quantised with amax/448 scales).
     page_size > 1: page-granular tables (synth.build_paged_table) over a [pool + page_size, Hkv, D] buffer."""
+    if act_dtype is None:
+        act_dtype = kv_dtype if kv_dtype in (torch.bfloat16, torch.float16) else torch.bfloat16
     gen = torch.Generator().manual_seed(seed)
     b = len(seq_lens)
     r2t = torch.zeros((b + extra_rows, max(max(seq_lens), 1) + 4), dtype=torch.int32)
@@ -82,11 +87,11 @@ def random_decode_case(hq, hkv, d, seq_lens, seed, kv_dtype=torch.bfloat16, shar
         need = shared_prefix + sum(n - shared_prefix if shared_prefix and n >= shared_prefix else n for n in seq_lens)
         pool = need + 17
         rpi = synth.build_page_table(r2t, seq_lens, pool, gen, mode, shared_prefix)
-    kf = torch.randn((pool + page_size, hkv, d), generator=gen).to(torch.bfloat16)
-    vf = torch.randn((pool + page_size, hkv, d), generator=gen).to(torch.bfloat16)
-    q = torch.randn((b, hq, d), generator=gen).to(torch.bfloat16)
+    kf = torch.randn((pool + page_size, hkv, d), generator=gen).to(act_dtype)
+    vf = torch.randn((pool + page_size, hkv, d), generator=gen).to(act_dtype)
+    q = torch.randn((b, hq, d), generator=gen).to(act_dtype)
     ks = vs = None
-    if kv_dtype != torch.bfloat16:
+    if kv_dtype != act_dtype:
         from oracle import attn_oracle as O
         if per_head:
             ks = kf.float().abs().amax(dim=(0, 2)) / 448.0
@@ -102,8 +107,10 @@ def random_decode_case(hq, hkv, d, seq_lens, seed, kv_dtype=torch.bfloat16, shar
 
 
 def random_extend_case(hq, hkv, d, prefix_lens, extend_lens, seed, kv_dtype=torch.bfloat16, per_head=True,
-                       extra_rows=2, mode="random", page_size=1):
-    """CPU tensors for one extend case: pool holding the prefixes (quantised for fp8), new q/k/v in bf16."""
+                       extra_rows=2, mode="random", page_size=1, act_dtype=None):
+    """CPU tensors for one extend case: pool holding the prefixes (quantised for fp8), new q/k/v in the model dtype."""
+    if act_dtype is None:
+        act_dtype = kv_dtype if kv_dtype in (torch.bfloat16, torch.float16) else torch.bfloat16
     gen = torch.Generator().manual_seed(seed)
     seq_lens = [p + e for p, e in zip(prefix_lens, extend_lens)]
     b = len(seq_lens)
@@ -114,14 +121,14 @@ def random_extend_case(hq, hkv, d, prefix_lens, extend_lens, seed, kv_dtype=torc
     else:
         pool = sum(seq_lens) + 19
         rpi = synth.build_page_table(r2t, seq_lens, pool, gen, mode)
-    kf = torch.randn((pool + page_size, hkv, d), generator=gen).to(torch.bfloat16)
-    vf = torch.randn((pool + page_size, hkv, d), generator=gen).to(torch.bfloat16)
+    kf = torch.randn((pool + page_size, hkv, d), generator=gen).to(act_dtype)
+    vf = torch.randn((pool + page_size, hkv, d), generator=gen).to(act_dtype)
     t = sum(extend_lens)
-    q = torch.randn((t, hq, d), generator=gen).to(torch.bfloat16)
-    k_new = torch.randn((t, hkv, d), generator=gen).to(torch.bfloat16)
-    v_new = torch.randn((t, hkv, d), generator=gen).to(torch.bfloat16)
+    q = torch.randn((t, hq, d), generator=gen).to(act_dtype)
+    k_new = torch.randn((t, hkv, d), generator=gen).to(act_dtype)
+    v_new = torch.randn((t, hkv, d), generator=gen).to(act_dtype)
     ks = vs = None
-    if kv_dtype != torch.bfloat16:
+    if kv_dtype != act_dtype:
         from oracle import attn_oracle as O
         if per_head:
             ks = kf.float().abs().amax(dim=(0, 2)) / 448.0
@@ -147,7 +154,7 @@ def run_extend_case(c, logit_cap=0.0, idx_dtype=torch.int64, save_kv_cache=True,
     hkv = c["k_buf"].shape[1]
     kv_dtype = c.get("kv_dtype", torch.bfloat16)
     runner = make_runner_from_case(c["k_buf"], c["v_buf"], c["req_to_token"], kv_dtype, c.get("k_scale"),
-                                   c.get("v_scale"), tp_hq=hq, page_size=c.get("page_size", 1))
+                                   c.get("v_scale"), tp_hq=hq, page_size=c.get("page_size", 1), dtype=c["q"].dtype)
     backend = CudaB200AttnBackend(runner, force_path=force_path)
     layer = synth.make_layer(runner, 0, logit_cap)
     layer.scaling = c["sm_scale"]
@@ -167,7 +174,7 @@ def run_extend_case(c, logit_cap=0.0, idx_dtype=torch.int64, save_kv_cache=True,
                       req_to_token_pool=runner.req_to_token_pool, token_to_kv_pool=runner.token_to_kv_pool,
                       attn_backend=backend)
     if qkv_slices:  # q/k/v as column slices of the fused qkv GEMM output (llama.py:149-152)
-        qkv = torch.zeros((t, (hq + 2 * hkv) * d), dtype=torch.bfloat16, device="cuda")
+        qkv = torch.zeros((t, (hq + 2 * hkv) * d), dtype=c["q"].dtype, device="cuda")
         qkv[:, : hq * d] = c["q"].reshape(t, -1).cuda()
         qkv[:, hq * d: (hq + hkv) * d] = c["k_new"].reshape(t, -1).cuda()
         qkv[:, (hq + hkv) * d:] = c["v_new"].reshape(t, -1).cuda()

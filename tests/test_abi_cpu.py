@@ -92,6 +92,45 @@ def test_rope_store_argument_checks_run_before_any_launch():
     assert lib.b200_rope_kv_store(params(k=base + 2), None) == _lib.ERR_INVALID   # misaligned
     assert lib.b200_rope_kv_store(params(k_buf=base), None) == _lib.ERR_INVALID   # k_buf without v_buf
     assert lib.b200_rope_kv_store(params(cache_dtype=5), None) == _lib.ERR_UNSUPPORTED
+    # a 16-bit cos/sin cache is in the model dtype; a pool is the model dtype or fp8-e4m3
+    assert lib.b200_rope_kv_store(params(act_dtype=_lib.ACT_F16), None) == _lib.ERR_UNSUPPORTED        # fp16 q/k, bf16 cache
+    assert lib.b200_rope_kv_store(params(cache_dtype=_lib.CACHE_F16), None) == _lib.ERR_UNSUPPORTED    # bf16 q/k, fp16 cache
+    assert lib.b200_rope_kv_store(params(act_dtype=7, cache_dtype=_lib.CACHE_F32), None) == _lib.ERR_UNSUPPORTED
+    pooled = dict(k_buf=base, v_buf=base, v=base, loc=base, v_src_stride_t=128, v_src_stride_h=64, k_stride_t=128,
+                  v_stride_t=128, cache_dtype=_lib.CACHE_F32)
+    assert lib.b200_rope_kv_store(params(act_dtype=_lib.ACT_F16, kv_dtype=_lib.KV_BF16, **pooled), None) == _lib.ERR_UNSUPPORTED
+    assert lib.b200_rope_kv_store(params(act_dtype=_lib.ACT_BF16, kv_dtype=_lib.KV_F16, **pooled), None) == _lib.ERR_UNSUPPORTED
+
+
+def test_model_dtype_and_pool_dtype_pairing():
+    """bf16 activations go with a bf16 or fp8-e4m3 pool, fp16 activations with an fp16 or fp8-e4m3 pool
+    (kv_cache_dtype "auto" = the model dtype, model_runner.py:366-367); checked in Python and again behind the C ABI."""
+    from scratchpad_b200.pool import act_dtype_code, check_dtype_pair, kv_dtype_code
+    assert kv_dtype_code(torch.float16) == _lib.KV_F16 and act_dtype_code(torch.float16) == _lib.ACT_F16
+    assert kv_dtype_code(torch.bfloat16) == _lib.KV_BF16 and act_dtype_code(torch.bfloat16) == _lib.ACT_BF16
+    for kv, act in ((_lib.KV_BF16, _lib.ACT_BF16), (_lib.KV_FP8_E4M3, _lib.ACT_BF16), (_lib.KV_F16, _lib.ACT_F16),
+                    (_lib.KV_FP8_E4M3, _lib.ACT_F16)):
+        check_dtype_pair(kv, act)
+    for kv, act in ((_lib.KV_F16, _lib.ACT_BF16), (_lib.KV_BF16, _lib.ACT_F16)):
+        with pytest.raises(NotImplementedError):
+            check_dtype_pair(kv, act)
+    with pytest.raises(NotImplementedError):
+        act_dtype_code(torch.float32)
+    # b200_kv_store / b200_attn_decode / b200_attn_extend refuse the pairing on the host, before any launch
+    lib = _lib.load()
+    buf = (ctypes.c_uint8 * 4096)()
+    base = (ctypes.addressof(buf) + 15) & ~15
+    rc = lib.b200_kv_store(base, base, 128, 128, base, _lib.IDX_I64, base, base, 128, 64, 128, 64, 1, 2, 64, 64,
+                           _lib.KV_BF16, _lib.ACT_F16, None, None, None)
+    assert rc == _lib.ERR_UNSUPPORTED
+    dp = _lib.DecodeParams(q=base, k_buf=base, v_buf=base, o=base, req_to_token=base, workspace=base, bs=1, max_bs=1,
+                           hq=8, hkv=2, d=64, dv=64, kv_dtype=_lib.KV_F16, act_dtype=_lib.ACT_BF16)
+    assert lib.b200_attn_decode(dp, None) == _lib.ERR_UNSUPPORTED
+    ep = _lib.ExtendParams(q=base, k_new=base, v_new=base, k_buf=base, v_buf=base, o=base, req_to_token=base,
+                           req_pool_indices=base, seq_lens=base, extend_seq_lens=base, extend_start_loc=base, bs=1,
+                           hq=8, hkv=2, d=64, dv=64, total_tokens=4, max_extend_len=4, kv_dtype=_lib.KV_BF16,
+                           act_dtype=_lib.ACT_F16)
+    assert lib.b200_attn_extend(ep, None) == _lib.ERR_UNSUPPORTED
 
 
 def test_rotary_module_builds_the_reference_cache():
@@ -103,8 +142,9 @@ def test_rotary_module_builds_the_reference_cache():
                "original_max_position_embeddings": 8192}
     for name in golden_names("rope"):
         g = load_golden(name)
+        dtype = torch.float16 if g.get("dtype", "bf16") == "f16" else torch.bfloat16  # ropeh_*: fp16 model dtype
         emb = get_rope(g["head_size"], g["rotary_dim"], g["max_position"], g["base"], bool(g["is_neox"]),
-                       scaling if g["llama3"] else None, dtype=torch.bfloat16)
+                       scaling if g["llama3"] else None, dtype=dtype)
         want = g["cos_sin_cache"].view(torch.int16)
         assert torch.equal(emb.cos_sin_cache.cpu().view(torch.int16), want), name
     with pytest.raises(RuntimeError):  # no CPU fallback

@@ -23,22 +23,20 @@ def bits(x):
     return x.contiguous().view(torch.int16)
 
 
-def _bf16(a):
-    return a.view(torch.int16).view(torch.bfloat16) if a.dtype != torch.bfloat16 else a
-
-
-@pytest.mark.parametrize("name", golden_names("rope"))
-@pytest.mark.parametrize("cache_dtype", [torch.bfloat16, torch.float32])
-def test_rotation_matches_reference_golden_bit_exact(name, cache_dtype):
+@pytest.mark.parametrize("name", golden_names("rope"))  # rope_*: bf16 model dtype, ropeh_*: fp16
+@pytest.mark.parametrize("cache", ["model_dtype", "f32"])
+def test_rotation_matches_reference_golden_bit_exact(name, cache):
     g = load_golden(name)
-    emb = RotaryEmbedding(g["head_size"], g["rotary_dim"], g["max_position"], g["base"], bool(g["is_neox"]),
-                          torch.bfloat16)
-    emb.cos_sin_cache = _bf16(g["cos_sin_cache"]).to(cache_dtype).cuda()  # the reference module's own cache
-    q, k = _bf16(g["q"]).cuda(), _bf16(g["k"]).cuda()
+    dtype = torch.float16 if g.get("dtype", "bf16") == "f16" else torch.bfloat16
+    as_model = lambda a: a.view(torch.int16).view(dtype)  # the fixtures hold 16-bit patterns
+    emb = RotaryEmbedding(g["head_size"], g["rotary_dim"], g["max_position"], g["base"], bool(g["is_neox"]), dtype)
+    ref_cache = as_model(g["cos_sin_cache"])  # the reference module's own cache
+    emb.cos_sin_cache = (ref_cache if cache == "model_dtype" else ref_cache.float()).cuda()
+    q, k = as_model(g["q"]).cuda(), as_model(g["k"]).cuda()
     q2, k2 = emb(g["positions"].cuda(), q, k)
     assert q2.data_ptr() == q.data_ptr() and k2.data_ptr() == k.data_ptr()  # in place, like forward_cuda
-    assert torch.equal(bits(q.cpu()), bits(_bf16(g["q_out"])))
-    assert torch.equal(bits(k.cpu()), bits(_bf16(g["k_out"])))
+    assert torch.equal(bits(q.cpu()), bits(as_model(g["q_out"])))
+    assert torch.equal(bits(k.cpu()), bits(as_model(g["k_out"])))
 
 
 @pytest.mark.parametrize("kv_dtype", [torch.bfloat16, torch.float8_e4m3fn])

@@ -143,6 +143,39 @@ def triton_extend(q, k_new, v_new, k_buf, v_buf, req_to_token, req_pool_indices,
     return o
 
 
+class TrtllmGenDecode:
+    """FlashInfer's ``trtllm-gen`` paged decode (SURVEY.md 8d "stretch" comparator): NVIDIA's own Blackwell-native
+    (tcgen05 / TMA) FMHA cubins shipped in ``flashinfer-cubin``, reached through
+    ``flashinfer.decode.trtllm_batch_decode_with_kv_cache``.  Not a path the reference engine takes -- it needs pages of
+    >= 16 tokens, the reference runs page size 1 -- but the strongest library kernel for this op on this GPU, so it is
+    timed on the very pool bytes the b200 backend reads when the pool is paged: the ``[P + page, Hkv, D]`` buffer is
+    viewed (no copy) as ``[pages, page, Hkv, D]`` (``kv_layout="NHD"``), the block table is every ``page``-th entry of
+    the request's ``req_to_token`` row divided by the page size."""
+
+    def __init__(self, req_to_token: torch.Tensor, req_pool_indices: torch.Tensor, seq_lens: torch.Tensor, page_size: int):
+        from . import fi_env
+        fi_env.patch_jit()
+        import flashinfer.decode as fd
+        self.fn = fd.trtllm_batch_decode_with_kv_cache
+        self.page = int(page_size)
+        self.seq_lens = seq_lens.to(torch.int32).contiguous()
+        self.max_seq_len = int(seq_lens.max().item())
+        npages = (self.max_seq_len + self.page - 1) // self.page
+        rows = req_to_token[req_pool_indices.long()]
+        self.block_tables = (rows[:, : npages * self.page : self.page] // self.page).to(torch.int32).contiguous()
+        self.workspace = torch.zeros(128 << 20, dtype=torch.uint8, device=req_to_token.device)
+
+    def paged_view(self, buf: torch.Tensor) -> torch.Tensor:
+        rows, hkv, d = buf.shape
+        assert rows % self.page == 0 and buf.is_contiguous()
+        return buf.view(rows // self.page, self.page, hkv, d)
+
+    def __call__(self, q3: torch.Tensor, k_buf: torch.Tensor, v_buf: torch.Tensor, sm_scale: float) -> torch.Tensor:
+        return self.fn(q3, (self.paged_view(k_buf), self.paged_view(v_buf)), self.workspace, self.block_tables,
+                       self.seq_lens, self.max_seq_len, bmm1_scale=float(sm_scale), bmm2_scale=1.0, kv_layout="NHD",
+                       backend="trtllm-gen")
+
+
 def time_cuda(fn, iters: int, warmup: int = 3):
     """Mean seconds per call of ``fn(i)``, CUDA events on the current stream."""
     for i in range(warmup):

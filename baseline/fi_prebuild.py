@@ -42,6 +42,10 @@ def main() -> int:
         for kv in (f16, fp8):
             jobs.append(("prefill", get_batch_prefill_module, ("fa2", f16, kv, f16, i32, hd, hd, none, False, False, False)))
     jobs.append(("cascade", get_cascade_module, ()))
+    # the trtllm-gen FMHA launcher (its kernels are prebuilt cubins from flashinfer-cubin): compile only -- loading the
+    # shared object needs libcuda, which the build container does not have
+    from flashinfer.decode import gen_trtllm_gen_fmha_module
+    jobs.append(("trtllm-gen fmha", lambda: gen_trtllm_gen_fmha_module().build(False), ()))
     t0 = time.time()
     for name, fn, args in jobs:
         t = time.time()

@@ -496,6 +496,23 @@ def decode_comparators(st, q3, iters: int):
     else:
         out["triton_note"] = ("the reference's Triton backend has no fp8 scale semantics (SURVEY section 0 fact 4); "
                               "its bf16 figure is on the bf16 twin of this shape")
+    page = int(getattr(pool, "page_size", 1))
+    if page >= 16 and not fp8 and not st["fused_kv"]:
+        # SURVEY 8d stretch comparator: FlashInfer's trtllm-gen decode (NVIDIA's Blackwell-native FMHA cubins) on the
+        # same paged pool bytes -- not a path of the reference engine (page size 1), the best library kernel there is
+        try:
+            tg = C.TrtllmGenDecode(runner.req_to_token_pool.req_to_token, fb.req_pool_indices, fb.seq_lens, page)
+            theirs_o = [None]
+
+            def trt(i):
+                theirs_o[0] = tg(q3, pool.k_buffer[i % L], pool.v_buffer[i % L], sm_scale)
+
+            out["trtllm_gen_us"] = C.time_cuda(trt, iters) * 1e6
+            out["trtllm_gen_max_abs_vs_ours"] = (ours_last - theirs_o[0].reshape(B, -1).float()).abs().max().item()
+            out["speedup_vs_trtllm_gen"] = out["trtllm_gen_us"] / out["ours_attn_us"]
+            del tg
+        except Exception as e:  # noqa: BLE001
+            out["trtllm_gen_error"] = repr(e)[:300]
     if "flashinfer_us" in out:
         out["speedup_vs_flashinfer"] = out["flashinfer_us"] / out["ours_attn_us"]
     if "triton_us" in out:
@@ -1253,7 +1270,10 @@ def main():
             # C4 in both slot orders SURVEY 8d asks for: random-permuted (worst case) and contiguous runs (what an
             # unfragmented allocator hands out: prefix tiles then arrive by TMA like the new tokens do)
             plan += [("C5", {"shard": 8}), ("C2", {"shard": 8}), ("C3B", {"shard": 8}), ("C4", {}),
-                     ("C4", {"index_mode": "contiguous"})]
+                     ("C4", {"index_mode": "contiguous"}),
+                     # the headline shape over 64-token pages: whole tiles by TMA, and FlashInfer's trtllm-gen decode
+                     # (which needs pages) as a comparator on the same bytes
+                     ("C3B", {"page_size": 64})]
         for name, over in plan:
             a2 = copy.copy(args)
             a2.workload = name
@@ -1270,7 +1290,7 @@ def main():
                 else:
                     if wl.hkv_total % (world * a2.shard):
                         continue
-                    cmp_here = want_cmp and a2.shard == 1 and name in ("C2", "C3U")
+                    cmp_here = want_cmp and a2.shard == 1 and (name in ("C2", "C3U") or a2.page_size > 1)
                     rr = measure_decode(a2, rank, world, local_rank, dist, 64, 16, want_e2e=(a2.shard == 1),
                                         want_parity=not args.no_parity, want_comparators=cmp_here,
                                         roofline_launches=64)

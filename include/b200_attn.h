@@ -268,6 +268,13 @@ int b200_debug_gather(const void* buf, int64_t stride_t_bytes, int32_t row_bytes
  * 0 row gather only, 1 TMA (one box per K / V tile) for every tile whose slots are consecutive, row gather for the rest. */
 int b200_debug_last_tma_mode(void);
 
+/* Test hook: the split-KV kernel hands 7/8 of a launch's KV tiles to its CTAs as equal static ranges and lets them claim
+ * the rest in small chunks (one atomicAdd each) once a CTA's share reaches `tiles` tiles -- by default only launches of
+ * ~360 us and more whose slots the plan finds handed out as runs, where the per-SM bandwidth spread costs more than the
+ * chunk switches and the extra partials.  Tests lower the threshold to
+ * run that schedule on small batches; <= 0 restores the default.  Returns the previous value; affects later plans. */
+int b200_debug_set_dyn_min_base(int32_t tiles);
+
 /* Test hook (synchronises the device): KV tiles the decode kernels fetched by TMA box copies on the current device
  * since the last call with reset != 0 (-1 on a CUDA error).  b200_debug_last_tma_mode() says the TMA-capable kernel
  * was launched; this says how often its TMA branch was actually taken. */

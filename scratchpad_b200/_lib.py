@@ -38,6 +38,7 @@ EXPORTS = (
     "b200_kv_store",
     "b200_rope_kv_store",
     "b200_debug_last_tma_mode",
+    "b200_debug_set_dyn_min_base",
     "b200_debug_tma_tiles",
     "b200_debug_extend_tma_tiles",
     "b200_debug_check_paged",
@@ -177,6 +178,7 @@ def load() -> C.CDLL:
     lib.b200_debug_decode_naive.argtypes = [C.POINTER(DecodeParams), vp, vp, i32, vp]
     for name in EXPORTS[3:]:
         getattr(lib, name).restype = C.c_int
+    lib.b200_debug_set_dyn_min_base.argtypes = [i32]
     lib.b200_debug_tma_tiles.restype = C.c_int64
     lib.b200_debug_tma_tiles.argtypes = [i32]
     lib.b200_debug_extend_tma_tiles.restype = C.c_int64

@@ -45,7 +45,17 @@
 
 namespace b200 {
 
-constexpr int kStages = 3;
+// Ring depth and CTAs per SM of the split-KV kernels.  3 stages of 32 KiB x 2 CTAs per SM is the shipped point; deeper
+// rings with one CTA per SM (-DB200_DEC_STAGES=5..7 -DB200_DEC_MINBLOCKS=1: up to 192 KiB in flight per SM) are a build
+// option for A/B runs
+#ifndef B200_DEC_STAGES
+#define B200_DEC_STAGES 3
+#endif
+#ifndef B200_DEC_MINBLOCKS
+#define B200_DEC_MINBLOCKS 2
+#endif
+constexpr int kStages = B200_DEC_STAGES;
+constexpr int kMinBlocks = B200_DEC_MINBLOCKS;
 // Partials per (cta, request): the token sub-slices of a tile are combined inside the CTA, so one.  The two build
 // switches below exist for A/B measurements of exactly these two design decisions (tools/gpu_ab_lib.sh):
 //   -DB200_NO_CTA_REDUCE  every sub-slice flushes its own partial (round-1 behaviour)
@@ -68,8 +78,58 @@ constexpr bool cta_reduce_fits(int nsub, int vh, int d, int stage_bytes) {
 }
 constexpr int kPlanMagic = 0x62323030;  // "b200"
 constexpr int kHdrInts = 16;
-// header words: 0 total tiles, 1 tiles per CTA, 2 CTAs used, 3 bs, 4 tile tokens, 5 grid, 6 magic,
-// 7 / 8: kHdrShared / kHdrCasTiles (common.cuh)
+// header words: 0 total tiles, 1 tiles per static chunk (= per CTA when nothing is dynamic), 2 chunks, 3 bs, 4 tile
+// tokens, 5 grid, 6 magic, 7 / 8: kHdrShared / kHdrCasTiles (common.cuh), 9 tiles per dynamic chunk, 10 first dynamic tile
+//
+// Tile schedule.  The batch's KV tiles are one sequence cut into CHUNKS of consecutive tiles; a partial (O, lse) is
+// flushed per (chunk, request), slot chunk + request -- unique along the monotone staircase, no atomics.  Chunk x < grid
+// is CTA x's own (no claim); when a CTA's share is long enough (>= kDynMinBase tiles, ~360 us of streaming) AND the plan
+// finds the slots of most requests handed out as runs (whole tiles by TMA), only 7/8 of
+// the tiles are handed out that way and the last eighth is cut into chunks of 1/32 share which CTAs CLAIM as they run
+// dry (one atomicAdd per chunk and head group).  Why: with equal static ranges the CTAs of one launch finish up to 8 %
+// apart -- per-SM bandwidth differs, not the work (tools/dec_trace.py: C3B over 64-token pages, loop done at 545 .. 623
+// us, mean 575) -- and the kernel ends with its slowest CTA.  Chunk boundaries are closed-form (sched_*), so the merge
+// finds a request's partials without a table.
+constexpr int kDynMinBase = 256;     // tiles per CTA below which everything stays static (a chunk switch costs ~3 us;
+                                     // measured: C3B, 443 tiles per CTA, gains 2-3 %; C3U, 222, loses 3 % to the merge)
+constexpr int kDynChunksPerCta = 4;  // dynamic chunks per CTA on average: (1/8 share) / (1/32 share)
+constexpr int kMaxHeadGroups = 64;   // claim counters: one per blockIdx.y
+#ifdef B200_STATIC_TILES
+constexpr bool kDynamicTail = false;  // A/B switch: equal static ranges only (round 1 / early round 2)
+#else
+constexpr bool kDynamicTail = true;
+#endif
+__host__ __device__ inline int max_chunks(int grid) { return grid * (1 + kDynChunksPerCta) + 1; }
+struct Sched {
+  int total, grid, s_tiles, d_tiles, dyn0, nch;
+};
+__host__ __device__ inline Sched make_sched(int total, int grid, int dyn_min_base) {
+  Sched sc;
+  sc.total = total;
+  sc.grid = grid;
+  int base = (total + grid - 1) / grid;
+  if (base < 1) base = 1;
+  sc.s_tiles = base;
+  sc.d_tiles = 1;
+  if (kDynamicTail && base >= dyn_min_base && base >= 8) {
+    sc.s_tiles = base - base / 8;
+    sc.d_tiles = (base + 31) / 32;  // ceil: at most 4 * grid dynamic chunks (+1)
+  }
+  sc.dyn0 = grid * sc.s_tiles;
+  if (sc.dyn0 >= total) {
+    sc.dyn0 = total;
+    sc.nch = (total + sc.s_tiles - 1) / sc.s_tiles;
+  } else {
+    sc.nch = grid + (total - sc.dyn0 + sc.d_tiles - 1) / sc.d_tiles;
+  }
+  return sc;
+}
+__device__ __forceinline__ int sched_chunk_begin(int c, int grid, int s_tiles, int d_tiles) {
+  return c < grid ? c * s_tiles : grid * s_tiles + (c - grid) * d_tiles;
+}
+__device__ __forceinline__ int sched_chunk_of(int t, int dyn0, int grid, int s_tiles, int d_tiles) {
+  return t < dyn0 ? t / s_tiles : grid + (t - dyn0) / d_tiles;
+}
 constexpr int kExtraCasTiles = 4;    // row tiles beyond ceil(bs / requests-per-tile): room for that many more prefix groups
 constexpr int kMaxGroupBs = 1024;    // prefix groups are found by one CTA; larger batches run without the cascade
 constexpr int kMaxCasSplits = 8;     // KV splits of the shared-prefix leg (workspace is sized for this many)
@@ -78,7 +138,7 @@ constexpr int kMinShared = 1024;     // shorter common prefixes stay on the spli
 constexpr int kMinCasRows = 64;      // bs * g below this: the dense leg would be mostly padding
 
 struct WsLayout {
-  size_t tile_off, seq_len, req_idx, cta_b0, part_lse, part_o, cas_lse, cas_o, total;
+  size_t tile_off, seq_len, req_idx, cta_b0, claim, part_lse, part_o, cas_lse, cas_o, total;
   // prefix groups (cascade): per request / per sorted position / per row tile of the shared-prefix leg
   size_t shared32, perm, grp_of, grp_min, grp_size, grp_fin, ct_first, ct_cnt, ct_leader, ct_shared;
 };
@@ -94,9 +154,11 @@ static WsLayout ws_layout(int max_bs, int grid, int nsub, int hq, int dv) {
   off = align_up(off + (size_t)max_bs * sizeof(int), 16);
   L.req_idx = off;
   off = align_up(off + (size_t)max_bs * sizeof(int), 16);
-  L.cta_b0 = off;  // request holding the first tile of each CTA
-  off = align_up(off + (size_t)grid * sizeof(int), 256);
-  size_t nparts = (size_t)(grid + max_bs) * nsub * hq;
+  L.cta_b0 = off;  // request holding the first tile of each chunk
+  off = align_up(off + (size_t)max_chunks(grid) * sizeof(int), 256);
+  L.claim = off;   // claim counters of the dynamic chunks, one per head group (zeroed by the plan and by every merge)
+  off = align_up(off + (size_t)kMaxHeadGroups * sizeof(int), 256);
+  size_t nparts = (size_t)(max_chunks(grid) + max_bs) * nsub * hq;
   L.part_lse = off;
   off = align_up(off + nparts * sizeof(float), 256);
   L.part_o = off;
@@ -229,16 +291,18 @@ struct CasPlan {  // prefix-group tables of the cascade (null perm = cascade off
 
 __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* __restrict__ tile_off,
                                                     int* __restrict__ seq32, int* __restrict__ req32,
-                                                    int* __restrict__ cta_b0,
+                                                    int* __restrict__ cta_b0, int* __restrict__ claim,
                                                     const void* __restrict__ req, const void* __restrict__ seq,
-                                                    int idx64, int bs, int tile_tokens, int grid, const CasPlan cp) {
+                                                    int idx64, int bs, int tile_tokens, int grid, int dyn_min_base,
+                                                    const int32_t* __restrict__ r2t, int64_t r2t_stride, const CasPlan cp) {
   __shared__ int warp_sums[32];
   __shared__ int s_running;
+  __shared__ int s_runs, s_probed;  // requests whose first tile's slots are / were probed for being consecutive
   pdl_wait();
   pdl_launch_dependents();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ int s_cas_tiles, s_max_shared;
-  if (tid == 0) s_running = s_cas_tiles = s_max_shared = 0;
+  if (tid == 0) s_running = s_cas_tiles = s_max_shared = s_runs = s_probed = 0;
   __syncthreads();
   // Prefix groups (group_kernel / lcp_kernel ran before us): the part of a group's common prefix that the dense
   // tcgen05 leg takes over; the split-KV tiles of its requests start behind it.
@@ -284,6 +348,18 @@ __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* 
         cp.shared32[i] = shared;
       }
       n = static_cast<int>((s - shared + tile_tokens - 1) / tile_tokens);
+      // Does the allocator hand out runs (a paged pool, or an unfragmented token-granular one)?  Probe the first 16
+      // slots behind the shared prefix of every request that has them.  The dynamically claimed tail (make_sched) is
+      // only worth its chunk switches and extra partials where whole tiles arrive by TMA: there the CTAs of a launch
+      // finish up to 8 % apart, over scattered slots less than 4 %.
+      if (r2t != nullptr && s - shared >= 16) {
+        const int32_t* row = r2t + static_cast<int64_t>(req32[i]) * r2t_stride + shared;
+        bool run = true;
+        const int s0 = __ldg(row);
+        for (int k = 1; k < 16; ++k) run = run && __ldg(row + k) == s0 + k;
+        atomicAdd(&s_probed, 1);
+        if (run) atomicAdd(&s_runs, 1);
+      }
     }
     int x = n;
 #pragma unroll
@@ -311,13 +387,12 @@ __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* 
     __syncthreads();
   }
   {
-    // first request of every CTA's tile range: last b with tile_off[b] <= c * tpc (removes a
+    // first request of every chunk's tile range: last b with tile_off[b] <= first tile of the chunk (removes a
     // dependent-load binary search from the decode kernel's prologue)
-    const int total = s_running;
-    int tpc = (total + grid - 1) / grid;
-    if (tpc < 1) tpc = 1;
-    for (int c = tid; c < grid; c += 1024) {
-      const int gt = c * tpc;
+    const Sched sc = make_sched(s_running, grid, (s_probed > 0 && 2 * s_runs >= s_probed) ? dyn_min_base : (1 << 30));
+    if (tid < kMaxHeadGroups) claim[tid] = 0;
+    for (int c = tid; c < sc.nch; c += 1024) {
+      const int gt = sched_chunk_begin(c, grid, sc.s_tiles, sc.d_tiles);
       int lo = 0, hi = bs;
       while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -329,12 +404,13 @@ __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* 
   }
   if (tid == 0) {
     const int total = s_running;
+    const Sched sc = make_sched(total, grid, (s_probed > 0 && 2 * s_runs >= s_probed) ? dyn_min_base : (1 << 30));
     tile_off[bs] = total;
-    int tpc = (total + grid - 1) / grid;
-    if (tpc < 1) tpc = 1;
     hdr[0] = total;
-    hdr[1] = tpc;
-    hdr[2] = (total + tpc - 1) / tpc;
+    hdr[1] = sc.s_tiles;
+    hdr[2] = sc.nch;
+    hdr[9] = sc.d_tiles;
+    hdr[10] = sc.dyn0;
     hdr[3] = bs;
     hdr[4] = tile_tokens;
     hdr[5] = grid;
@@ -360,6 +436,7 @@ struct DecodeArgs {
   const int* seq_len;
   const int* req_idx;
   const int* cta_b0;
+  int* claim;  // per head group: next dynamic chunk
   const int* shared32;  // per request: tokens the shared-prefix leg handles (null = cascade off)
   float* part_o;
   float* part_lse;
@@ -447,7 +524,11 @@ struct DecodeCfg {
   static constexpr int HALVES = SEG / ROWB;            // 256-byte segments are kept as two 128-byte column halves
   // paged: + kStages mbarriers behind the ring.  No alignment slack (the dynamic segment is declared 1024-aligned):
   // two CTAs of 98,368 B (+1 KiB each that the system reserves) stay inside the 196 KiB shared-memory carve-out
-  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + (PAGED ? 64 : 0);
+  // + 64 bytes behind the ring: the paged kernels' kStages mbarriers, and (every kernel) the word the claimed chunk id
+  // is broadcast through
+  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 64;
+  static constexpr int NEXT_CHUNK_OFF = kStages * STAGE_BYTES + 56;
+  static_assert(kStages <= 7, "the mbarriers and the chunk word share 64 bytes");
   // the token sub-slices of a tile are combined inside the CTA where the scratch fits a ring stage (everywhere but the
   // fp8 two-q-tile variants): then ONE partial per (cta, request), else one per sub-slice
   static constexpr bool REDUCE = cta_reduce_fits(NSUB, VH, D, STAGE_BYTES);
@@ -535,21 +616,32 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
   pdl_launch_dependents();  // let the merge grid get scheduled behind us; it waits for our completion
   DEC_TRACE(1);
 
-  const int total = __ldg(a.hdr + 0), tpc = __ldg(a.hdr + 1);
+  // (the schedule words are re-read from the header at every chunk switch -- asm volatile, so that the compiler does not
+  // keep five more values alive across the tile loop; the fp8 kernels run at their 128-register cap)
+  auto hdr_word = [&](int i) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(a.hdr + i));
+    return v;
+  };
+  const int grid = gridDim.x;
   // Belt and braces behind the host-side B200_ERR_NOT_PLANNED check (a graph replayed without its plan refresh, a
   // workspace overwritten by someone else): without a plan for exactly this batch there is nothing safe to read.
   // The merge kernel makes the same test and writes NaN, so the failure is visible in the output.
-  if (__ldg(a.hdr + 6) != kPlanMagic || __ldg(a.hdr + 3) != a.bs) return;
-  const int gt_begin = cta * tpc;
-  const int gt_end = min(gt_begin + tpc, total);
-  if (gt_begin >= gt_end) return;
-  const int lo = __ldg(a.cta_b0 + cta);
-  Cursor pc;  // producer cursor
-  pc.gt = gt_begin;
-  pc.gt_end = gt_end;
-  pc.b = lo;
-  cursor_load_req(pc, a);
-  Cursor cc = pc;  // consumer cursor
+  if (__ldg(a.hdr + 6) != kPlanMagic || __ldg(a.hdr + 3) != a.bs || __ldg(a.hdr + 5) != grid) return;
+  // chunk x < grid is CTA x's own; further chunks (the dynamic tail of a long launch) are claimed at the bottom
+  int chunk = cta;
+  if (chunk >= hdr_word(2)) return;
+  Cursor pc, cc;  // producer / consumer cursor over the current chunk's tiles
+  auto enter_chunk = [&](int c) {
+    const int total = hdr_word(0), s_tiles = hdr_word(1), d_tiles = hdr_word(9);
+    const int gt_begin = sched_chunk_begin(c, grid, s_tiles, d_tiles);
+    pc.gt = gt_begin;
+    pc.gt_end = min(gt_begin + (c < grid ? s_tiles : d_tiles), total);
+    pc.b = __ldg(a.cta_b0 + c);
+    cursor_load_req(pc, a);
+    cc = pc;
+  };
+  enter_chunk(chunk);
 
   // ---- producer: per-thread constants of the copy mapping -------------------
   const int p_tok = tid / CPT;  // token of pass 0; pass i adds i * TOK_PER_PASS
@@ -790,7 +882,7 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
     }
   };
 
-  // one partial per (cta, request): slot = cta + b is unique along the monotone staircase of (cta, request)
+  // one partial per (chunk, request): slot = chunk + b is unique along the monotone staircase of (chunk, request)
   // pairs.  (A fused "last CTA to arrive merges" variant was measured in round 1 and was slower -- 184 vs 169 us
   // at C2: the fence + atomic round trip + merge reads stall the copy pipeline at every request boundary -- so the
   // merge stays a separate, programmatically-dependent launch.)
@@ -848,7 +940,7 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
       l1 += __shfl_xor_sync(0xffffffffu, l1, x);
     }
     const float inv0 = l0 > 0.f ? vs / l0 : 0.f, inv1 = l1 > 0.f ? vs / l1 : 0.f;
-    const int64_t slot = C::REDUCE ? static_cast<int64_t>(cta + b) : static_cast<int64_t>(cta + b) * C::NSUB + w_sub;
+    const int64_t slot = C::REDUCE ? static_cast<int64_t>(chunk + b) : static_cast<int64_t>(chunk + b) * C::NSUB + w_sub;
     const int n0 = q0 + 2 * cid, n1 = n0 + 1;  // q-head index inside the group
     const int64_t pi0 = slot * a.hq + kvh * G + n0;
     const int64_t pi1 = pi0 + 1;
@@ -985,15 +1077,29 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
 #endif
   };  // pipeline
 
-  prefetch_slots(pc);
+  volatile int* next_chunk = reinterpret_cast<volatile int*>(smem + C::NEXT_CHUNK_OFF);
+  for (;;) {
+    prefetch_slots(pc);
+    if constexpr (PAGED) {
+      // consecutive slots among the valid tokens of this chunk's first tile?  (a single valid token says nothing)
+      const int nvalid0 = min(TN, pc.seq_len - (pc.gt - pc.b_begin) * TN);
+      if (!kTwoLoops || (nvalid0 >= 2 && slots_consecutive(nvalid0))) pipeline(std::true_type{});
+      else pipeline(std::false_type{});
+    } else {
+      pipeline(std::false_type{});
+    }
+    const int nch = hdr_word(2);
+    if (nch <= grid) break;  // nothing dynamic in this launch: one chunk per CTA
+    // claim the next chunk of the dynamic tail (one atomic per chunk and head group); the barrier also keeps the next
+    // chunk's first copies out of ring stages a slower warp is still reading
+    if (tid == 0) *next_chunk = grid + atomicAdd(a.claim + blockIdx.y, 1);
+    __syncthreads();
+    chunk = *next_chunk;
+    if (chunk >= nch) break;
+    enter_chunk(chunk);
+  }
   if constexpr (PAGED) {
-    // consecutive slots among the valid tokens of this CTA's first tile?  (a single valid token says nothing)
-    const int nvalid0 = min(TN, pc.seq_len - (pc.gt - pc.b_begin) * TN);
-    if (!kTwoLoops || (nvalid0 >= 2 && slots_consecutive(nvalid0))) pipeline(std::true_type{});
-    else pipeline(std::false_type{});
     if (tid == 0 && n_tma_tiles) atomicAdd(&g_tma_tiles, static_cast<unsigned long long>(n_tma_tiles));
-  } else {
-    pipeline(std::false_type{});
   }
   DEC_TRACE(4);
   cp_async_wait<0>();
@@ -1001,12 +1107,12 @@ __device__ __forceinline__ void decode_body(const DecodeArgs& a, const CUtensorM
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::NT, 2) decode_mma_kernel(const DecodeArgs a) {
+__global__ void __launch_bounds__(C::NT, kMinBlocks) decode_mma_kernel(const DecodeArgs a) {
   decode_body<C>(a, nullptr, nullptr);
 }
 // paged pools: the two tensor maps (K and V pool of this layer) ride in the kernel parameters
 template <class C>
-__global__ void __launch_bounds__(C::NT, 2) decode_paged_kernel(const __grid_constant__ DecodeArgs a,
+__global__ void __launch_bounds__(C::NT, kMinBlocks) decode_paged_kernel(const __grid_constant__ DecodeArgs a,
                                                                 const __grid_constant__ CUtensorMap tmk,
                                                                 const __grid_constant__ CUtensorMap tmv) {
   decode_body<C>(a, &tmk, &tmv);
@@ -1018,20 +1124,27 @@ __global__ void __launch_bounds__(C::NT, 2) decode_paged_kernel(const __grid_con
 // slots of the pair are consecutive ((c + b) * nsub + sub), still L2-resident.
 // ---------------------------------------------------------------------------
 template <int DV>
-__global__ void __launch_bounds__(256, 4) merge_kernel(const int* __restrict__ hdr, const int* __restrict__ tile_off,
+#ifdef B200_MERGE_DEEP  // A/B: twice the loads in flight per warp at 3 instead of 4 CTAs per SM
+#define B200_MERGE_MINBLOCKS 3
+#else
+#define B200_MERGE_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, B200_MERGE_MINBLOCKS) merge_kernel(const int* __restrict__ hdr, const int* __restrict__ tile_off,
                                                     const float* __restrict__ part_o,
                                                     const float* __restrict__ part_lse, uint16_t* __restrict__ o, int o_half,
                                                     int64_t o_st, int64_t o_sh, int bs, int hq, int nsub,
                                                     const float* __restrict__ cas_o, const float* __restrict__ cas_lse,
-                                                    int cas_splits, const int* __restrict__ shared32) {
+                                                    int cas_splits, const int* __restrict__ shared32, int* __restrict__ claim) {
   pdl_wait();
   pdl_launch_dependents();
+  // the split-KV grid has completed: its claim counters start the next launch (next layer, same plan) at zero
+  if (blockIdx.x == 0 && threadIdx.x < kMaxHeadGroups) claim[threadIdx.x] = 0;
   constexpr int VPL = DV / 32;  // floats per lane
   const int lane = threadIdx.x & 31;
   const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (pair >= bs * hq) return;
   const int b = pair / hq, h = pair % hq;
-  const int tpc = __ldg(hdr + 1);
+  const int s_tiles = __ldg(hdr + 1), d_tiles = __ldg(hdr + 9), dyn0 = __ldg(hdr + 10), grid = __ldg(hdr + 5);
   if (__ldg(hdr + 6) != kPlanMagic || __ldg(hdr + 3) != bs) {  // no plan for this batch in the workspace: poison o
     uint16_t* bad = o + static_cast<int64_t>(b) * o_st + static_cast<int64_t>(h) * o_sh + lane * (DV / 32);
 #pragma unroll
@@ -1049,7 +1162,7 @@ __global__ void __launch_bounds__(256, 4) merge_kernel(const int* __restrict__ h
   int64_t first = 0;
   int n = 0;
   if (t1 > t0) {
-    const int c0 = t0 / tpc, c1 = (t1 - 1) / tpc;
+    const int c0 = sched_chunk_of(t0, dyn0, grid, s_tiles, d_tiles), c1 = sched_chunk_of(t1 - 1, dyn0, grid, s_tiles, d_tiles);
     first = static_cast<int64_t>(c0 + b) * nsub;
     n = (c1 - c0 + 1) * nsub;
   }
@@ -1067,7 +1180,11 @@ __global__ void __launch_bounds__(256, 4) merge_kernel(const int* __restrict__ h
       // several partials per round trip: all loads of a group are issued before the first FMA consumes one (with one
       // warp per (request, head) and few warps per SM at small shards, a load-use chain per partial was the
       // whole kernel: 16-24 partials x L2 latency)
+#ifdef B200_MERGE_DEEP
+      constexpr int kGroup = 32 / VPL;        // 32 registers: the requests in a dynamically claimed tail have ~18 partials
+#else
       constexpr int kGroup = 32 / (VPL * 2);  // 16 registers of loads in flight: 8 partials (DV 64) or 4 (DV 128)
+#endif
       for (int j0 = 0; j0 < cnt; j0 += kGroup) {
         float vbuf[kGroup][VPL];
 #pragma unroll
@@ -1293,6 +1410,7 @@ static bool plan_matches(const PlanRecord& r) {
   return false;
 }
 
+static int g_dyn_min_base = kDynMinBase;  // b200_debug_set_dyn_min_base: tests force the dynamic tail onto small batches
 static int g_last_tma_mode = 0;  // test / bench introspection: 0 row gather only, 1 TMA for tiles of consecutive slots
 
 template <class C>
@@ -1393,12 +1511,13 @@ static int get_config(int max_bs, int hq, int hkv, int d, int dv, int kv_dtype, 
   out->q_tiles = kc.qt;
   out->tile_tokens = 16 * out->sub_splits;
   const int gy = hkv / kc.hpc;
+  if (gy > kMaxHeadGroups) return B200_ERR_UNSUPPORTED;  // one claim counter per head group
   // persistent grid: every resident CTA slot of the machine, shared by the head groups
   int gx = di.num_sms * occ / gy;
   if (gx < 1) gx = 1;
   out->grid_ctas = gx;
   out->stages = kStages;
-  out->smem_bytes = kStages * 2 * kc.hpc * out->tile_tokens * d * elt;
+  out->smem_bytes = kStages * 2 * kc.hpc * out->tile_tokens * d * elt + 64;
   out->num_sms = di.num_sms;
   out->workspace_bytes = ws_layout(max_bs, gx, out->partials_per_slot, hq, dv).total;
   return B200_OK;
@@ -1496,8 +1615,8 @@ int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs, co
   }
   plan_kernel<<<1, 1024, 0, st>>>(
       reinterpret_cast<int*>(ws), reinterpret_cast<int*>(ws + L.tile_off), reinterpret_cast<int*>(ws + L.seq_len),
-      reinterpret_cast<int*>(ws + L.req_idx), reinterpret_cast<int*>(ws + L.cta_b0), req_pool_indices, seq_lens, idx_dtype == B200_IDX_I64, bs,
-      cfg.tile_tokens, cfg.grid_ctas, cp);
+      reinterpret_cast<int*>(ws + L.req_idx), reinterpret_cast<int*>(ws + L.cta_b0), reinterpret_cast<int*>(ws + L.claim), req_pool_indices, seq_lens, idx_dtype == B200_IDX_I64, bs,
+      cfg.tile_tokens, cfg.grid_ctas, g_dyn_min_base, req_to_token, req_to_token_stride, cp);
   B200_CUDA_TRY(cudaGetLastError());
   PlanRecord rec;
   rec.ws = workspace; rec.bs = bs; rec.hq = hq; rec.hkv = hkv; rec.d = d; rec.kv_dtype = kv_dtype;
@@ -1548,6 +1667,7 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
   a.seq_len = reinterpret_cast<const int*>(ws + L.seq_len);
   a.req_idx = reinterpret_cast<const int*>(ws + L.req_idx);
   a.cta_b0 = reinterpret_cast<const int*>(ws + L.cta_b0);
+  a.claim = reinterpret_cast<int*>(ws + L.claim);
   a.part_lse = reinterpret_cast<float*>(ws + L.part_lse);
   a.part_o = reinterpret_cast<float*>(ws + L.part_o);
   a.hq = p->hq;
@@ -1615,11 +1735,11 @@ int b200_attn_decode(const b200_decode_params* p, b200_stream_t stream) {
     return launch_pdl(merge_kernel<64>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
                       static_cast<const float*>(a.part_lse), o, o_half, static_cast<int64_t>(p->o_stride_t),
                       static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
-                      static_cast<int>(cfg.partials_per_slot), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
+                      static_cast<int>(cfg.partials_per_slot), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32), a.claim);
   return launch_pdl(merge_kernel<128>, mgrid, dim3(256), 0, st, a.hdr, a.tile_off, static_cast<const float*>(a.part_o),
                     static_cast<const float*>(a.part_lse), o, o_half, static_cast<int64_t>(p->o_stride_t),
                     static_cast<int64_t>(p->o_stride_h), static_cast<int>(p->bs), static_cast<int>(p->hq),
-                    static_cast<int>(cfg.partials_per_slot), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32));
+                    static_cast<int>(cfg.partials_per_slot), static_cast<const float*>(cas_o), static_cast<const float*>(cas_lse), cas_splits, reinterpret_cast<const int*>(ws + L.shared32), a.claim);
 }
 
 #ifdef B200_DEC_TRACE
@@ -1629,6 +1749,14 @@ int b200_debug_dec_trace_read(unsigned long long* host_dst) {
 #endif
 
 int b200_debug_last_tma_mode(void) { return g_last_tma_mode; }
+
+// Test hook: tiles per CTA from which b200_attn_plan cuts the last eighth of the tiles into dynamically claimed chunks
+// (<= 0 restores the default, kDynMinBase); returns the previous value.  Plans made afterwards use it.
+int b200_debug_set_dyn_min_base(int32_t tiles) {
+  const int prev = g_dyn_min_base;
+  g_dyn_min_base = tiles > 0 ? tiles : kDynMinBase;
+  return prev;
+}
 
 // Test hook (synchronises): number of KV tiles the decode kernels fetched by TMA box copies on the current device since
 // the last call with reset != 0; proves that the TMA branch is taken, not merely that the TMA-capable kernel ran.

@@ -96,6 +96,31 @@ def test_decode_matches_reference_triton_kernel(hq, hkv, d, lens, cap):
     G.assert_close(ours, theirs.float().cpu(), G.BF16_ABS, G.BF16_REL, what="ours vs in-tree Triton decode")
 
 
+@needs_fi
+@pytest.mark.parametrize("page_size", [16, 64])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_paged_decode_matches_flashinfer_trtllm_gen(page_size, dtype):
+    """SURVEY 8d stretch comparator: FlashInfer's trtllm-gen decode (NVIDIA's Blackwell-native FMHA cubins) on the same
+    paged pool bytes, the [P + page, Hkv, D] buffer viewed as [pages, page, Hkv, D] and the block table cut out of
+    req_to_token (baseline/comparators.py TrtllmGenDecode).  Skipped when the cubins / launcher cannot be loaded."""
+    from baseline import comparators as C
+    hq, hkv, d, lens = 32, 8, 128, [4100, 129, 64, 2, 999, 31, 2048]
+    c = G.random_decode_case(hq, hkv, d, lens, seed=23, kv_dtype=dtype, page_size=page_size)
+    ours, backend, runner, fb, layer = G.run_decode_case(
+        c["q"], c["k_buf"], c["v_buf"], c["req_to_token"], c["req_pool_indices"], c["seq_lens"], c["sm_scale"], 0.0,
+        dtype, page_size=page_size)
+    pool = runner.token_to_kv_pool
+    try:
+        tg = C.TrtllmGenDecode(runner.req_to_token_pool.req_to_token, fb.req_pool_indices, fb.seq_lens, page_size)
+        theirs = tg(c["q"].cuda(), pool.k_buffer[0], pool.v_buffer[0], c["sm_scale"])
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001  (no cubins, no launcher, unsupported page size: not this repo's code)
+        pytest.skip(f"trtllm-gen decode unavailable: {e!r}"[:200])
+    tol = (G.BF16_ABS, G.BF16_REL) if dtype == torch.bfloat16 else (G.F16_ABS, G.F16_REL)
+    tol = (tol[0], max(tol[1], G.BF16_REL))  # their P is rounded to the 16-bit type as ours is; compare at the bf16 bound
+    G.assert_close(ours, theirs.float().cpu(), *tol, what=f"ours vs trtllm-gen decode, page {page_size}, {dtype}")
+
+
 EXTEND_SHAPES = [
     # hq, hkv, d, prefix_lens, extend_lens
     (32, 8, 128, [300, 0, 129, 1000], [130, 257, 1, 64]),

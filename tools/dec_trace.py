@@ -26,6 +26,9 @@ names = ["enter", "after pdl_wait", "prologue issued + Q", "first tile landed", 
 print(f"{len(b)} CTAs; ns from the first CTA's entry: min / median / max")
 for i, n in enumerate(names):
     print(f"  {n:22s} {b[:, i].min():8d} {int(np.median(b[:, i])):8d} {b[:, i].max():8d}")
+ends = np.sort(b[:, 4])
+print("loop-done percentiles (ns): " + "  ".join(f"p{q}={int(np.percentile(ends, q))}" for q in (1, 10, 25, 50, 75, 90, 99, 100)))
+print(f"mean loop-done {ends.mean():.0f} ns; if every CTA finished at the mean the kernel would end {ends.max() - ends.mean():.0f} ns earlier")
 d = b[:, 1:] - b[:, :-1]
 print("per-CTA phase lengths (ns): median / max")
 for i, n in enumerate(["pdl_wait", "metadata + prologue issue + Q load", "wait for first tile", "streaming loop", "drain"]):

@@ -37,6 +37,7 @@
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include <cstring>
+#include <cstdio>
 #include <mutex>
 #include <type_traits>
 
@@ -103,7 +104,12 @@ __host__ __device__ inline int max_chunks(int grid) { return grid * (1 + kDynChu
 struct Sched {
   int total, grid, s_tiles, d_tiles, dyn0, nch;
 };
-__host__ __device__ inline Sched make_sched(int total, int grid, int dyn_min_base) {
+// dyn: {tiles per CTA from which the tail is dynamic, denominator of the dynamic fraction, denominator of the chunk size}
+struct DynParams {
+  int min_base, frac_den, chunk_den;
+};
+__host__ __device__ inline Sched make_sched(int total, int grid, DynParams dyn) {
+  const int dyn_min_base = dyn.min_base;
   Sched sc;
   sc.total = total;
   sc.grid = grid;
@@ -112,8 +118,8 @@ __host__ __device__ inline Sched make_sched(int total, int grid, int dyn_min_bas
   sc.s_tiles = base;
   sc.d_tiles = 1;
   if (kDynamicTail && base >= dyn_min_base && base >= 8) {
-    sc.s_tiles = base - base / 8;
-    sc.d_tiles = (base + 31) / 32;  // ceil: at most 4 * grid dynamic chunks (+1)
+    sc.s_tiles = base - base / dyn.frac_den;
+    sc.d_tiles = (base + dyn.chunk_den - 1) / dyn.chunk_den;  // ceil: at most chunk_den / frac_den (<= 4) * grid dynamic chunks (+1)
   }
   sc.dyn0 = grid * sc.s_tiles;
   if (sc.dyn0 >= total) {
@@ -123,6 +129,11 @@ __host__ __device__ inline Sched make_sched(int total, int grid, int dyn_min_bas
     sc.nch = grid + (total - sc.dyn0 + sc.d_tiles - 1) / sc.d_tiles;
   }
   return sc;
+}
+// the dynamic tail only where the plan's probe found most requests' slots handed out as runs
+__device__ __forceinline__ DynParams runs_dyn(DynParams dyn, int probed, int runs) {
+  if (!(probed > 0 && 2 * runs >= probed)) dyn.min_base = 1 << 30;
+  return dyn;
 }
 __device__ __forceinline__ int sched_chunk_begin(int c, int grid, int s_tiles, int d_tiles) {
   return c < grid ? c * s_tiles : grid * s_tiles + (c - grid) * d_tiles;
@@ -293,7 +304,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* 
                                                     int* __restrict__ seq32, int* __restrict__ req32,
                                                     int* __restrict__ cta_b0, int* __restrict__ claim,
                                                     const void* __restrict__ req, const void* __restrict__ seq,
-                                                    int idx64, int bs, int tile_tokens, int grid, int dyn_min_base,
+                                                    int idx64, int bs, int tile_tokens, int grid, DynParams dyn,
                                                     const int32_t* __restrict__ r2t, int64_t r2t_stride, const CasPlan cp) {
   __shared__ int warp_sums[32];
   __shared__ int s_running;
@@ -389,7 +400,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* 
   {
     // first request of every chunk's tile range: last b with tile_off[b] <= first tile of the chunk (removes a
     // dependent-load binary search from the decode kernel's prologue)
-    const Sched sc = make_sched(s_running, grid, (s_probed > 0 && 2 * s_runs >= s_probed) ? dyn_min_base : (1 << 30));
+    const Sched sc = make_sched(s_running, grid, runs_dyn(dyn, s_probed, s_runs));
     if (tid < kMaxHeadGroups) claim[tid] = 0;
     for (int c = tid; c < sc.nch; c += 1024) {
       const int gt = sched_chunk_begin(c, grid, sc.s_tiles, sc.d_tiles);
@@ -404,7 +415,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(int* __restrict__ hdr, int* 
   }
   if (tid == 0) {
     const int total = s_running;
-    const Sched sc = make_sched(total, grid, (s_probed > 0 && 2 * s_runs >= s_probed) ? dyn_min_base : (1 << 30));
+    const Sched sc = make_sched(total, grid, runs_dyn(dyn, s_probed, s_runs));
     tile_off[bs] = total;
     hdr[0] = total;
     hdr[1] = sc.s_tiles;
@@ -1411,6 +1422,25 @@ static bool plan_matches(const PlanRecord& r) {
 }
 
 static int g_dyn_min_base = kDynMinBase;  // b200_debug_set_dyn_min_base: tests force the dynamic tail onto small batches
+// B200_SCHED="frac_den,chunk_den" (measurement switch): the last 1/frac_den of the tiles in chunks of 1/chunk_den share;
+// chunk_den <= 4 * frac_den keeps the chunk count inside the workspace (max_chunks)
+static DynParams dyn_params() {
+  static int frac_den = 8, chunk_den = 32;
+  static bool parsed = false, off = false;  // "0,0": equal static ranges only
+  if (!parsed) {
+    parsed = true;
+    if (const char* e = getenv("B200_SCHED")) {
+      int a = 0, b = 0;
+      if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 2 && b >= a && b <= kDynChunksPerCta * a) {
+        frac_den = a;
+        chunk_den = b;
+      } else if (a == 0) {
+        off = true;
+      }
+    }
+  }
+  return DynParams{off ? (1 << 30) : g_dyn_min_base, frac_den, chunk_den};
+}
 static int g_last_tma_mode = 0;  // test / bench introspection: 0 row gather only, 1 TMA for tiles of consecutive slots
 
 template <class C>
@@ -1616,7 +1646,7 @@ int b200_attn_plan(void* workspace, uint64_t workspace_bytes, int32_t max_bs, co
   plan_kernel<<<1, 1024, 0, st>>>(
       reinterpret_cast<int*>(ws), reinterpret_cast<int*>(ws + L.tile_off), reinterpret_cast<int*>(ws + L.seq_len),
       reinterpret_cast<int*>(ws + L.req_idx), reinterpret_cast<int*>(ws + L.cta_b0), reinterpret_cast<int*>(ws + L.claim), req_pool_indices, seq_lens, idx_dtype == B200_IDX_I64, bs,
-      cfg.tile_tokens, cfg.grid_ctas, g_dyn_min_base, req_to_token, req_to_token_stride, cp);
+      cfg.tile_tokens, cfg.grid_ctas, dyn_params(), req_to_token, req_to_token_stride, cp);
   B200_CUDA_TRY(cudaGetLastError());
   PlanRecord rec;
   rec.ws = workspace; rec.bs = bs; rec.hq = hq; rec.hkv = hkv; rec.d = d; rec.kv_dtype = kv_dtype;

@@ -38,7 +38,9 @@ for f, c in sorted(per.items(), key=lambda kv: demangle(kv[0])):
     for op, n in c.items():
         if not KEY.match(op):
             continue
-        if op.startswith(("UTCHMMA", "UTCBAR", "UTMALDG", "LDGSTS", "HMMA", "SYNCS", "F2FP")):
+        if op.startswith("HMMA"):  # HMMA.16816.F32 = f16 operands (fp8 pools, fp16 models), .F32.BF16 = bf16 operands
+            key = ".".join(op.split(".")[:4])
+        elif op.startswith(("UTCHMMA", "UTCBAR", "UTMALDG", "LDGSTS", "SYNCS", "F2FP")):
             key = ".".join(op.split(".")[:3])
         elif op.startswith("MUFU"):
             key = "MUFU.EX2"
@@ -48,7 +50,7 @@ for f, c in sorted(per.items(), key=lambda kv: demangle(kv[0])):
         tot[key] += n
     lines.append(f"{name}\n    instructions {sum(c.values())}: " + ", ".join(f"{k} {v}" for k, v in sorted(sel.items())))
 hdr = [
-    "# SASS opcode histogram of scratchpad_b200/csrc/libb200attn.so (sm_100a), round 2",
+    "# SASS opcode histogram of scratchpad_b200/csrc/libb200attn.so (sm_100a), round 2 (final code: bf16 and fp16 model dtypes)",
     "# how: cuobjdump -sass libb200attn.so, opcodes counted per kernel; regenerate with `python tools/sass_hist.py`",
     "# what to look for: UTCHMMA = tcgen05.mma (UTCHMMA.2CTA = cta_group::2), LDTM/STTM = tcgen05.ld/st (TMEM), UTCBAR = tcgen05.commit,",
     "#   UTMALDG = cp.async.bulk.tensor (TMA), LDGSTS = cp.async 16-byte copies, HMMA.16816 = mma.sync m16n8k16, MOVM = movmatrix,",

@@ -275,6 +275,12 @@ int b200_debug_last_tma_mode(void);
  * run that schedule on small batches; <= 0 restores the default.  Returns the previous value; affects later plans. */
 int b200_debug_set_dyn_min_base(int32_t tiles);
 
+/* Test hook (host only): the tile schedule b200_attn_plan writes for `total` KV tiles on a persistent grid of `grid` CTAs
+ * when the slots are runs (min_base <= 0: the library's threshold).  out[8] = tiles per static chunk, tiles per dynamic
+ * chunk, first dynamically claimed tile, number of chunks, chunk capacity of the workspace, the chunk owning tile
+ * `probe`, the first tile of that chunk and of the next one (-1 when probe is out of range). */
+int b200_debug_sched(int32_t total, int32_t grid, int32_t min_base, int32_t probe, int32_t* out);
+
 /* Test hook (synchronises the device): KV tiles the decode kernels fetched by TMA box copies on the current device
  * since the last call with reset != 0 (-1 on a CUDA error).  b200_debug_last_tma_mode() says the TMA-capable kernel
  * was launched; this says how often its TMA branch was actually taken. */

@@ -39,6 +39,7 @@ EXPORTS = (
     "b200_rope_kv_store",
     "b200_debug_last_tma_mode",
     "b200_debug_set_dyn_min_base",
+    "b200_debug_sched",
     "b200_debug_tma_tiles",
     "b200_debug_extend_tma_tiles",
     "b200_debug_check_paged",
@@ -179,6 +180,7 @@ def load() -> C.CDLL:
     for name in EXPORTS[3:]:
         getattr(lib, name).restype = C.c_int
     lib.b200_debug_set_dyn_min_base.argtypes = [i32]
+    lib.b200_debug_sched.argtypes = [i32, i32, i32, i32, C.POINTER(C.c_int32)]
     lib.b200_debug_tma_tiles.restype = C.c_int64
     lib.b200_debug_tma_tiles.argtypes = [i32]
     lib.b200_debug_extend_tma_tiles.restype = C.c_int64

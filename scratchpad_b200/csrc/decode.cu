@@ -135,10 +135,10 @@ __device__ __forceinline__ DynParams runs_dyn(DynParams dyn, int probed, int run
   if (!(probed > 0 && 2 * runs >= probed)) dyn.min_base = 1 << 30;
   return dyn;
 }
-__device__ __forceinline__ int sched_chunk_begin(int c, int grid, int s_tiles, int d_tiles) {
+__host__ __device__ __forceinline__ int sched_chunk_begin(int c, int grid, int s_tiles, int d_tiles) {
   return c < grid ? c * s_tiles : grid * s_tiles + (c - grid) * d_tiles;
 }
-__device__ __forceinline__ int sched_chunk_of(int t, int dyn0, int grid, int s_tiles, int d_tiles) {
+__host__ __device__ __forceinline__ int sched_chunk_of(int t, int dyn0, int grid, int s_tiles, int d_tiles) {
   return t < dyn0 ? t / s_tiles : grid + (t - dyn0) / d_tiles;
 }
 constexpr int kExtraCasTiles = 4;    // row tiles beyond ceil(bs / requests-per-tile): room for that many more prefix groups
@@ -1779,6 +1779,27 @@ int b200_debug_dec_trace_read(unsigned long long* host_dst) {
 #endif
 
 int b200_debug_last_tma_mode(void) { return g_last_tma_mode; }
+
+// Test hook (host only, no device needed): the tile schedule b200_attn_plan would write for `total` tiles on a persistent
+// grid of `grid` CTAs when the slots are runs -- out[0..5] = tiles per static chunk, tiles per dynamic chunk, first dynamic
+// tile, number of chunks, capacity of the workspace's chunk tables, and, for the tile `probe`, the chunk that owns it;
+// out[6], out[7] = first tile of that chunk and of the next one.
+int b200_debug_sched(int32_t total, int32_t grid, int32_t min_base, int32_t probe, int32_t* out) {
+  if (!out || total < 0 || grid <= 0) return B200_ERR_INVALID;
+  DynParams dyn = dyn_params();
+  if (min_base > 0) dyn.min_base = min_base;
+  const Sched sc = make_sched(total, grid, dyn);
+  out[0] = sc.s_tiles;
+  out[1] = sc.d_tiles;
+  out[2] = sc.dyn0;
+  out[3] = sc.nch;
+  out[4] = max_chunks(grid);
+  const int c = (probe >= 0 && probe < total) ? sched_chunk_of(probe, sc.dyn0, grid, sc.s_tiles, sc.d_tiles) : -1;
+  out[5] = c;
+  out[6] = c >= 0 ? sched_chunk_begin(c, grid, sc.s_tiles, sc.d_tiles) : -1;
+  out[7] = c >= 0 ? sched_chunk_begin(c + 1, grid, sc.s_tiles, sc.d_tiles) : -1;
+  return B200_OK;
+}
 
 // Test hook: tiles per CTA from which b200_attn_plan cuts the last eighth of the tiles into dynamically claimed chunks
 // (<= 0 restores the default, kDynMinBase); returns the previous value.  Plans made afterwards use it.
